@@ -1,0 +1,172 @@
+/*
+ * lmpc_b200.h -- C ABI of the B200-native batched LMPC solve (liblmpc_b200.so).
+ *
+ * Drop-in boundary for the per-tick solve of MPC-Berkeley/Racing-LMPC-ROS2.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference's src/):
+ *
+ *   lmpc_create / lmpc_destroy          RacingMPC::RacingMPC(config, model, full_dynamics=false)
+ *                                       mpc/racing_mpc/include/racing_mpc/racing_mpc.hpp:46-49,
+ *                                       vehicle_model_factory.cpp:31-50 ("single_track_planar_model")
+ *   lmpc_solve_batch                    RacingMPC::solve(in, out, stats)   racing_mpc.hpp:52,
+ *                                       racing_mpc.cpp:209-372  (B independent ticks per call)
+ *   lmpc_linearise_batch                BaseVehicleModel::discrete_dynamics_jacobian() {x,u,k,dt}->{A,B,g}
+ *                                       single_track_planar_model.cpp:377-387
+ *   lmpc_discrete_dynamics_batch        BaseVehicleModel::discrete_dynamics() {x,u,k,dt}->{xip1}
+ *                                       single_track_planar_model.cpp:370-375
+ *   lmpc_safe_set_add_lap               SafeSetManager::add_lap(x,u,k,t,total_length)   safe_set.hpp:119-121
+ *   lmpc_safe_set_load                  SafeSetRecorder::load(from_files,total_length)  safe_set.cpp:260-276
+ *   lmpc_safe_set_query_batch           SafeSetManager::query(const SSQuery&) -> SSResult  safe_set.cpp:153-180
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; functions return an lmpc_status code
+ *     and never throw across the ABI.
+ *   - every array is fp64, instance-major: element [b] of a batch is the reference's dense
+ *     column-major casadi::DM for that tick (X_ref[b] = 6 x N column-major = N rows of 6).
+ *   - `memspace` says where the caller's buffers live.  LMPC_MEM_HOST buffers are staged through
+ *     pinned memory owned by the handle (H2D, kernels, D2H, then a stream synchronise);
+ *     LMPC_MEM_DEVICE buffers are used in place, work is enqueued on the handle's stream and the
+ *     call returns without synchronising.
+ *   - a handle is thread-compatible, not thread-safe (same contract as RacingMPC::solve, which
+ *     the node serialises under a mutex, racing_mpc_node.cpp:158).
+ *   - there is NO CPU fallback: without a CUDA device lmpc_create returns LMPC_ERR_NO_DEVICE.
+ */
+#ifndef LMPC_B200_H_
+#define LMPC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMPC_NX 6
+#define LMPC_NU 2
+#define LMPC_MAX_N 64         /* horizon cap of the kernels (N is a runtime parameter below it) */
+#define LMPC_MAX_SS_PTS 128   /* num_ss_pts cap */
+
+/* Per-call / per-handle error codes. */
+enum lmpc_status {
+  LMPC_OK = 0,
+  LMPC_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  LMPC_ERR_NO_DEVICE = -2,    /* no CUDA device or driver */
+  LMPC_ERR_CUDA = -3,         /* CUDA runtime error (see lmpc_last_error) */
+  LMPC_ERR_ALLOC = -4,
+  LMPC_ERR_IO = -5,           /* safe-set file missing / malformed */
+  LMPC_ERR_CAPACITY = -6      /* batch larger than max_batch */
+};
+
+/* Per-instance solve status (lmpc_batch_out.status).  The reference signals failure by omitting
+ * "X_optm" from the output dict (racing_mpc.cpp:358-371); here a failed instance gets a code and
+ * never poisons the batch. */
+enum lmpc_instance_status {
+  LMPC_SOLVED = 0,
+  LMPC_MAX_ITER = 1,
+  LMPC_INFEASIBLE_IC = 2,     /* x_ic violates the hard box on x_0 (racing_mpc.cpp:147,199-201) */
+  LMPC_NO_SAFE_SET = 3,       /* learning mode with an empty safe set */
+  LMPC_NUMERIC = 4            /* factorisation broke down before convergence */
+};
+
+enum lmpc_memspace { LMPC_MEM_HOST = 0, LMPC_MEM_DEVICE = 1 };
+
+/* SingleTrackPlanarModel constants (BaseVehicleModelConfig + SingleTrackPlanarModelConfig,
+ * base_vehicle_model_config.hpp:30-153, single_track_planar_model.hpp:31-43).  Only
+ * simplify_lon_control=true / use_frenet=true is supported (what every launch file ships). */
+typedef struct lmpc_vehicle_params {
+  double mass, moi, wheel_base, cg_ratio, cg_height, fr, chassis_b;
+  double kd;                 /* powertrain.kd */
+  double kb;                 /* front_brake.bias */
+  double air_density, frontal_area, drag_coeff, cl_f, cl_r;
+  double mu;
+  double Bf, Cf, Br, Cr;     /* pacejka_b / pacejka_c front, rear */
+  double Fd_max, Fb_max, Td, Tb;
+  double max_steer, max_steer_rate;
+  int32_t integrator;        /* 0 = rk4, 1 = euler (base_vehicle_model IntegratorType) */
+  int32_t pad_;
+} lmpc_vehicle_params;
+
+/* RacingMPCConfig (racing_mpc_config.hpp:37-82) -- the fields the QP reads, plus the
+ * interior-point options of this implementation (max_iter, tol). */
+typedef struct lmpc_mpc_config {
+  int32_t N;                 /* horizon (states x_0..x_{N-1}) */
+  int32_t learning;          /* 1 = LMPC cost + safe-set terminal set, 0 = tracking cost */
+  double margin;
+  double q_contour, q_heading, q_vel, q_vy, q_vyaw, q_boundary;
+  double R[4], R_d[4];
+  double x_max[6], x_min[6], u_max[2], u_min[2];   /* +-INFINITY (or |v| >= 1e19) = unbounded */
+  double convex_hull_slack[6];
+  int32_t num_ss_pts, num_ss_pts_per_lap, max_lap_stored;
+  int32_t max_iter;          /* IPM iteration cap (default 40 when <= 0) */
+  double tol;                /* IPM tolerance on mu / residuals (default 1e-12 when <= 0) */
+} lmpc_mpc_config;
+
+typedef struct lmpc_handle lmpc_handle;
+
+/* Inputs of B ticks: the keys RacingMPC::solve reads (racing_mpc.cpp:215-228). */
+typedef struct lmpc_batch_in {
+  const double* x_ic;          /* [B][6] */
+  const double* u_ic;          /* [B][2] */
+  const double* X_ref;         /* [B][N][6]   linearisation states (abscissa aligned inside) */
+  const double* U_ref;         /* [B][N-1][2] linearisation controls */
+  const double* T_ref;         /* [B][N-1]    "T_ref"/"T_optm_ref" */
+  const double* bound_left;    /* [B][N] */
+  const double* bound_right;   /* [B][N] */
+  const double* curvatures;    /* [B][N] */
+  const double* vel_ref;       /* [B][N] */
+  const double* total_length;  /* [B] */
+  const double* U_warm;        /* [B][N-1][2] optional "U_optm_ref" start; NULL => U_ref */
+} lmpc_batch_in;
+
+/* Outputs: the keys RacingMPC::solve writes (racing_mpc.cpp:256-257,347-352) plus cost/status.
+ * Any pointer may be NULL to skip that output. */
+typedef struct lmpc_batch_out {
+  double* X_optm;              /* [B][N][6] */
+  double* U_optm;              /* [B][N-1][2] */
+  double* dU_optm;             /* [B][N-1][2] */
+  double* convex_combi_optm;   /* [B][num_ss_pts]   (learning) */
+  double* ss_x;                /* [B][num_ss_pts][6] safe-set columns used by the QP (padded) */
+  double* ss_j;                /* [B][num_ss_pts]    their cost-to-go J - J[0] */
+  double* cost;                /* [B] objective value (the reference never returns it) */
+  int32_t* status;             /* [B] lmpc_instance_status */
+  int32_t* iters;              /* [B] interior-point iterations (stats["iter_count"]) */
+} lmpc_batch_out;
+
+int lmpc_version(void);
+const char* lmpc_status_string(int status);
+
+int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_params* vehicle, int device_ordinal,
+                int max_batch, lmpc_handle** out);
+int lmpc_destroy(lmpc_handle* h);
+/* cudaStream_t to enqueue on (NULL = the legacy default stream). */
+int lmpc_set_stream(lmpc_handle* h, void* cuda_stream);
+const char* lmpc_last_error(const lmpc_handle* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches evidence) */
+int64_t lmpc_launch_count(const lmpc_handle* h);
+
+/* ---- safe set (host-side ingestion, device-resident slab) ---- */
+int lmpc_safe_set_add_lap(lmpc_handle* h, int n, const double* x /*[n][6]*/, const double* u /*[n][2]*/,
+                          const double* k /*[n]*/, const double* t /*[n]*/, double total_length);
+int lmpc_safe_set_load(lmpc_handle* h, const char* file_prefix, double total_length);
+int lmpc_safe_set_clear(lmpc_handle* h);
+int lmpc_safe_set_num_laps(const lmpc_handle* h);
+/* k-NN query of B points (s, e_y).  ss_x [B][max_total][6], ss_j [B][max_total] (raw J), count [B].
+ * Columns beyond count[b] are left untouched. */
+int lmpc_safe_set_query_batch(lmpc_handle* h, int B, const double* query_s_ey /*[B][2]*/, int max_total,
+                              int max_per_lap, double* ss_x, double* ss_j, int32_t* count, int memspace);
+
+/* ---- vehicle model ---- */
+int lmpc_discrete_dynamics_batch(lmpc_handle* h, int n, const double* x, const double* u,
+                                 const double* kappa, const double* dt, double* x_next, int memspace);
+/* A [n][36] and B [n][12] column-major per item, g [n][6]; x_next may be NULL. */
+int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa,
+                         const double* dt, double* A, double* Bm, double* g, double* x_next, int memspace);
+
+/* ---- the hot path: B independent MPC ticks ---- */
+int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out,
+                     int memspace);
+/* Blocks until everything enqueued on the handle's stream has finished. */
+int lmpc_synchronize(lmpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMPC_B200_H_ */

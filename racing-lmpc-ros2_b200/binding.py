@@ -1,0 +1,110 @@
+"""ctypes mirror of include/lmpc_b200.h (PODs + function prototypes) and the library loader.
+
+The CUDA library is built in-tree (csrc/liblmpc_b200.so, see build.py).  Loading it never touches
+the GPU; every compute entry point needs one (lmpc_create returns LMPC_ERR_NO_DEVICE otherwise).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblmpc_b200.so")
+
+LMPC_MEM_HOST, LMPC_MEM_DEVICE = 0, 1
+STATUS_NAMES = {0: "SOLVED", 1: "MAX_ITER", 2: "INFEASIBLE_IC", 3: "NO_SAFE_SET", 4: "NUMERIC"}
+
+
+class VehicleParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "mass", "moi", "wheel_base", "cg_ratio", "cg_height", "fr", "chassis_b", "kd", "kb",
+        "air_density", "frontal_area", "drag_coeff", "cl_f", "cl_r", "mu", "Bf", "Cf", "Br", "Cr",
+        "Fd_max", "Fb_max", "Td", "Tb", "max_steer", "max_steer_rate")] + [
+        ("integrator", C.c_int32), ("pad_", C.c_int32)]
+
+
+class MpcConfig(C.Structure):
+    _fields_ = [("N", C.c_int32), ("learning", C.c_int32), ("margin", C.c_double),
+                ("q_contour", C.c_double), ("q_heading", C.c_double), ("q_vel", C.c_double),
+                ("q_vy", C.c_double), ("q_vyaw", C.c_double), ("q_boundary", C.c_double),
+                ("R", C.c_double * 4), ("R_d", C.c_double * 4),
+                ("x_max", C.c_double * 6), ("x_min", C.c_double * 6),
+                ("u_max", C.c_double * 2), ("u_min", C.c_double * 2),
+                ("convex_hull_slack", C.c_double * 6),
+                ("num_ss_pts", C.c_int32), ("num_ss_pts_per_lap", C.c_int32),
+                ("max_lap_stored", C.c_int32), ("max_iter", C.c_int32), ("tol", C.c_double)]
+
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int32)
+
+
+class BatchIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "x_ic", "u_ic", "X_ref", "U_ref", "T_ref", "bound_left", "bound_right", "curvatures",
+        "vel_ref", "total_length", "U_warm")]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost", "status", "iters")]
+
+
+def fill_struct(st, d):
+    for name, _ in st._fields_:
+        if name not in d:
+            continue
+        cur = getattr(st, name)
+        if hasattr(cur, "__len__"):
+            arr = np.asarray(d[name], dtype=np.float64).ravel()
+            for i in range(len(cur)):
+                cur[i] = float(arr[i])
+        else:
+            setattr(st, name, d[name])
+    return st
+
+
+EXPORTS = [
+    "lmpc_version", "lmpc_status_string", "lmpc_create", "lmpc_destroy", "lmpc_set_stream",
+    "lmpc_last_error", "lmpc_launch_count", "lmpc_safe_set_add_lap", "lmpc_safe_set_load",
+    "lmpc_safe_set_clear", "lmpc_safe_set_num_laps", "lmpc_safe_set_query_batch",
+    "lmpc_discrete_dynamics_batch", "lmpc_linearise_batch", "lmpc_solve_batch", "lmpc_synchronize",
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} is missing: the CUDA library is not built (run `python -c 'import __graft_entry__ as g; "
+            "g.build()'`).  There is no CPU fallback for the solve path.")
+    L = C.CDLL(p)
+    vp = C.c_void_p
+    L.lmpc_version.restype = C.c_int
+    L.lmpc_status_string.restype = C.c_char_p
+    L.lmpc_status_string.argtypes = [C.c_int]
+    L.lmpc_create.argtypes = [C.POINTER(MpcConfig), C.POINTER(VehicleParams), C.c_int, C.c_int, C.POINTER(vp)]
+    L.lmpc_destroy.argtypes = [vp]
+    L.lmpc_set_stream.argtypes = [vp, vp]
+    L.lmpc_last_error.restype = C.c_char_p
+    L.lmpc_last_error.argtypes = [vp]
+    L.lmpc_launch_count.restype = C.c_int64
+    L.lmpc_launch_count.argtypes = [vp]
+    L.lmpc_safe_set_add_lap.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_double]
+    L.lmpc_safe_set_load.argtypes = [vp, C.c_char_p, C.c_double]
+    L.lmpc_safe_set_clear.argtypes = [vp]
+    L.lmpc_safe_set_num_laps.argtypes = [vp]
+    L.lmpc_safe_set_query_batch.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+    L.lmpc_discrete_dynamics_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+    L.lmpc_linearise_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.lmpc_solve_batch.argtypes = [vp, C.c_int, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_int]
+    L.lmpc_synchronize.argtypes = [vp]
+    if path is None:
+        _lib = L
+    return L

@@ -1,0 +1,451 @@
+// lmpc_capi.cu -- implementation of the C ABI declared in include/lmpc_b200.h.
+//
+// Host side of the drop-in boundary: owns the device workspace, the device-resident safe-set slab
+// (host-side ingestion mirrors SafeSetManager::add_lap / SafeSetRecorder::load, reference
+// safe_set.cpp:116-151,260-276) and launches the three kernels of lmpc_kernels.cuh on the handle's
+// stream.  No CPU compute path exists: every entry point needs the CUDA device.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lmpc_b200.h"
+#include "lmpc_host_params.h"
+#include "lmpc_kernels.cuh"
+
+namespace {
+
+struct HostLap {
+  int n;
+  std::vector<double> ps, pe, xr, J;
+  std::vector<int> canon;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct lmpc_handle {
+  lmpc_mpc_config cfg;
+  lmpc_vehicle_params veh;
+  LmpcQpParams P;
+  LmpcModel M;
+  int device = 0;
+  int max_batch = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // safe set: circular buffer, oldest first (boost::circular_buffer semantics, safe_set.cpp:139-151)
+  std::vector<HostLap> laps;
+  DevBuf slab;
+  std::vector<LmpcLapView> dev_laps;   // newest first, device pointers into the slab
+  // device workspace
+  DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj;
+  // device staging for host-memory callers
+  DevBuf st_in, st_out;
+  size_t qp_smem = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return LMPC_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+
+static int dev_reserve(lmpc_handle* h, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes) return LMPC_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  if (cudaMalloc(&b.p, bytes) != cudaSuccess) { h->err = "cudaMalloc failed"; return LMPC_ERR_ALLOC; }
+  b.bytes = bytes;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_version(void) { return 100; }
+
+extern "C" const char* lmpc_status_string(int s) {
+  switch (s) {
+    case LMPC_OK: return "ok";
+    case LMPC_ERR_INVALID: return "invalid argument or unsupported configuration";
+    case LMPC_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case LMPC_ERR_CUDA: return "CUDA runtime error";
+    case LMPC_ERR_ALLOC: return "allocation failed";
+    case LMPC_ERR_IO: return "safe-set file missing or malformed";
+    case LMPC_ERR_CAPACITY: return "batch exceeds max_batch";
+    default: return "unknown";
+  }
+}
+
+extern "C" const char* lmpc_last_error(const lmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t lmpc_launch_count(const lmpc_handle* h) { return h ? h->launches : 0; }
+
+template <int KPL>
+static int set_qp_attr(lmpc_handle* h) {
+  CK(cudaFuncSetAttribute(lmpc_qp_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem));
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_params* vehicle, int device_ordinal,
+                           int max_batch, lmpc_handle** out) {
+  if (!config || !vehicle || !out || max_batch < 1) return LMPC_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return LMPC_ERR_NO_DEVICE;
+  if (device_ordinal < 0 || device_ordinal >= ndev) return LMPC_ERR_INVALID;
+  if (vehicle->integrator != 0 && vehicle->integrator != 1) return LMPC_ERR_INVALID;
+  lmpc_handle* h = new lmpc_handle();
+  h->cfg = *config; h->veh = *vehicle; h->device = device_ordinal; h->max_batch = max_batch;
+  int rc = lmpc_make_qp_params(*config, *vehicle, &h->P);
+  if (rc != LMPC_OK) { delete h; return rc; }
+  h->M = lmpc_make_model(*vehicle);
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return LMPC_ERR_NO_DEVICE; }
+  h->qp_smem = sizeof(double) * (size_t)(h->P.total + (h->P.learning ? h->P.K : 0));
+  const int kpl = (h->P.K + 31) / 32;
+  if (kpl <= 1) rc = set_qp_attr<1>(h); else if (kpl == 2) rc = set_qp_attr<2>(h); else if (kpl == 3) rc = set_qp_attr<3>(h); else rc = set_qp_attr<4>(h);
+  if (rc != LMPC_OK) { fprintf(stderr, "lmpc_create: %s\n", h->err.c_str()); delete h; return rc; }
+  const size_t B = (size_t)max_batch, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)std::max(h->P.K, 1);
+  rc = dev_reserve(h, h->ws_abg, sizeof(double) * 54 * NS * B);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_cen, sizeof(double) * 6 * B);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_ssx, sizeof(double) * 6 * K * B);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_ssj, sizeof(double) * K * B);
+  (void)N;
+  if (rc != LMPC_OK) { lmpc_destroy(h); return rc; }
+  *out = h;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_destroy(lmpc_handle* h) {
+  if (!h) return LMPC_ERR_INVALID;
+  cudaSetDevice(h->device);
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->st_in, &h->st_out})
+    if (b->p) cudaFree(b->p);
+  delete h;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_set_stream(lmpc_handle* h, void* s) {
+  if (!h) return LMPC_ERR_INVALID;
+  h->stream = (cudaStream_t)s;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_synchronize(lmpc_handle* h) {
+  if (!h) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return LMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ safe set
+static int upload_safe_set(lmpc_handle* h) {
+  CK(cudaSetDevice(h->device));
+  h->dev_laps.clear();
+  size_t total_pts = 0;
+  for (const HostLap& l : h->laps) total_pts += 3 * (size_t)l.n;
+  if (total_pts == 0) return LMPC_OK;
+  // slab layout per point set: ps | pe | J | xr[6] (doubles) then canon (ints); one allocation
+  const size_t dbl = total_pts * 9, ints = total_pts;
+  const size_t bytes = dbl * sizeof(double) + ints * sizeof(int);
+  // a new slab every time: kernels already enqueued on the stream may still read the old one
+  CK(cudaStreamSynchronize(h->stream));
+  int rc = dev_reserve(h, h->slab, bytes);
+  if (rc != LMPC_OK) return rc;
+  std::vector<double> hd(dbl);
+  std::vector<int> hi(ints);
+  double* dbase = (double*)h->slab.p;
+  int* ibase = (int*)((char*)h->slab.p + dbl * sizeof(double));
+  size_t od = 0, oi = 0;
+  std::vector<LmpcLapView> views(h->laps.size());
+  for (size_t li = 0; li < h->laps.size(); li++) {
+    const HostLap& l = h->laps[li];
+    const size_t m = 3 * (size_t)l.n;
+    LmpcLapView v;
+    std::memcpy(&hd[od], l.ps.data(), m * sizeof(double)); v.ps = dbase + od; od += m;
+    std::memcpy(&hd[od], l.pe.data(), m * sizeof(double)); v.pe = dbase + od; od += m;
+    std::memcpy(&hd[od], l.J.data(), m * sizeof(double)); v.J = dbase + od; od += m;
+    std::memcpy(&hd[od], l.xr.data(), 6 * m * sizeof(double)); v.xr = dbase + od; od += 6 * m;
+    std::memcpy(&hi[oi], l.canon.data(), m * sizeof(int)); v.canon = ibase + oi; oi += m;
+    v.m = (int)m; v.take = 0; v.out_off = 0;
+    views[li] = v;
+  }
+  CK(cudaMemcpyAsync(dbase, hd.data(), dbl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(ibase, hi.data(), ints * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));   // hd / hi are stack-scoped
+  for (size_t li = h->laps.size(); li-- > 0;) h->dev_laps.push_back(views[li]);   // newest first
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_safe_set_add_lap(lmpc_handle* h, int n, const double* x, const double* u, const double* k,
+                                     const double* t, double L) {
+  (void)u; (void)k; (void)t;   // kept for signature parity; only the (uncalled) regression query reads them
+  if (!h || n < 1 || !x) return LMPC_ERR_INVALID;
+  HostLap lap;
+  lap.n = n;
+  const size_t m = 3 * (size_t)n;
+  lap.ps.resize(m); lap.pe.resize(m); lap.J.resize(m); lap.xr.resize(6 * m); lap.canon.resize(m);
+  // SSTrajectory::process_lap_data (safe_set.cpp:116-137): x_repeat = [x - L e0, x, x + L e0],
+  // J = [J + n - 1, J, J - n + 1] with J_j = n - 1 - j
+  for (int rep = 0; rep < 3; rep++)
+    for (int j = 0; j < n; j++) {
+      const size_t q = (size_t)rep * n + j;
+      for (int c = 0; c < 6; c++) lap.xr[6 * q + c] = x[6 * (size_t)j + c];
+      lap.xr[6 * q] += (rep - 1) * L;
+      lap.ps[q] = lap.xr[6 * q]; lap.pe[q] = lap.xr[6 * q + 1];
+      lap.J[q] = (double)(n - 1 - j) + (1 - rep) * (double)(n - 1);
+    }
+  // exact-duplicate keys resolve to the first inserted index (trajectory_kd_tree.cpp:38)
+  std::vector<int> order(m);
+  for (size_t i = 0; i < m; i++) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (lap.ps[a] != lap.ps[b]) return lap.ps[a] < lap.ps[b];
+    if (lap.pe[a] != lap.pe[b]) return lap.pe[a] < lap.pe[b];
+    return a < b;
+  });
+  for (size_t i = 0; i < m;) {
+    size_t j = i;
+    while (j < m && lap.ps[order[j]] == lap.ps[order[i]] && lap.pe[order[j]] == lap.pe[order[i]]) { lap.canon[order[j]] = order[i]; j++; }
+    i = j;
+  }
+  const size_t cap = (size_t)std::max(h->cfg.max_lap_stored, 1);
+  if (h->laps.size() == cap) h->laps.erase(h->laps.begin());   // circular_buffer::push_back overwrites the oldest
+  h->laps.push_back(std::move(lap));
+  return upload_safe_set(h);
+}
+
+static bool read_matrix(const std::string& path, int cols, std::vector<double>& out, int& rows) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return false;
+  out.clear();
+  double v;
+  while (fscanf(f, "%lf", &v) == 1) out.push_back(v);
+  fclose(f);
+  if (out.empty() || out.size() % (size_t)cols) return false;
+  rows = (int)(out.size() / (size_t)cols);
+  return true;
+}
+
+extern "C" int lmpc_safe_set_load(lmpc_handle* h, const char* prefix, double L) {
+  if (!h || !prefix) return LMPC_ERR_INVALID;
+  std::vector<double> x, u, k, t;
+  int nx = 0, nu = 0, nk = 0, nt = 0;
+  const std::string p(prefix);
+  if (!read_matrix(p + "_x.txt", 6, x, nx) || !read_matrix(p + "_u.txt", 2, u, nu) ||
+      !read_matrix(p + "_k.txt", 1, k, nk) || !read_matrix(p + "_t.txt", 1, t, nt) || nx != nu || nx != nk || nx != nt) {
+    h->err = "cannot load lap " + p;
+    return LMPC_ERR_IO;
+  }
+  return lmpc_safe_set_add_lap(h, nx, x.data(), u.data(), k.data(), t.data(), L);
+}
+
+extern "C" int lmpc_safe_set_clear(lmpc_handle* h) {
+  if (!h) return LMPC_ERR_INVALID;
+  h->laps.clear();
+  h->dev_laps.clear();
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_safe_set_num_laps(const lmpc_handle* h) { return h ? (int)h->laps.size() : 0; }
+
+// newest -> oldest while num_total < max_total (safe_set.cpp:164); the columns a lap contributes and
+// where they land do not depend on the query
+static void make_lap_table(const lmpc_handle* h, int max_total, int per_lap, LmpcLapTable* tab) {
+  tab->n_used = 0; tab->count = 0;
+  int total = 0;
+  for (size_t j = 0; j < h->dev_laps.size() && total < max_total && tab->n_used < LMPC_MAX_LAPS_USED; j++) {
+    LmpcLapView v = h->dev_laps[j];
+    v.take = std::min(per_lap, v.m);
+    v.out_off = total;
+    total += v.take;
+    tab->lap[tab->n_used++] = v;
+  }
+  tab->count = std::min(total, max_total);
+}
+
+static int launch_ss_query(lmpc_handle* h, const LmpcLapTable& tab, int B, const double* d_query, int qstride,
+                           int max_total, int pad_to, double* d_ssx, double* d_ssj) {
+  if (tab.n_used == 0) return LMPC_OK;
+  const int warps = B * tab.n_used, threads = 128;
+  const int blocks = (warps * 32 + threads - 1) / threads;
+  lmpc_ss_query_kernel<<<blocks, threads, 0, h->stream>>>(tab, B, d_query, qstride, max_total, pad_to, d_ssx, d_ssj);
+  h->launches++;
+  CK(cudaGetLastError());
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_safe_set_query_batch(lmpc_handle* h, int B, const double* query, int max_total, int max_per_lap,
+                                         double* ss_x, double* ss_j, int32_t* count, int memspace) {
+  if (!h || B < 1 || !query || !ss_x || !ss_j || max_total < 1 || max_per_lap < 1) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  LmpcLapTable tab;
+  make_lap_table(h, max_total, max_per_lap, &tab);
+  const size_t nq = 2 * (size_t)B, nx = 6 * (size_t)max_total * B, nj = (size_t)max_total * B;
+  const double* dq = query; double* dx = ss_x; double* dj = ss_j;
+  if (memspace == LMPC_MEM_HOST) {
+    int rc = dev_reserve(h, h->st_in, sizeof(double) * nq);
+    if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * (nx + nj));
+    if (rc != LMPC_OK) return rc;
+    CK(cudaMemcpyAsync(h->st_in.p, query, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream));
+    dq = (const double*)h->st_in.p; dx = (double*)h->st_out.p; dj = dx + nx;
+  }
+  // pad_to == count: no padding in the raw query (SafeSetManager::query returns `count` columns)
+  int rc = launch_ss_query(h, tab, B, dq, 2, max_total, max_total, dx, dj);
+  if (rc != LMPC_OK) return rc;
+  if (memspace == LMPC_MEM_HOST) {
+    CK(cudaMemcpyAsync(ss_x, dx, sizeof(double) * nx, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ss_j, dj, sizeof(double) * nj, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (count) for (int b = 0; b < B; b++) count[b] = tab.count;
+  } else if (count) {
+    std::vector<int32_t> hc((size_t)B, tab.count);
+    CK(cudaMemcpyAsync(count, hc.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ model
+static int model_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa, const double* dt,
+                       double* A, double* Bm, double* g, double* xnext, int memspace, bool jac) {
+  if (!h || n < 1 || !x || !u || !kappa || !dt) return LMPC_ERR_INVALID;
+  if (jac && (!A || !Bm || !g)) return LMPC_ERR_INVALID;
+  if (!jac && !xnext) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t nn = (size_t)n;
+  const double *dx = x, *du = u, *dk = kappa, *dd = dt;
+  double *dA = A, *dB = Bm, *dg = g, *dxn = xnext;
+  if (memspace == LMPC_MEM_HOST) {
+    int rc = dev_reserve(h, h->st_in, sizeof(double) * nn * 10);
+    if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * nn * 60);
+    if (rc != LMPC_OK) return rc;
+    double* si = (double*)h->st_in.p;
+    CK(cudaMemcpyAsync(si, x, sizeof(double) * 6 * nn, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(si + 6 * nn, u, sizeof(double) * 2 * nn, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(si + 8 * nn, kappa, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(si + 9 * nn, dt, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
+    dx = si; du = si + 6 * nn; dk = si + 8 * nn; dd = si + 9 * nn;
+    double* so = (double*)h->st_out.p;
+    dA = so; dB = so + 36 * nn; dg = so + 48 * nn; dxn = so + 54 * nn;
+  }
+  const int threads = 64, blocks = (n + threads - 1) / threads;
+  if (jac) lmpc_linearise_items_kernel<<<blocks, threads, 0, h->stream>>>(h->M, n, dx, du, dk, dd, dA, dB, dg, (xnext || memspace == LMPC_MEM_HOST) ? dxn : nullptr);
+  else lmpc_step_items_kernel<<<blocks, threads, 0, h->stream>>>(h->M, n, dx, du, dk, dd, dxn);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (memspace == LMPC_MEM_HOST) {
+    if (jac) {
+      CK(cudaMemcpyAsync(A, dA, sizeof(double) * 36 * nn, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(Bm, dB, sizeof(double) * 12 * nn, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(g, dg, sizeof(double) * 6 * nn, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (xnext) CK(cudaMemcpyAsync(xnext, dxn, sizeof(double) * 6 * nn, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_discrete_dynamics_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa,
+                                            const double* dt, double* x_next, int memspace) {
+  return model_batch(h, n, x, u, kappa, dt, nullptr, nullptr, nullptr, x_next, memspace, false);
+}
+
+extern "C" int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa,
+                                    const double* dt, double* A, double* Bm, double* g, double* x_next, int memspace) {
+  return model_batch(h, n, x, u, kappa, dt, A, Bm, g, x_next, memspace, true);
+}
+
+// ------------------------------------------------------------------------------------------ solve
+template <int KPL>
+static void launch_qp(lmpc_handle* h, const LmpcQpBatch& a) {
+  lmpc_qp_kernel<KPL><<<a.B, 32, h->qp_smem, h->stream>>>(h->P, a);
+}
+
+extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int memspace) {
+  if (!h || !in || !out || B < 1) return LMPC_ERR_INVALID;
+  if (B > h->max_batch) return LMPC_ERR_CAPACITY;
+  if (!in->x_ic || !in->u_ic || !in->X_ref || !in->U_ref || !in->T_ref || !in->bound_left || !in->bound_right ||
+      !in->curvatures || !in->vel_ref || !in->total_length)
+    return LMPC_ERR_INVALID;
+  if (!out->X_optm || !out->U_optm || !out->dU_optm || !out->status || !out->iters) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t Bz = (size_t)B, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)h->P.K;
+  const bool learn = h->P.learning != 0;
+  // element counts of the 11 inputs and 9 outputs, in struct order
+  const size_t nin[11] = {6 * Bz, 2 * Bz, 6 * N * Bz, 2 * NS * Bz, NS * Bz, N * Bz, N * Bz, N * Bz, N * Bz, Bz, 2 * NS * Bz};
+  const double* hin[11] = {in->x_ic, in->u_ic, in->X_ref, in->U_ref, in->T_ref, in->bound_left, in->bound_right,
+                           in->curvatures, in->vel_ref, in->total_length, in->U_warm};
+  const double* din[11];
+  const size_t nout_d[7] = {6 * N * Bz, 2 * NS * Bz, 2 * NS * Bz, K * Bz, 6 * K * Bz, K * Bz, Bz};
+  double* hout_d[7] = {out->X_optm, out->U_optm, out->dU_optm, out->convex_combi_optm, out->ss_x, out->ss_j, out->cost};
+  double* dout_d[7];
+  int32_t *d_status = out->status, *d_iters = out->iters;
+  if (memspace == LMPC_MEM_HOST) {
+    size_t tin = 0, tout = 0;
+    for (int k = 0; k < 11; k++) tin += nin[k];
+    for (int k = 0; k < 7; k++) tout += nout_d[k];
+    int rc = dev_reserve(h, h->st_in, sizeof(double) * tin);
+    if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * tout + 2 * sizeof(int32_t) * Bz);
+    if (rc != LMPC_OK) return rc;
+    double* p = (double*)h->st_in.p;
+    for (int k = 0; k < 11; k++) {
+      if (hin[k]) { CK(cudaMemcpyAsync(p, hin[k], sizeof(double) * nin[k], cudaMemcpyHostToDevice, h->stream)); din[k] = p; }
+      else din[k] = nullptr;
+      p += nin[k];
+    }
+    double* q = (double*)h->st_out.p;
+    for (int k = 0; k < 7; k++) { dout_d[k] = q; q += nout_d[k]; }
+    d_status = (int32_t*)q; d_iters = d_status + Bz;
+  } else {
+    for (int k = 0; k < 11; k++) din[k] = hin[k];
+    for (int k = 0; k < 7; k++) dout_d[k] = hout_d[k];
+  }
+  double* abg = (double*)h->ws_abg.p; double* cen = (double*)h->ws_cen.p;
+  // the safe-set columns go straight to the caller's ss_x / ss_j when given (device), else to the workspace
+  double* ssx = (memspace == LMPC_MEM_DEVICE && out->ss_x) ? out->ss_x : (memspace == LMPC_MEM_HOST ? dout_d[4] : (double*)h->ws_ssx.p);
+  double* ssj = (memspace == LMPC_MEM_DEVICE && out->ss_j) ? out->ss_j : (memspace == LMPC_MEM_HOST ? dout_d[5] : (double*)h->ws_ssj.p);
+
+  // K1: linearise
+  {
+    const int n = B * (int)NS, threads = 64, blocks = (n + threads - 1) / threads;
+    lmpc_linearise_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, din[0], din[2], din[3], din[4], din[7], din[9], abg, cen);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272)
+  LmpcLapTable tab;
+  tab.n_used = 0; tab.count = 0;
+  if (learn) {
+    make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
+    int rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, ssx, ssj);
+    if (rc != LMPC_OK) return rc;
+  }
+  // K3: QP
+  LmpcQpBatch a;
+  a.x_ic = din[0]; a.u_ic = din[1]; a.U0 = din[10] ? din[10] : din[3]; a.T_ref = din[4];
+  a.bl = din[5]; a.br = din[6]; a.vref = din[8]; a.ABg = abg; a.ssx = ssx; a.ssj = ssj; a.cen = cen;
+  a.X = dout_d[0]; a.U = dout_d[1]; a.dU = dout_d[2];
+  a.lam = (memspace == LMPC_MEM_HOST) ? (out->convex_combi_optm ? dout_d[3] : nullptr) : out->convex_combi_optm;
+  a.cost = (memspace == LMPC_MEM_HOST) ? (out->cost ? dout_d[6] : nullptr) : out->cost;
+  a.status = d_status; a.iters = d_iters; a.ss_count = tab.count; a.B = B;
+  const int kpl = (h->P.K + 31) / 32;
+  if (kpl <= 1) launch_qp<1>(h, a); else if (kpl == 2) launch_qp<2>(h, a); else if (kpl == 3) launch_qp<3>(h, a); else launch_qp<4>(h, a);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (memspace == LMPC_MEM_HOST) {
+    for (int k = 0; k < 7; k++) {
+      if (!hout_d[k]) continue;
+      if ((k == 3 || k == 4 || k == 5) && !learn) continue;
+      CK(cudaMemcpyAsync(hout_d[k], dout_d[k], sizeof(double) * nout_d[k], cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaMemcpyAsync(out->status, d_status, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out->iters, d_iters, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}

@@ -1,0 +1,88 @@
+// lmpc_host_params.h -- host-side conversion of the C-ABI PODs into the kernels' parameter blocks.
+#pragma once
+#include "../../include/lmpc_b200.h"
+#include "lmpc_model.cuh"
+
+static inline LmpcModel lmpc_make_model(const lmpc_vehicle_params& v) {
+  LmpcModel P;
+  P.m = v.mass; P.Jzz = v.moi; P.l = v.wheel_base;
+  P.lr = v.cg_ratio * v.wheel_base;            // single_track_planar_model.cpp:229
+  P.lf = v.wheel_base - P.lr;                  // :230
+  P.fr = v.fr; P.hcog = v.cg_height; P.kd = v.kd; P.kb = v.kb;
+  P.rho = v.air_density; P.Af = v.frontal_area; P.cd = v.drag_coeff; P.clf = v.cl_f; P.clr = v.cl_r;
+  P.mu = v.mu; P.Bf = v.Bf; P.Cf = v.Cf; P.Br = v.Br; P.Cr = v.Cr;
+  P.integrator = v.integrator;
+  return P;
+}
+
+#include <math.h>
+#include <string.h>
+#include "lmpc_qp_core.cuh"
+
+static inline bool lmpc_finite_bound(double b) { return isfinite(b) && fabs(b) < 1e19; }
+
+// Validates the configuration and fills the kernel parameter block (row structure, merged boxes,
+// shared-memory layout).  Returns LMPC_OK or LMPC_ERR_INVALID.
+static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehicle_params& v, LmpcQpParams* out) {
+  LmpcQpParams P;
+  memset(&P, 0, sizeof P);
+  if (c.N < 3 || c.N > LMPC_MAX_N) return LMPC_ERR_INVALID;
+  P.N = c.N; P.NS = c.N - 1;
+  P.learning = c.learning ? 1 : 0;
+  P.K = P.learning ? c.num_ss_pts : 0;
+  if (P.learning && (P.K < LMPC_MB || P.K > LMPC_MAX_SS_PTS || c.num_ss_pts_per_lap < 1)) return LMPC_ERR_INVALID;
+  P.soft = c.q_boundary > 0.0 ? 1 : 0;                                  // racing_mpc.cpp:528
+  double hs = 0.0;
+  for (int k = 0; k < 6; k++) hs += c.convex_hull_slack[k] * c.convex_hull_slack[k];
+  P.hull_slack = hs > 0.0 ? 1 : 0;                                      // racing_mpc.cpp:493
+  P.nh = 0;
+  if (P.learning)
+    for (int k = 0; k < 6; k++) {
+      if (P.hull_slack && c.convex_hull_slack[k] == 0.0) continue;      // free slack component: vacuous row
+      P.hidx[P.nh] = k;
+      P.Einv[P.nh] = P.hull_slack ? 1.0 / (2.0 * c.convex_hull_slack[k]) : 0.0;
+      P.nh++;
+    }
+  for (int k = 0; k < 6; k++) P.chs[k] = P.hull_slack ? c.convex_hull_slack[k] : 0.0;
+  P.nxb = 0;
+  for (int k = 0; k < 6; k++) {
+    if (lmpc_finite_bound(c.x_max[k])) { P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = 1.0; P.xb_h[P.nxb] = c.x_max[k]; P.nxb++; }
+    if (lmpc_finite_bound(c.x_min[k])) { P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = -1.0; P.xb_h[P.nxb] = -c.x_min[k]; P.nxb++; }
+  }
+  P.RS = P.nxb + 10;
+  // merged u box: RacingMPC primal bounds (racing_mpc.cpp:148) and the model's actuator rows
+  // (single_track_planar_model.cpp:114,120); rate box (:146-151)
+  const double alo[2] = {v.Fb_max / 1000.0, -v.max_steer}, ahi[2] = {v.Fd_max / 1000.0, v.max_steer};
+  for (int k = 0; k < 2; k++) { P.ulo[k] = fmax(c.u_min[k], alo[k]); P.uhi[k] = fmin(c.u_max[k], ahi[k]); }
+  P.dlo[0] = v.Fb_max / 1000.0 / v.Tb; P.dhi[0] = v.Fd_max / 1000.0 / v.Td;
+  P.dlo[1] = -v.max_steer_rate;        P.dhi[1] = v.max_steer_rate;
+  for (int k = 0; k < 2; k++) {
+    P.ub_act[2 * k] = lmpc_finite_bound(P.uhi[k]); P.ub_act[2 * k + 1] = lmpc_finite_bound(P.ulo[k]);
+    P.db_act[2 * k] = lmpc_finite_bound(P.dhi[k]); P.db_act[2 * k + 1] = lmpc_finite_bound(P.dlo[k]);
+    if (!(P.ulo[k] < P.uhi[k]) || !(P.dlo[k] < P.dhi[k])) return LMPC_ERR_INVALID;
+  }
+  P.margin = c.margin + v.chassis_b / 2.0;                              // racing_mpc.cpp:531
+  P.qb = c.q_boundary;
+  const double w[6] = {0.0, c.q_contour, c.q_heading, c.q_vel, c.q_vy, c.q_vyaw};   // racing_mpc.cpp:459-463
+  for (int k = 0; k < 6; k++) { P.qx[k] = w[k]; P.qxN[k] = (k >= 1 && k <= 3) ? 10.0 * w[k] : 0.0; }   // :473-476
+  P.Rm[0] = c.R[0]; P.Rm[1] = 0.5 * (c.R[1] + c.R[2]); P.Rm[2] = c.R[3];
+  P.Rd[0] = c.R_d[0]; P.Rd[1] = 0.5 * (c.R_d[1] + c.R_d[2]); P.Rd[2] = c.R_d[3];
+  P.max_iter = c.max_iter > 0 ? c.max_iter : 40;
+  P.tol = c.tol > 0.0 ? c.tol : 1e-12;
+  P.NSd = P.N | 1;
+  const int d = P.NSd;
+  int o = 0;
+  auto take = [&](int n) { const int at = o; o += (n + 1) & ~1; return at; };   // keep 16-byte alignment
+  P.oABG = take(54 * P.NS);
+  P.oS = take(P.RS * d); P.oY = take(P.RS * d); P.oCR = take(P.RS * d);
+  P.oX = take(6 * d); P.oU = take(2 * d); P.oDX = take(6 * d); P.oDU = take(2 * d);
+  P.oHX = take(6 * d); P.oCZX = take(6 * d); P.oCZU = take(2 * d); P.oCZTH = take(d); P.oCW = take(2 * d);
+  P.oEE = take(3 * d); P.oUQ = take(3 * d);
+  P.oFAC = take(20 * P.NS); P.oKFF = take(6 * P.NS);
+  P.oBL = take(d); P.oBR = take(d); P.oVREF = take(d); P.oT = take(d);
+  P.oPM = take(64); P.oL1 = take(8); P.oLTH = take(8); P.oMAB = take(48); P.oAXBW = take(16); P.oYY = take(64);
+  P.oTERM = take(TB_SIZE);
+  P.total = o;
+  *out = P;
+  return LMPC_OK;
+}

@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's RacingMPC / SafeSetManager / BaseVehicleModel surface for B
+ticks at a time, on top of the C ABI (include/lmpc_b200.h).
+
+    mpc = BatchedRacingMPC(vehicle_dict, config_dict, max_batch=1024)   # RacingMPC(config, model)
+    mpc.add_lap(x, u, k, t, L)                                          # SafeSetManager::add_lap
+    out = mpc.solve(batch)                                              # RacingMPC::solve, B ticks
+
+`batch` uses the reference's input keys (racing_mpc.cpp:215-228); each value is instance-major
+(X_ref: (B, N, 6) == B column-major 6 x N DMs).  numpy arrays take the HOST path (H2D / D2H inside the
+call); torch CUDA tensors take the DEVICE path (zero copies, work enqueued on the current torch
+stream).  Output keys: X_optm, U_optm, dU_optm, convex_combi_optm, ss_x, ss_j, cost, status, iters.
+There is no CPU fallback: construction raises without the CUDA library and a GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import binding as B
+
+IN_KEYS = ("x_ic", "u_ic", "X_ref", "U_ref", "T_ref", "bound_left", "bound_right", "curvatures",
+           "vel_ref", "total_length")
+
+
+class LmpcError(RuntimeError):
+    pass
+
+
+def _check(lib, h, rc, what):
+    if rc != 0:
+        msg = lib.lmpc_status_string(rc).decode()
+        detail = lib.lmpc_last_error(h).decode() if h else ""
+        raise LmpcError(f"{what}: {msg} ({rc}) {detail}")
+
+
+class BatchedRacingMPC:
+    def __init__(self, vehicle, config, max_batch=1024, device=0, lib_path=None):
+        self.lib = B.load_library(lib_path)
+        self.vehicle = dict(vehicle)
+        self.config = dict(config)
+        self.N = int(config["N"])
+        self.K = int(config["num_ss_pts"])
+        self.learning = bool(config["learning"])
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self._veh = B.fill_struct(B.VehicleParams(), vehicle)
+        self._cfg = B.fill_struct(B.MpcConfig(), config)
+        self._h = C.c_void_p()
+        rc = self.lib.lmpc_create(C.byref(self._cfg), C.byref(self._veh), self.device, self.max_batch,
+                                  C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            _check(self.lib, None, rc, "lmpc_create")
+        self._solved = False
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.lmpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def set_stream(self, stream=None):
+        """Enqueue on `stream` (a torch.cuda.Stream, a raw cudaStream_t int, or None = default)."""
+        ptr = 0
+        if stream is not None:
+            ptr = int(getattr(stream, "cuda_stream", stream))
+        _check(self.lib, self._h, self.lib.lmpc_set_stream(self._h, C.c_void_p(ptr)), "lmpc_set_stream")
+
+    def synchronize(self):
+        _check(self.lib, self._h, self.lib.lmpc_synchronize(self._h), "lmpc_synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.lmpc_launch_count(self._h))
+
+    def solved(self):
+        """RacingMPC::solved(): latches true after the first successful solve."""
+        return self._solved
+
+    # ------------------------------------------------------------------ safe set
+    def add_lap(self, x, u, k, t, total_length):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        k = np.ascontiguousarray(k, dtype=np.float64).ravel()
+        t = np.ascontiguousarray(t, dtype=np.float64).ravel()
+        assert x.ndim == 2 and x.shape[1] == 6
+        rc = self.lib.lmpc_safe_set_add_lap(self._h, x.shape[0], x.ctypes.data, u.ctypes.data, k.ctypes.data,
+                                            t.ctypes.data, float(total_length))
+        _check(self.lib, self._h, rc, "lmpc_safe_set_add_lap")
+
+    def load_lap(self, prefix, total_length):
+        _check(self.lib, self._h, self.lib.lmpc_safe_set_load(self._h, str(prefix).encode(), float(total_length)),
+               "lmpc_safe_set_load")
+
+    def clear_safe_set(self):
+        _check(self.lib, self._h, self.lib.lmpc_safe_set_clear(self._h), "lmpc_safe_set_clear")
+
+    def num_laps(self):
+        return int(self.lib.lmpc_safe_set_num_laps(self._h))
+
+    def ss_query(self, queries, max_total=None, per_lap=None):
+        """SafeSetManager::query for B points (B, 2) -> ss_x (B, count, 6), ss_j (B, count)."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 2)
+        Bn = q.shape[0]
+        mt = int(self.K if max_total is None else max_total)
+        pl = int(self.config["num_ss_pts_per_lap"] if per_lap is None else per_lap)
+        sx = np.zeros((Bn, mt, 6)); sj = np.zeros((Bn, mt)); cnt = np.zeros(Bn, dtype=np.int32)
+        rc = self.lib.lmpc_safe_set_query_batch(self._h, Bn, q.ctypes.data, mt, pl, sx.ctypes.data, sj.ctypes.data,
+                                                cnt.ctypes.data, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_safe_set_query_batch")
+        c = int(cnt[0]) if Bn else 0
+        return sx[:, :c], sj[:, :c]
+
+    # ------------------------------------------------------------------ model
+    def discrete_dynamics(self, x, u, kappa, dt):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 6)
+        n = x.shape[0]
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 2)
+        kappa = np.ascontiguousarray(np.broadcast_to(kappa, (n,)), dtype=np.float64)
+        dt = np.ascontiguousarray(np.broadcast_to(dt, (n,)), dtype=np.float64)
+        xn = np.zeros((n, 6))
+        rc = self.lib.lmpc_discrete_dynamics_batch(self._h, n, x.ctypes.data, u.ctypes.data, kappa.ctypes.data,
+                                                   dt.ctypes.data, xn.ctypes.data, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_discrete_dynamics_batch")
+        return xn
+
+    def linearise(self, x, u, kappa, dt):
+        """discrete_dynamics_jacobian: returns A (n,6,6), B (n,6,2), g (n,6), x_next (n,6)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 6)
+        n = x.shape[0]
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(n, 2)
+        kappa = np.ascontiguousarray(np.broadcast_to(kappa, (n,)), dtype=np.float64)
+        dt = np.ascontiguousarray(np.broadcast_to(dt, (n,)), dtype=np.float64)
+        A = np.zeros((n, 36)); Bm = np.zeros((n, 12)); g = np.zeros((n, 6)); xn = np.zeros((n, 6))
+        rc = self.lib.lmpc_linearise_batch(self._h, n, x.ctypes.data, u.ctypes.data, kappa.ctypes.data, dt.ctypes.data,
+                                           A.ctypes.data, Bm.ctypes.data, g.ctypes.data, xn.ctypes.data, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_linearise_batch")
+        return A.reshape(n, 6, 6).transpose(0, 2, 1).copy(), Bm.reshape(n, 2, 6).transpose(0, 2, 1).copy(), g, xn
+
+    # ------------------------------------------------------------------ solve
+    def _shapes(self, Bn):
+        N, K = self.N, max(self.K, 1)
+        return dict(X_optm=(Bn, N, 6), U_optm=(Bn, N - 1, 2), dU_optm=(Bn, N - 1, 2), convex_combi_optm=(Bn, K),
+                    ss_x=(Bn, K, 6), ss_j=(Bn, K), cost=(Bn,))
+
+    def alloc_host_outputs(self, Bn, pinned=False):
+        """Output buffers for the host path (optionally CUDA-pinned through torch)."""
+        out = {}
+        if pinned:
+            import torch
+            for k, shp in self._shapes(Bn).items():
+                out[k] = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
+            out["status"] = torch.empty(Bn, dtype=torch.int32).pin_memory().numpy()
+            out["iters"] = torch.empty(Bn, dtype=torch.int32).pin_memory().numpy()
+        else:
+            for k, shp in self._shapes(Bn).items():
+                out[k] = np.zeros(shp)
+            out["status"] = np.zeros(Bn, dtype=np.int32)
+            out["iters"] = np.zeros(Bn, dtype=np.int32)
+        return out
+
+    def solve(self, batch, out=None):
+        first = batch["x_ic"]
+        if isinstance(first, np.ndarray):
+            return self._solve_host(batch, out)
+        return self._solve_device(batch, out)
+
+    def _solve_host(self, batch, out=None):
+        Bn = int(np.asarray(batch["x_ic"]).shape[0])
+        keep = {k: np.ascontiguousarray(batch[k], dtype=np.float64) for k in IN_KEYS}
+        warm = batch.get("U_optm_ref", None)
+        if warm is not None:
+            keep["U_warm"] = np.ascontiguousarray(warm, dtype=np.float64)
+        bi = B.BatchIn()
+        for k in IN_KEYS:
+            setattr(bi, k, keep[k].ctypes.data)
+        bi.U_warm = keep["U_warm"].ctypes.data if "U_warm" in keep else None
+        if out is None:
+            out = self.alloc_host_outputs(Bn)
+        bo = B.BatchOut()
+        for k in ("X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost", "status", "iters"):
+            setattr(bo, k, out[k].ctypes.data)
+        rc = self.lib.lmpc_solve_batch(self._h, Bn, C.byref(bi), C.byref(bo), B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_solve_batch")
+        if (out["status"] == 0).any():
+            self._solved = True
+        return out
+
+    def alloc_device_outputs(self, Bn, device=None):
+        import torch
+        dev = device or torch.device("cuda", self.device)
+        out = {k: torch.empty(shp, dtype=torch.float64, device=dev) for k, shp in self._shapes(Bn).items()}
+        out["status"] = torch.empty(Bn, dtype=torch.int32, device=dev)
+        out["iters"] = torch.empty(Bn, dtype=torch.int32, device=dev)
+        return out
+
+    def _solve_device(self, batch, out=None):
+        """torch CUDA tensors in, torch CUDA tensors out; asynchronous on the handle's stream."""
+        import torch
+        Bn = int(batch["x_ic"].shape[0])
+        for k in IN_KEYS:
+            t = batch[k]
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                raise LmpcError(f"device path needs contiguous float64 CUDA tensors ({k})")
+        if out is None:
+            out = self.alloc_device_outputs(Bn, batch["x_ic"].device)
+        bi = B.BatchIn()
+        for k in IN_KEYS:
+            setattr(bi, k, batch[k].data_ptr())
+        warm = batch.get("U_optm_ref", None)
+        bi.U_warm = warm.data_ptr() if warm is not None else None
+        bo = B.BatchOut()
+        for k in ("X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost", "status", "iters"):
+            setattr(bo, k, out[k].data_ptr())
+        rc = self.lib.lmpc_solve_batch(self._h, Bn, C.byref(bi), C.byref(bo), B.LMPC_MEM_DEVICE)
+        _check(self.lib, self._h, rc, "lmpc_solve_batch")
+        self._solved = True
+        return out

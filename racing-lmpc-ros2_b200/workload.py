@@ -111,8 +111,9 @@ def make_batch(vehicle, config, B, seed, track, laps=None, dt=0.025, mode="barc"
         U_ref[:, :, 1] = np.arctan(vehicle["wheel_base"] * track_lookup(track, s0, "curvature"))[:, None]
         U_ref[:, :, 0] = 0.5
         u_ic = U_ref[:, 0, :].copy()
-    lo = np.where(np.isfinite(xmin), xmin + 1e-3 * np.maximum(1.0, np.abs(xmin)), -np.inf)
-    hi = np.where(np.isfinite(xmax), xmax - 1e-3 * np.maximum(1.0, np.abs(xmax)), np.inf)
+    with np.errstate(invalid="ignore"):
+        lo = np.where(np.isfinite(xmin), xmin + 1e-3 * np.maximum(1.0, np.abs(xmin)), -np.inf)
+        hi = np.where(np.isfinite(xmax), xmax - 1e-3 * np.maximum(1.0, np.abs(xmax)), np.inf)
     x_ic = np.clip(x_ic, lo, hi)
     # keep e_y inside the (margin-shrunk) track
     mrg = config["margin"] + vehicle["chassis_b"] / 2.0 + 0.02

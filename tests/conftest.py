@@ -1,0 +1,73 @@
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+warnings.filterwarnings("ignore", category=RuntimeWarning)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def relerr(a, b):
+    """SURVEY 8c parity metric: per channel max|a-b| / max(1, max|b|), worst channel."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    a2 = a.reshape(-1, a.shape[-1]) if a.ndim > 1 else a.reshape(-1, 1)
+    b2 = b.reshape(-1, b.shape[-1]) if b.ndim > 1 else b.reshape(-1, 1)
+    return float((np.abs(a2 - b2).max(axis=0) / np.maximum(1.0, np.abs(b2).max(axis=0))).max())
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import racing_lmpc_ros2_b200 as P
+    return P
+
+
+@pytest.fixture(scope="session")
+def laps(pkg):
+    return pkg.workload.load_laps()
+
+
+@pytest.fixture(scope="session")
+def barc_track(pkg):
+    return pkg.workload.load_track("barc_center")
+
+
+@pytest.fixture(scope="session")
+def putnam_track(pkg):
+    return pkg.workload.load_track("putnam_optm")
+
+
+CASES = {
+    # name: (vehicle key, config factory name, N, track, workload mode)
+    "barc_lmpc": ("BARC_VEHICLE", "barc_lmpc_config", 20, "barc_center", "barc"),
+    "barc_tracking": ("BARC_VEHICLE", "barc_tracking_config", 20, "barc_center", "barc"),
+    "iac_tracking": ("IAC_VEHICLE", "iac_tracking_config", 40, "putnam_optm", "track"),
+}
+
+
+def make_case(pkg, name, tol=None, N=None):
+    vk, ck, n0, tk, mode = CASES[name]
+    veh = getattr(pkg.configs, vk)
+    cfg = getattr(pkg.configs, ck)(N or n0)
+    if tol is not None:
+        cfg["tol"] = tol
+    return veh, cfg, pkg.workload.load_track(tk), mode
+
+
+def make_oracle(pkg, name, tol=None, N=None, with_laps=True):
+    from oracle import Oracle
+    veh, cfg, track, mode = make_case(pkg, name, tol, N)
+    o = Oracle(veh, cfg)
+    if cfg["learning"] and with_laps:
+        for l in pkg.workload.load_laps():
+            o.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    return o, veh, cfg, track, mode

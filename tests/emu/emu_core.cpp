@@ -1,0 +1,48 @@
+// Test-only lane-loop emulator of the product's warp kernels (LMPC_EMULATE build of the same
+// .cuh sources).  Lets the kernel logic be checked against the CPU oracle without a GPU, and run
+// with reversed lane order to expose phase-ordering (race) mistakes.  Never linked into the product.
+#define LMPC_EMULATE 1
+#include <stdlib.h>
+#include <vector>
+#include "../../racing-lmpc-ros2_b200/csrc/lmpc_host_params.h"
+#include "../../racing-lmpc-ros2_b200/csrc/lmpc_ss_core.cuh"
+int g_lmpc_emu_reverse = 0;
+
+extern "C" void emu_set_reverse(int r) { g_lmpc_emu_reverse = r; }
+
+extern "C" void emu_linearise(const lmpc_vehicle_params* v, const double* x, const double* u, double kappa, double dt,
+                              double* A, double* B, double* g, double* xn) {
+  LmpcModel P = lmpc_make_model(*v);
+  lmpc_linearise(P, x, u, kappa, dt, A, B, g, xn);
+}
+
+// one lap at a time: (query, lap) exactly as the kernel does it
+extern "C" void emu_ss_query_lap(int m, const double* ps, const double* pe, const double* xr, const double* J, const int* canon,
+                                 int take, int out_off, double qs, double qe, int max_total, double* ss_x, double* ss_j,
+                                 int last, int count, int pad_to) {
+  LmpcLapView lap = {ps, pe, xr, J, canon, m, take, out_off};
+  lmpc_ss_query_warp(lap, qs, qe, max_total, ss_x, ss_j, last != 0, count, pad_to);
+}
+
+// full QP solve of one instance given its linearisation and safe-set columns
+extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params* v, const double* x_ic, const double* u_ic,
+                            const double* U0, const double* T, const double* bl, const double* br, const double* vref,
+                            const double* ABg, const double* ssx, const double* ssj_raw, const double* cen, int ss_count,
+                            double* X, double* U, double* dU, double* lam, double* cost, int* status, int* iters,
+                            int* smem_doubles) {
+  LmpcQpParams P;
+  int rc = lmpc_make_qp_params(*c, *v, &P);
+  if (rc != LMPC_OK) return rc;
+  if (smem_doubles) *smem_doubles = P.total;
+  std::vector<double> sm((size_t)P.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
+  std::vector<double> ssc((size_t)(P.K > 0 ? P.K : 1), 0.0);
+  for (int k = 0; k < P.K; k++) ssc[k] = ssj_raw[k] - ssj_raw[0];        // racing_mpc.cpp:280
+  LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssc.data(), cen, ss_count};
+  LmpcQpOut out = {X, U, dU, lam, cost, status, iters};
+  const int kpl = (P.K + 31) / 32;
+  if (kpl <= 1) lmpc_qp_solve_warp<1>(P, in, sm.data(), out);
+  else if (kpl == 2) lmpc_qp_solve_warp<2>(P, in, sm.data(), out);
+  else if (kpl == 3) lmpc_qp_solve_warp<3>(P, in, sm.data(), out);
+  else lmpc_qp_solve_warp<4>(P, in, sm.data(), out);
+  return LMPC_OK;
+}

@@ -1,0 +1,157 @@
+"""Lane-loop emulation of the CUDA kernels' source (tests/emu, -DLMPC_EMULATE build of the same .cuh
+files) against the CPU oracle.  This is how the warp kernels' logic is checked on a box without a GPU;
+the emulator is a test artefact and is never loaded by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CASES, ROOT, make_oracle, relerr
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "liblmpc_emu.so")
+DP = C.POINTER(C.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(DP)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU_DIR, "emu_core.cpp")] + [
+        os.path.join(ROOT, "racing-lmpc-ros2_b200", "csrc", f)
+        for f in ("lmpc_qp_core.cuh", "lmpc_ss_core.cuh", "lmpc_model.cuh", "lmpc_warp.cuh", "lmpc_host_params.h")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", EMU_SO, srcs[0]])
+    return C.CDLL(EMU_SO)
+
+
+def _emu_solve(emu, pkg, od, veh, cfg, inp, reverse=0):
+    from racing_lmpc_ros2_b200 import binding as Bd
+    emu.emu_set_reverse(reverse)
+    vs = Bd.fill_struct(Bd.VehicleParams(), veh)
+    cs = Bd.fill_struct(Bd.MpcConfig(), cfg)
+    N, K = cfg["N"], cfg["num_ss_pts"]
+    Xr = inp["X_ref"].copy()
+    for j in range(N):
+        Xr[j, 0] = od.align_abscissa(Xr[j, 0], inp["x_ic"][0], inp["total_length"])
+    ABg = np.zeros((N - 1, 54))
+    A1 = np.zeros(36); B1 = np.zeros(12); g1 = np.zeros(6); xn = np.zeros(6)
+    for j in range(N - 1):   # the product's own (analytic) linearisation, emulated
+        u = np.ascontiguousarray(inp["U_ref"][j])
+        emu.emu_linearise(C.byref(vs), _p(np.ascontiguousarray(Xr[j])), _p(u), C.c_double(inp["curvatures"][j]),
+                          C.c_double(inp["T_ref"][j]), _p(A1), _p(B1), _p(g1), _p(xn))
+        ABg[j, :36] = A1; ABg[j, 36:48] = B1; ABg[j, 48:] = g1
+    if cfg["learning"]:
+        sx, sj = od.ss_query(Xr[N - 1, 0], Xr[N - 1, 1])
+        cnt = len(sj)
+        ssx = np.zeros((K, 6)); ssj = np.zeros(K)
+        ssx[:cnt] = sx; ssj[:cnt] = sj; ssx[cnt:] = sx[-1]; ssj[cnt:] = sj[-1]
+    else:
+        ssx = np.zeros((1, 6)); ssj = np.zeros(1); cnt = 0
+    cen = np.ascontiguousarray(Xr[N - 1])
+    X = np.zeros((N, 6)); U = np.zeros((N - 1, 2)); dU = np.zeros((N - 1, 2)); lam = np.zeros(max(K, 1))
+    cost = C.c_double(); st = C.c_int(); it = C.c_int(); smd = C.c_int()
+    rc = emu.emu_qp_solve(C.byref(cs), C.byref(vs), _p(inp["x_ic"]), _p(inp["u_ic"]), _p(np.ascontiguousarray(inp["U_ref"])),
+                          _p(inp["T_ref"]), _p(inp["bound_left"]), _p(inp["bound_right"]), _p(inp["vel_ref"]), _p(ABg),
+                          _p(ssx), _p(ssj), _p(cen), cnt, _p(X), _p(U), _p(dU), _p(lam), C.byref(cost), C.byref(st),
+                          C.byref(it), C.byref(smd))
+    assert rc == 0
+    return dict(X=X, U=U, dU=dU, lam=lam, cost=cost.value, status=st.value, iters=it.value, smem=smd.value * 8, ss_x=ssx)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_qp_kernel_matches_dense_oracle(emu, pkg, name):
+    od, veh, cfg, track, mode = make_oracle(pkg, name, tol=1e-11)
+    cfgk = dict(cfg, tol=1e-13)
+    batch = pkg.workload.make_batch(veh, cfg, 10, 0xE31 + len(name), track, pkg.workload.load_laps(), mode=mode)
+    worst = 0.0
+    for b in range(10):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        k = _emu_solve(emu, pkg, od, veh, cfgk, inp)
+        assert k["status"] == 0
+        worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"]))
+        assert abs(k["cost"] - d["cost"]) < 1e-8 * max(1, abs(d["cost"]))
+        if cfg["learning"]:
+            assert np.allclose(k["ss_x"].T @ k["lam"], d["ss_x"].T @ d["lam"], atol=1e-7)
+            assert abs(k["lam"].sum() - 1) < 1e-9 and k["lam"].min() >= 0
+    assert worst < 1e-6, worst
+
+
+def test_emulated_qp_kernel_is_lane_order_independent(emu, pkg):
+    """Running the lanes of every phase in reverse order must give bit-identical results: a phase that
+    read shared memory written by another lane in the same phase would differ."""
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc", tol=1e-11)
+    cfgk = dict(cfg, tol=1e-13)
+    batch = pkg.workload.make_batch(veh, cfg, 3, 0xAB, track, pkg.workload.load_laps(), mode=mode)
+    for b in range(3):
+        inp = pkg.workload.instance(batch, b)
+        f = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=0)
+        r = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=1)
+        for key in ("X", "U", "dU", "lam"):
+            assert np.array_equal(f[key], r[key]), key
+        assert f["iters"] == r["iters"] and f["cost"] == r["cost"]
+
+
+def test_qp_shared_memory_budget(emu, pkg):
+    """BASELINE config 2 (N=20, K=96) must fit 7 warps per SM: <= (228 KB - 7 KB reserved) / 7."""
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc")
+    batch = pkg.workload.make_batch(veh, cfg, 1, 1, track, pkg.workload.load_laps(), mode=mode)
+    k = _emu_solve(emu, pkg, od, veh, cfg, pkg.workload.instance(batch, 0))
+    assert k["smem"] + 8 * cfg["num_ss_pts"] <= (228 * 1024 - 7 * 1024) // 7
+
+
+def test_emulated_ss_query_matches_oracle(emu, pkg, laps, barc_track):
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc")
+    L = barc_track["length"]
+    rng = np.random.default_rng(2)
+    # build the slab exactly as the C-ABI's add_lap does (tripled points, J, canon)
+    slabs = []
+    for lap in reversed(laps):
+        x = lap["x"]; n = x.shape[0]
+        off = np.zeros_like(x); off[:, 0] = L
+        xr = np.ascontiguousarray(np.vstack([x - off, x, x + off]))
+        J = np.linspace(n - 1, 0, n); Jr = np.ascontiguousarray(np.concatenate([J + n - 1, J, J - n + 1]))
+        canon = np.arange(3 * n, dtype=np.int32)
+        slabs.append((np.ascontiguousarray(xr[:, 0]), np.ascontiguousarray(xr[:, 1]), xr, Jr, canon))
+    for rev in (0, 1):
+        emu.emu_set_reverse(rev)
+        for _ in range(15):
+            qs, qe = rng.uniform(-3, 20), rng.uniform(-.4, .4)
+            sx = np.zeros((96, 6)); sj = np.zeros(96)
+            for j, (ps, pe, xr, Jr, canon) in enumerate(slabs):
+                emu.emu_ss_query_lap(len(ps), _p(ps), _p(pe), _p(xr), _p(Jr), canon.ctypes.data_as(C.POINTER(C.c_int)), 32,
+                                     32 * j, C.c_double(qs), C.c_double(qe), 96, _p(sx), _p(sj), int(j == 2), 96, 96)
+            ox, oj = od.ss_query(qs, qe)
+            assert np.array_equal(sx, ox) and np.array_equal(sj, oj)
+
+
+def test_emulated_ss_query_exact_fallback(emu, pkg):
+    """Clustered data: most of the nearest points fall on few lanes, forcing the exact continuation."""
+    from oracle import Oracle
+    veh = pkg.configs.BARC_VEHICLE
+    cfg = pkg.configs.barc_lmpc_config(20)
+    n = 400
+    x = np.zeros((n, 6)); x[:, 0] = np.linspace(0, 40, n)
+    # every 32nd point (same lane) is pulled next to the query
+    x[::32, 0] = 5.0 + 1e-3 * np.arange(len(x[::32])); x[::32, 1] = 0.01
+    L = 1000.0
+    o = Oracle(veh, cfg)
+    o.add_lap(x, np.zeros((n, 2)), np.zeros(n), np.arange(float(n)), L)
+    off = np.zeros_like(x); off[:, 0] = L
+    xr = np.ascontiguousarray(np.vstack([x - off, x, x + off]))
+    J = np.linspace(n - 1, 0, n); Jr = np.ascontiguousarray(np.concatenate([J + n - 1, J, J - n + 1]))
+    canon = np.arange(3 * n, dtype=np.int32)
+    ps = np.ascontiguousarray(xr[:, 0]); pe = np.ascontiguousarray(xr[:, 1])
+    sx = np.zeros((32, 6)); sj = np.zeros(32)
+    emu.emu_set_reverse(0)
+    emu.emu_ss_query_lap(3 * n, _p(ps), _p(pe), _p(xr), _p(Jr), canon.ctypes.data_as(C.POINTER(C.c_int)), 32, 0,
+                         C.c_double(5.0), C.c_double(0.0), 32, _p(sx), _p(sj), 1, 32, 32)
+    ox, oj = o.ss_query(5.0, 0.0, max_total=32, per_lap=32)
+    assert np.array_equal(sx, ox) and np.array_equal(sj, oj)
