@@ -95,8 +95,10 @@ typedef struct lmpc_mpc_config {
   double x_max[6], x_min[6], u_max[2], u_min[2];   /* +-INFINITY (or |v| >= 1e19) = unbounded */
   double convex_hull_slack[6];
   int32_t num_ss_pts, num_ss_pts_per_lap, max_lap_stored;
-  int32_t max_iter;          /* IPM iteration cap (default 40 when <= 0) */
-  double tol;                /* IPM tolerance on mu / residuals (default 1e-12 when <= 0) */
+  int32_t max_iter;          /* interior-point iteration cap (default 30 when <= 0) */
+  double tol;                /* target accuracy of the returned X/U/dU, per channel relative to
+                              * max(1, |channel|) (default 1e-9 when <= 0); the complementarity
+                              * floor is 1e-4 * tol */
 } lmpc_mpc_config;
 
 typedef struct lmpc_handle lmpc_handle;
@@ -163,6 +165,11 @@ int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, const double* u
 /* ---- the hot path: B independent MPC ticks ---- */
 int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out,
                      int memspace);
+/* Per-kernel device timing (measurement aid): when enabled, CUDA events are recorded on the handle's
+ * stream around the three kernels of every lmpc_solve_batch; lmpc_get_kernel_ms synchronises and
+ * returns the summed milliseconds {linearise, safe-set query, QP} over the recorded solves. */
+int lmpc_set_timing(lmpc_handle* h, int enable);
+int lmpc_get_kernel_ms(lmpc_handle* h, double* ms3, int* nsolves);
 /* Blocks until everything enqueued on the handle's stream has finished. */
 int lmpc_synchronize(lmpc_handle* h);
 

@@ -89,7 +89,8 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
   if (st != ORC_OK) { out->status = st; free(p); return st; }
   port_ws* w = (port_ws*)calloc(1, sizeof *w);
   const int N = p->N, K = p->K, soft = p->soft_boundary, learn = p->learning;
-  const double tol = c->tol > 0 ? c->tol : 1e-9;
+  const double step_tol = c->tol > 0 ? c->tol : 1e-9;   /* target accuracy of the returned trajectory */
+  const double tol = 1e-4 * step_tol;                  /* complementarity / residual floor */
   const int max_iter = c->max_iter > 0 ? c->max_iter : 60;
   const double Rm[3] = {c->R[0], 0.5 * (c->R[1] + c->R[2]), c->R[3]};
   const double Rd[3] = {c->R_d[0], 0.5 * (c->R_d[1] + c->R_d[2]), c->R_d[3]};
@@ -151,6 +152,13 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       w->x[6 * (i + 1) + r] = a;
     }
   }
+  /* channel scales max(1, |channel|) of the parity metric, from the initial iterate */
+  double chx[6] = {1, 1, 1, 1, 1, 1}, chu[2] = {1, 1}, chd[2] = {1, 1};
+  for (int i = 0; i < N; i++) for (int k = 0; k < 6; k++) chx[k] = fmax(chx[k], fabs(w->x[6 * i + k]));
+  for (int i = 0; i < N - 1; i++) for (int k = 0; k < 2; k++) {
+    const double up = i ? w->u[2 * (i - 1) + k] : p->u_ic[k];
+    chu[k] = fmax(chu[k], fabs(w->u[2 * i + k])); chd[k] = fmax(chd[k], fabs(w->u[2 * i + k] - up) / p->T[i]);
+  }
   const double sfloor = getenv("ORC_SFLOOR") ? atof(getenv("ORC_SFLOOR")) : 1e-2;
   const double mu0 = getenv("ORC_MU0") ? atof(getenv("ORC_MU0")) : 0.1;
   const double th0 = getenv("ORC_TH0") ? atof(getenv("ORC_TH0")) : 0.01;
@@ -177,7 +185,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     for (int j = 0; j < K; j++) if (fabs(p->ssc[j]) > R0) R0 = fabs(p->ssc[j]);
     if (2.0 * qb * w->th > R0) R0 = 2.0 * qb * w->th;
   }
-  double rho_d = 1.0;
+  double rho_d = 1.0, prev_stepn = 0.0;
   int it, status = ORC_MAX_ITER;
 
   for (it = 0; it < max_iter; it++) {
@@ -512,6 +520,15 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         for (int j = 0; j < K; j++) { mua += (w->lam[j] + aa * w->dlam[j]) * (w->ylam[j] + aa * w->dylam[j]); w->corr_lam[j] = w->dlam[j] * w->dylam[j]; }
         mua /= (double)m_total;
         sigma = pow(mua / mu, 3.0);
+        { /* safeguarded second-order term (Mehrotra's corrector is harmful when the affine step is short) */
+          const int mode = getenv("ORC_CORR") ? atoi(getenv("ORC_CORR")) : 5;
+          const double sc = mode == 1 ? aa : (mode == 2 ? aa * aa : (mode == 3 ? (aa < 0.5 ? aa : 1.0) : (mode == 4 ? fmin(1.0, aa / 0.7) : (mode == 5 ? (aa < 0.2 ? aa : 1.0) : 1.0))));
+          if (sc != 1.0) {
+            for (int j = 0; j < N * MAXROW; j++) if (w->act[j]) w->corr[j] *= sc;
+            w->corr_th *= sc;
+            for (int j = 0; j < K; j++) w->corr_lam[j] *= sc;
+          }
+        }
       } else {
         { const double eta = getenv("ORC_ETA") ? atof(getenv("ORC_ETA")) : 1.0; double tau = 1.0 - fmin(0.005, eta * mu); alpha = tau * amax; if (alpha > 1.0) alpha = 1.0; }
       }
@@ -523,6 +540,25 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     if (soft) { w->th += alpha * w->dth; w->yth += alpha * w->dyth; }
     for (int j = 0; j < K; j++) { w->lam[j] += alpha * w->dlam[j]; w->ylam[j] += alpha * w->dylam[j]; }
     rho_d *= (1.0 - alpha);
+    { /* step-based acceptance: the primal step, per channel relative to max(1, |channel|), bounds the
+       * remaining error once the iteration is in its fast final phase */
+      double sx[6] = {0}, su[2] = {0}, sd[2] = {0};
+      for (int i = 0; i < N; i++) for (int k = 0; k < 6; k++) sx[k] = fmax(sx[k], fabs(w->dx[6 * i + k]));
+      for (int i = 0; i < N - 1; i++) for (int k = 0; k < 2; k++) {
+        const double dup = i ? w->du[2 * (i - 1) + k] : 0.0;
+        su[k] = fmax(su[k], fabs(w->du[2 * i + k])); sd[k] = fmax(sd[k], fabs(w->du[2 * i + k] - dup) / p->T[i]);
+      }
+      double stepn = 0.0;
+      for (int k = 0; k < 6; k++) stepn = fmax(stepn, sx[k] / chx[k]);
+      for (int k = 0; k < 2; k++) stepn = fmax(stepn, fmax(su[k] / chu[k], sd[k] / chd[k]));
+      stepn *= alpha;
+      if (getenv("ORC_PORT_DEBUG")) fprintf(stderr, "   stepn %.3e\n", stepn);
+      /* geometric-tail estimate of the remaining error from two consecutive steps */
+      const double ratio = (prev_stepn > 0.0) ? stepn / prev_stepn : 1.0;
+      const double est = (ratio < 0.9) ? stepn * ratio / (1.0 - ratio) : 1e300;
+      prev_stepn = stepn;
+      if (!getenv("ORC_NOSTEP") && stepn < step_tol && est < step_tol && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) { status = ORC_OK; it++; break; }
+    }
     if (getenv("ORC_PORT_DEBUG")) fprintf(stderr, "it %2d mu %.3e rp %.3e sigma %.3e alpha %.4f th %.3e rnu %.2e\n", it, mu, rpn, sigma, alpha, w->th, rnu);
   }
 done:

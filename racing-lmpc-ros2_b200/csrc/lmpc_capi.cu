@@ -49,7 +49,13 @@ struct lmpc_handle {
   // device staging for host-memory callers
   DevBuf st_in, st_out;
   size_t qp_smem = 0;
+  // optional per-kernel timing: events recorded on the stream around the three kernels of each solve
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;   // 4 events per recorded solve (ring)
+  int tcount = 0;
 };
+
+static const int kTimingRing = 1024;
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -124,6 +130,7 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
 extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
+  for (auto& e : h->tev) cudaEventDestroy(e);
   for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
@@ -133,6 +140,34 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
 extern "C" int lmpc_set_stream(lmpc_handle* h, void* s) {
   if (!h) return LMPC_ERR_INVALID;
   h->stream = (cudaStream_t)s;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_set_timing(lmpc_handle* h, int enable) {
+  if (!h) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (enable && h->tev.empty()) {
+    h->tev.resize(4 * (size_t)kTimingRing);
+    for (auto& e : h->tev) CK(cudaEventCreate(&e));
+  }
+  h->timing = enable != 0;
+  h->tcount = 0;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_get_kernel_ms(lmpc_handle* h, double* ms3, int* nsolves) {
+  if (!h || !ms3) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  ms3[0] = ms3[1] = ms3[2] = 0.0;
+  const int n = std::min(h->tcount, kTimingRing);
+  for (int k = 0; k < n; k++)
+    for (int j = 0; j < 3; j++) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, h->tev[4 * (size_t)k + j], h->tev[4 * (size_t)k + j + 1]));
+      ms3[j] += ms;
+    }
+  if (nsolves) *nsolves = n;
   return LMPC_OK;
 }
 
@@ -410,6 +445,8 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
   double* ssx = (memspace == LMPC_MEM_DEVICE && out->ss_x) ? out->ss_x : (memspace == LMPC_MEM_HOST ? dout_d[4] : (double*)h->ws_ssx.p);
   double* ssj = (memspace == LMPC_MEM_DEVICE && out->ss_j) ? out->ss_j : (memspace == LMPC_MEM_HOST ? dout_d[5] : (double*)h->ws_ssj.p);
 
+  cudaEvent_t* tev = (h->timing && !h->tev.empty()) ? &h->tev[4 * (size_t)(h->tcount % kTimingRing)] : nullptr;
+  if (tev) CK(cudaEventRecord(tev[0], h->stream));
   // K1: linearise
   {
     const int n = B * (int)NS, threads = 64, blocks = (n + threads - 1) / threads;
@@ -417,6 +454,7 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
     h->launches++;
     CK(cudaGetLastError());
   }
+  if (tev) CK(cudaEventRecord(tev[1], h->stream));
   // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272)
   LmpcLapTable tab;
   tab.n_used = 0; tab.count = 0;
@@ -425,6 +463,7 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
     int rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, ssx, ssj);
     if (rc != LMPC_OK) return rc;
   }
+  if (tev) CK(cudaEventRecord(tev[2], h->stream));
   // K3: QP
   LmpcQpBatch a;
   a.x_ic = din[0]; a.u_ic = din[1]; a.U0 = din[10] ? din[10] : din[3]; a.T_ref = din[4];
@@ -437,6 +476,7 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
   if (kpl <= 1) launch_qp<1>(h, a); else if (kpl == 2) launch_qp<2>(h, a); else if (kpl == 3) launch_qp<3>(h, a); else launch_qp<4>(h, a);
   h->launches++;
   CK(cudaGetLastError());
+  if (tev) { CK(cudaEventRecord(tev[3], h->stream)); h->tcount++; }
   if (memspace == LMPC_MEM_HOST) {
     for (int k = 0; k < 7; k++) {
       if (!hout_d[k]) continue;

@@ -67,8 +67,8 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   for (int k = 0; k < 6; k++) { P.qx[k] = w[k]; P.qxN[k] = (k >= 1 && k <= 3) ? 10.0 * w[k] : 0.0; }   // :473-476
   P.Rm[0] = c.R[0]; P.Rm[1] = 0.5 * (c.R[1] + c.R[2]); P.Rm[2] = c.R[3];
   P.Rd[0] = c.R_d[0]; P.Rd[1] = 0.5 * (c.R_d[1] + c.R_d[2]); P.Rd[2] = c.R_d[3];
-  P.max_iter = c.max_iter > 0 ? c.max_iter : 40;
-  P.tol = c.tol > 0.0 ? c.tol : 1e-12;
+  P.max_iter = c.max_iter > 0 ? c.max_iter : 30;
+  P.tol = c.tol > 0.0 ? c.tol : 1e-9;
   P.NSd = P.N | 1;
   const int d = P.NSd;
   int o = 0;

@@ -222,7 +222,26 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
   warp_max(red0);
   double R0 = red0(0);
   if (soft) R0 = fmax(R0, 2.0 * P.qb * th);
-  double rho_d = 1.0;
+  double rho_d = 1.0, prev_stepn = 0.0;
+  // channel scales max(1, |channel|) of the parity metric (x, u, du), from the initial iterate
+  double chs_[10];
+  {
+    LaneVar<double> rc_[10];
+    LANES_BEGIN
+      double m[10] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+      for (int i = lane; i < N; i += 32) {
+        for (int c = 0; c < 6; c++) m[c] = fmax(m[c], fabs(X[c * d + i]));
+        if (i < NS) for (int c = 0; c < 2; c++) {
+          const double up = i ? U[c * d + i - 1] : uic[c];
+          m[6 + c] = fmax(m[6 + c], fabs(U[c * d + i]));
+          m[8 + c] = fmax(m[8 + c], fabs(U[c * d + i] - up) / TT[i]);
+        }
+      }
+      for (int q = 0; q < 10; q++) rc_[q](lane) = m[q];
+    LANES_END
+    for (int q = 0; q < 10; q++) { warp_max(rc_[q]); chs_[q] = 1.0 / rc_[q](0); }
+  }
+  const double mu_floor = 1e-4 * P.tol;
   int m_total = 0;
   {
     for (int sl = 0; sl < RS; sl++) for (int i = 0; i < N; i++) m_total += row_active(P, sl, i) ? 1 : 0;
@@ -265,9 +284,9 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
       for (int c = 0; c < 6; c++) warp_sum(rsig[c]);
       for (int a = 0; a < P.nh; a++) { const int c = P.hidx[a]; sig[a] = X[c * d + N - 1] - in.cen[c] - rsig[c](0); }
     }
-    if (mu < P.tol && rpn < P.tol && rho_d * R0 < P.tol && fabs(rnu) < P.tol) { status = LMPC_SOLVED; break; }
+    if (mu < mu_floor && rpn < mu_floor && rho_d * R0 < mu_floor && fabs(rnu) < mu_floor) { status = LMPC_SOLVED; break; }
 
-    double sigma = 0.0, alpha = 1.0, Pithth_keep = 0.0;
+    double sigma = 0.0, alpha = 1.0, Pithth_keep = 0.0, csc = 1.0;   // csc: safeguard scale of the second-order term
     bool fail = false;
     for (int pass = 0; pass < 2 && !fail; pass++) {
       const double smu = sigma * mu;
@@ -288,7 +307,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
             const double is = 1.0 / s;
             const double dj = y * is;
             const double rp = row_gv(P, sl, i, X, U, TT, th, uic) + s - row_h(P, sl, i, BL, BR);
-            const double t = (smu - (pass ? RScr[sl * d + i] : 0.0)) * is + dj * rp;
+            const double t = (smu - (pass ? csc * RScr[sl * d + i] : 0.0)) * is + dj * rp;
             if (sl < P.nxb) { const int c = P.xb_c[sl]; HX[c * d + i] += dj; CZX[c * d + i] += P.xb_sg[sl] * t; }
             else if (sl < P.nxb + 4) { const int q = sl - P.nxb; dub[q >> 1] += dj; tub[q >> 1] += ((q & 1) ? -t : t); }
             else if (sl < P.nxb + 8) { const int q = sl - P.nxb - 4; dd[q >> 1] += dj; td[q >> 1] += ((q & 1) ? -t : t); }
@@ -317,7 +336,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
       LANES_END
       warp_sum(red0); warp_sum(red1);
       double Dthth = red0(0), cth = red1(0);
-      if (soft) { Dthth += 2.0 * P.qb + yth / th; cth += 2.0 * P.qb * th - (smu - (pass ? corr_th : 0.0)) / th; }
+      if (soft) { Dthth += 2.0 * P.qb + yth / th; cth += 2.0 * P.qb * th - (smu - (pass ? csc * corr_th : 0.0)) / th; }
 
       // ---------- terminal value  P_{N-1}, l_{N-1}
       LANES_BEGIN
@@ -358,7 +377,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
           for (int p = 0; p < KPL; p++) {
             const int k = lane + 32 * p;
             if (k >= K) continue;
-            const double gl = sscv(lane).a[p] - (smu - (pass ? corl(lane).a[p] : 0.0)) / lam(lane).a[p];
+            const double gl = sscv(lane).a[p] - (smu - (pass ? csc * corl(lane).a[p] : 0.0)) / lam(lane).a[p];
             glam(lane).a[p] = gl;
             if (isB(lane).a[p]) { TB[TB_BG + isB(lane).a[p] - 1] = gl; continue; }
             const double om = omg_(lane).a[p];
@@ -650,7 +669,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
             const int k = lane + 32 * p;
             if (k >= K) continue;
             const double l = lam(lane).a[p], y = ylam(lane).a[p];
-            const double tl = (smu - (pass ? corl(lane).a[p] : 0.0)) / l;
+            const double tl = (smu - (pass ? csc * corl(lane).a[p] : 0.0)) / l;
             double dl;
             if (isB(lane).a[p]) dl = qv[isB(lane).a[p]];
             else {
@@ -664,7 +683,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
           }
         LANES_END
       }
-      if (soft) { const double tt = (smu - (pass ? corr_th : 0.0)) / th; dyth = tt - yth - (yth / th) * dth; }
+      if (soft) { const double tt = (smu - (pass ? csc * corr_th : 0.0)) / th; dyth = tt - yth - (yth / th) * dth; }
 
       // ---------- row directions, step length (lane = stage)
       LANES_BEGIN
@@ -675,7 +694,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
             const double s = RSs[sl * d + i], y = RSy[sl * d + i];
             const double rp = row_gv(P, sl, i, X, U, TT, th, uic) + s - row_h(P, sl, i, BL, BR);
             const double dg = row_gv(P, sl, i, DX, DU, TT, dth, zero2);
-            const double rc = s * y - smu + (pass ? RScr[sl * d + i] : 0.0);
+            const double rc = s * y - smu + (pass ? csc * RScr[sl * d + i] : 0.0);
             const double ds = -rp - dg;
             const double dy = (-rc - y * ds) / s;
             if (ds < 0.0) amax = fmin(amax, -s / ds);
@@ -705,6 +724,8 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
         const double mua = (1.0 - aa) * mu + aa * aa * cross * inv_m;
         const double rt = mua / mu;
         sigma = rt * rt * rt;
+        // Mehrotra's second-order term is harmful when the affine step is short: damp it then
+        csc = (aa < 0.2) ? aa : 1.0;
       } else {
         const double tau = 1.0 - fmin(0.005, mu);
         alpha = tau * amax; if (alpha > 1.0) alpha = 1.0;
@@ -724,7 +745,7 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
             const double s = RSs[sl * d + i], y = RSy[sl * d + i];
             const double rp = row_gv(P, sl, i, X, U, TT, th, uic) + s - row_h(P, sl, i, BL, BR);
             const double dg = row_gv(P, sl, i, DX, DU, TT, dth, zero2);
-            const double rc = s * y - smu + RScr[sl * d + i];
+            const double rc = s * y - smu + csc * RScr[sl * d + i];
             const double ds = -rp - dg;
             const double dy = (-rc - y * ds) / s;
             RSs[sl * d + i] = s + alpha * ds; RSy[sl * d + i] = y + alpha * dy;
@@ -744,6 +765,26 @@ LMPC_DEV void lmpc_qp_solve_warp(const LmpcQpParams& P, const LmpcQpIn& in, doub
       LANES_END
       if (soft) { th += alpha * dth; yth += alpha * dyth; }
       rho_d *= (1.0 - alpha);
+      // step-based acceptance: the primal step per channel, relative to max(1, |channel|), with a
+      // geometric-tail estimate of what is still to come
+      LANES_BEGIN
+        double m = 0.0;
+        for (int i = lane; i < N; i += 32) {
+          for (int c = 0; c < 6; c++) m = fmax(m, fabs(DX[c * d + i]) * chs_[c]);
+          if (i < NS) for (int c = 0; c < 2; c++) {
+            const double dup = i ? DU[c * d + i - 1] : 0.0;
+            m = fmax(m, fabs(DU[c * d + i]) * chs_[6 + c]);
+            m = fmax(m, fabs(DU[c * d + i] - dup) / TT[i] * chs_[8 + c]);
+          }
+        }
+        red0(lane) = m;
+      LANES_END
+      warp_max(red0);
+      const double stepn = alpha * red0(0);
+      const double ratio = (prev_stepn > 0.0) ? stepn / prev_stepn : 1.0;
+      const double est = (ratio < 0.9) ? stepn * ratio / (1.0 - ratio) : 1e300;
+      prev_stepn = stepn;
+      if (stepn < P.tol && est < P.tol && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) { status = LMPC_SOLVED; it++; break; }
     }
   }  // iterations
 

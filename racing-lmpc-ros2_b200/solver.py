@@ -74,6 +74,16 @@ class BatchedRacingMPC:
     def synchronize(self):
         _check(self.lib, self._h, self.lib.lmpc_synchronize(self._h), "lmpc_synchronize")
 
+    def set_timing(self, enable=True):
+        _check(self.lib, self._h, self.lib.lmpc_set_timing(self._h, 1 if enable else 0), "lmpc_set_timing")
+
+    def kernel_ms(self):
+        """(ms_linearise, ms_ss_query, ms_qp) summed over the solves recorded since set_timing, and their count."""
+        ms = (C.c_double * 3)()
+        n = C.c_int()
+        _check(self.lib, self._h, self.lib.lmpc_get_kernel_ms(self._h, ms, C.byref(n)), "lmpc_get_kernel_ms")
+        return (ms[0], ms[1], ms[2]), n.value
+
     @property
     def launch_count(self):
         return int(self.lib.lmpc_launch_count(self._h))

@@ -1,0 +1,232 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, against the committed golden vectors, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Tolerance: BASELINE.json's north star asks <= 1e-6 relative fp64 on
+X, U, dU; the tests assert that and report the (much smaller) typical figure."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES, make_case, make_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-6   # north_star: "matching reference trajectories to <= 1e-6 relative fp64"
+
+
+def _mpc(pkg, name, max_batch, tol=None, N=None, with_laps=True):
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    veh, cfg, track, mode = make_case(pkg, name, tol, N)
+    m = BatchedRacingMPC(veh, cfg, max_batch=max_batch)
+    if cfg["learning"] and with_laps:
+        for l in pkg.workload.load_laps():
+            m.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    return m, veh, cfg, track, mode
+
+
+def test_native_library_is_what_runs(pkg):
+    """The solve goes through csrc/liblmpc_b200.so (in-tree) and launches kernels on the GPU."""
+    from racing_lmpc_ros2_b200 import binding
+    m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 8)
+    assert os.path.samefile(binding.LIB_PATH, os.path.join(os.path.dirname(binding.__file__), "csrc", "liblmpc_b200.so"))
+    batch = pkg.workload.make_batch(veh, cfg, 8, 1, track, pkg.workload.load_laps(), mode=mode)
+    n0 = m.launch_count
+    out = m.solve(batch)
+    assert m.launch_count - n0 == 3          # linearise, safe-set query, QP
+    assert (out["status"] == 0).all()
+    with open("/proc/self/maps") as f:
+        assert "liblmpc_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("name", ["barc_lmpc", "iac_tracking"])
+def test_linearise_matches_oracle(pkg, name):
+    m, veh, cfg, track, mode = _mpc(pkg, name, 8, with_laps=False)
+    o, *_ = make_oracle(pkg, name, with_laps=False)
+    rng = np.random.default_rng(0)
+    n = 512
+    if name == "iac_tracking":
+        x = np.column_stack([rng.uniform(0, 2800, n), rng.uniform(-3, 3, n), rng.uniform(-.1, .1, n), rng.uniform(5, 90, n), rng.uniform(-3, 3, n), rng.uniform(-.5, .5, n)])
+        u = np.column_stack([rng.uniform(-10, 5, n), rng.uniform(-.2, .2, n)]); kap = rng.uniform(-.05, .05, n)
+    else:
+        x = np.column_stack([rng.uniform(0, 17, n), rng.uniform(-.3, .3, n), rng.uniform(-.3, .3, n), rng.uniform(.2, 3, n), rng.uniform(-.5, .5, n), rng.uniform(-2, 2, n)])
+        u = np.column_stack([rng.uniform(-.01, .01, n), rng.uniform(-.3, .3, n)]); kap = rng.uniform(-1, 1, n)
+    dt = rng.uniform(0.01, 0.05, n)
+    A, B, g, xn = m.linearise(x, u, kap, dt)
+    xn2 = m.discrete_dynamics(x, u, kap, dt)
+    worst = 0.0
+    for i in range(n):
+        A2, B2, g2, x2 = o.linearise(x[i], u[i], kap[i], dt[i])
+        sc = max(1.0, np.abs(x[i]).max())
+        worst = max(worst, np.abs(A[i] - A2).max() / max(1, np.abs(A2).max()), np.abs(B[i] - B2).max() / max(1, np.abs(B2).max()),
+                    np.abs(g[i] - g2).max() / sc, np.abs(xn[i] - x2).max() / sc, np.abs(xn2[i] - x2).max() / sc)
+        assert np.array_equal(A[i][:, 0], np.eye(6)[:, 0])
+    assert worst < 1e-12, worst   # analytic partials vs dual numbers, both fp64
+
+
+def test_safe_set_query_is_bit_exact(pkg, laps, barc_track):
+    m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 8)
+    o, *_ = make_oracle(pkg, "barc_lmpc")
+    rng = np.random.default_rng(5)
+    q = np.column_stack([rng.uniform(-20, 40, 300), rng.uniform(-.6, .6, 300)])
+    q[:8, 0] = laps[2]["x"][:8, 0]; q[:8, 1] = laps[2]["x"][:8, 1]      # queries on top of stored points
+    for mt, pl in ((96, 32), (96, 40), (50, 32), (10, 3), (1, 1)):
+        sx, sj = m.ss_query(q, max_total=mt, per_lap=pl)
+        for i in range(len(q)):
+            ox, oj = o.ss_query(q[i, 0], q[i, 1], max_total=mt, per_lap=pl)
+            assert np.array_equal(sx[i], ox) and np.array_equal(sj[i], oj), (mt, pl, i)
+
+
+def test_safe_set_edge_cases(pkg, laps, barc_track):
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    from oracle import Oracle
+    veh = pkg.configs.BARC_VEHICLE
+    L = barc_track["length"]
+    # circular buffer of 2 laps; one-lap padding; clustered points (exact fallback path); duplicate keys
+    cfg = pkg.configs.barc_lmpc_config(20)
+    m = BatchedRacingMPC(veh, dict(cfg, max_lap_stored=2), max_batch=4); o = Oracle(veh, dict(cfg, max_lap_stored=2))
+    for l in laps:
+        m.add_lap(l["x"], l["u"], l["k"], l["t"], L); o.add_lap(l["x"], l["u"], l["k"], l["t"], L)
+    assert m.num_laps() == 2
+    sx, sj = m.ss_query([[3.0, 0.0]]); ox, oj = o.ss_query(3.0, 0.0)
+    assert sx.shape[1] == 64 and np.array_equal(sx[0], ox) and np.array_equal(sj[0], oj)
+    n = 400
+    x = np.zeros((n, 6)); x[:, 0] = np.linspace(0, 40, n); x[::32, 0] = 5.0 + 1e-3 * np.arange(len(x[::32])); x[::32, 1] = 0.01
+    x[7] = x[6]                                   # an exact duplicate key
+    m = BatchedRacingMPC(veh, cfg, max_batch=4); o = Oracle(veh, cfg)
+    m.add_lap(x, np.zeros((n, 2)), np.zeros(n), np.arange(float(n)), 1000.0); o.add_lap(x, np.zeros((n, 2)), np.zeros(n), np.arange(float(n)), 1000.0)
+    for qs in (5.0, float(x[6, 0]), 39.9, -3.0):
+        sx, sj = m.ss_query([[qs, 0.0]], max_total=32, per_lap=32); ox, oj = o.ss_query(qs, 0.0, max_total=32, per_lap=32)
+        assert np.array_equal(sx[0], ox) and np.array_equal(sj[0], oj)
+    m.clear_safe_set()
+    assert m.num_laps() == 0
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_solve_matches_golden_vectors(pkg, name):
+    z = np.load(os.path.join(GOLD, f"golden_{name}.npz"))
+    batch = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
+    m, veh, cfg, track, mode = _mpc(pkg, name, 16)
+    out = m.solve(batch)
+    assert (out["status"] == 0).all()
+    eX, eU, eD = relerr(out["X_optm"], z["out_X"]), relerr(out["U_optm"], z["out_U"]), relerr(out["dU_optm"], z["out_dU"])
+    assert max(eX, eU, eD) < TOL, (eX, eU, eD)
+    assert np.abs(out["cost"] - z["out_cost"]).max() < 1e-7 * max(1, np.abs(z["out_cost"]).max())
+    if cfg["learning"]:   # lambda is not unique, SS*lambda is
+        sslam = np.einsum("bkc,bk->bc", out["ss_x"], out["convex_combi_optm"])
+        assert np.abs(sslam - z["out_sslam"]).max() < 1e-6 * max(1, np.abs(z["out_sslam"]).max())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_solve_matches_dense_oracle(pkg, name):
+    """Same seeded inputs through the CUDA path and the certified dense oracle (IPM + polish + KKT)."""
+    m, veh, cfg, track, mode = _mpc(pkg, name, 32)
+    od, *_ = make_oracle(pkg, name, tol=1e-11)
+    batch = pkg.workload.make_batch(veh, cfg, 24, 0xD15E, track, pkg.workload.load_laps(), mode=mode)
+    out = m.solve(batch)
+    worst, n = 0.0, 0
+    for b in range(24):
+        d = od.step(pkg.workload.instance(batch, b), impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        assert out["status"][b] == 0
+        worst = max(worst, relerr(out["X_optm"][b], d["X"]), relerr(out["U_optm"][b], d["U"]), relerr(out["dU_optm"][b], d["dU"]))
+        assert abs(out["cost"][b] - d["cost"]) < 1e-7 * max(1, abs(d["cost"]))
+        # the GPU point is feasible for the dense QP and attains the certified optimal value
+        cost, inf = od.check_candidate(pkg.workload.instance(batch, b), out["X_optm"][b], out["U_optm"][b], out["dU_optm"][b],
+                                       out["convex_combi_optm"][b] if cfg["learning"] else None)
+        assert inf < 1e-8 and cost <= d["cost"] + 1e-7 * max(1, abs(d["cost"]))
+        n += 1
+    assert n >= 16
+    assert worst < TOL, worst
+    print(f"[{name}] worst relative error vs dense oracle over {n} instances: {worst:.2e}")
+
+
+def test_full_size_batch_properties_config2(pkg):
+    """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): port parity on a sample plus
+    size-independent invariants on every instance."""
+    m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 1024)
+    o, *_ = make_oracle(pkg, "barc_lmpc", tol=1e-10)
+    batch = pkg.workload.make_batch(veh, cfg, 1024, 0xB200 + 2, track, pkg.workload.load_laps(), mode=mode)
+    out = m.solve(batch)
+    assert (out["status"] == 0).mean() > 0.995
+    ok = out["status"] == 0
+    X, U, dU, lam = out["X_optm"], out["U_optm"], out["dU_optm"], out["convex_combi_optm"]
+    assert np.abs(X[:, 0] - batch["x_ic"]).max() == 0.0                         # x_0 = x_ic
+    up = np.concatenate([batch["u_ic"][:, None, :], U[:, :-1]], axis=1)
+    assert np.abs(U - (up + batch["T_ref"][:, :, None] * dU))[ok].max() < 1e-12   # rate rows
+    assert (U[ok] <= np.array(cfg["u_max"]) + 1e-9).all() and (U[ok] >= np.array(cfg["u_min"]) - 1e-9).all()
+    assert np.abs(lam[ok].sum(axis=1) - 1).max() < 1e-9 and lam[ok].min() >= 0.0  # simplex
+    assert (out["ss_j"][:, 0] >= out["ss_j"].min(axis=1) - 1e-12).all()
+    # linear dynamics rows hold with the GPU's own linearisation
+    Xr = batch["X_ref"].copy()
+    for b in range(0, 1024, 64):
+        for j in range(cfg["N"]):
+            Xr[b, j, 0] = o.align_abscissa(Xr[b, j, 0], batch["x_ic"][b, 0], batch["total_length"][b])
+        A, Bm, g, _ = m.linearise(Xr[b, :-1], batch["U_ref"][b], batch["curvatures"][b, :-1], batch["T_ref"][b])
+        pred = np.einsum("irc,ic->ir", A, X[b, :-1]) + np.einsum("irc,ic->ir", Bm, U[b]) + g
+        assert np.abs(pred - X[b, 1:]).max() < 1e-9 * max(1, np.abs(X[b]).max())
+    ref = o.step_batch({k: v[:128] for k, v in batch.items()}, impl="port", nthreads=os.cpu_count() or 4)
+    e = max(relerr(X[:128], ref["X"]), relerr(U[:128], ref["U"]), relerr(dU[:128], ref["dU"]))
+    assert e < TOL, e
+    # idempotence / determinism: the same batch again gives bit-identical results
+    out2 = m.solve(batch)
+    assert np.array_equal(out2["X_optm"], X) and np.array_equal(out2["iters"], out["iters"])
+
+
+def test_full_size_batch_config3_iac_tracking(pkg):
+    """BASELINE config 3 (IAC Putnam tracking, N=40, batch 4096)."""
+    m, veh, cfg, track, mode = _mpc(pkg, "iac_tracking", 4096)
+    o, *_ = make_oracle(pkg, "iac_tracking", tol=1e-10)
+    batch = pkg.workload.make_batch(veh, cfg, 4096, 0xB200 + 3, track, pkg.workload.load_laps(), mode=mode)
+    out = m.solve(batch)
+    assert (out["status"] == 0).mean() > 0.99
+    ref = o.step_batch({k: v[:96] for k, v in batch.items()}, impl="port", nthreads=os.cpu_count() or 4)
+    sel = (out["status"][:96] == 0) & (ref["status"] == 0)
+    e = max(relerr(out["X_optm"][:96][sel], ref["X"][sel]), relerr(out["U_optm"][:96][sel], ref["U"][sel]), relerr(out["dU_optm"][:96][sel], ref["dU"][sel]))
+    assert e < TOL, e
+
+
+def test_failed_instances_do_not_poison_the_batch(pkg):
+    m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 16)
+    batch = pkg.workload.make_batch(veh, cfg, 16, 9, track, pkg.workload.load_laps(), mode=mode)
+    good = m.solve(batch)
+    bad = {k: v.copy() for k, v in batch.items()}
+    bad["x_ic"][3, 3] = 0.01                      # v_x below x_min: infeasible x_0 box (racing_mpc.cpp:147)
+    bad["x_ic"][7, :] = np.nan
+    out = m.solve(bad)
+    assert out["status"][3] == 2 and out["status"][7] != 0
+    keep = [i for i in range(16) if i not in (3, 7)]
+    assert np.array_equal(out["X_optm"][keep], good["X_optm"][keep])
+    # learning mode without a safe set: every instance reports NO_SAFE_SET
+    m2, *_ = _mpc(pkg, "barc_lmpc", 16, with_laps=False)
+    assert (m2.solve(batch)["status"] == 3).all()
+
+
+def test_device_path_matches_host_path(pkg):
+    import torch
+    m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 64)
+    batch = pkg.workload.make_batch(veh, cfg, 64, 21, track, pkg.workload.load_laps(), mode=mode)
+    host = m.solve(batch)
+    s = torch.cuda.Stream()
+    m.set_stream(s)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in batch.items()}
+    with torch.cuda.stream(s):
+        out = m.solve(dev)
+    s.synchronize()
+    m.set_stream(None)
+    for k in ("X_optm", "U_optm", "dU_optm", "convex_combi_optm", "cost", "ss_x", "ss_j"):
+        assert np.array_equal(out[k].cpu().numpy(), host[k]), k
+
+
+def test_horizon_is_a_runtime_parameter(pkg):
+    """N is a parameter of RacingMPCConfig (racing_mpc_config.hpp:47): the shipped YAMLs use 40 / 60."""
+    for name, N in (("barc_lmpc", 40), ("barc_tracking", 60), ("barc_lmpc", 5)):
+        m, veh, cfg, track, mode = _mpc(pkg, name, 8, N=N)
+        o, *_ = make_oracle(pkg, name, tol=1e-10, N=N)
+        batch = pkg.workload.make_batch(veh, cfg, 6, 3, track, pkg.workload.load_laps(), mode=mode)
+        out = m.solve(batch)
+        ref = o.step_batch(batch, impl="port", nthreads=4)
+        sel = (out["status"] == 0) & (ref["status"] == 0)
+        assert sel.sum() >= 4
+        e = max(relerr(out["X_optm"][sel], ref["X"][sel]), relerr(out["U_optm"][sel], ref["U"][sel]), relerr(out["dU_optm"][sel], ref["dU"][sel]))
+        assert e < TOL, (name, N, e)
