@@ -92,9 +92,19 @@ extern "C" const char* lmpc_status_string(int s) {
 extern "C" const char* lmpc_last_error(const lmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int64_t lmpc_launch_count(const lmpc_handle* h) { return h ? h->launches : 0; }
 
-template <int KPL>
+// dispatch over the instantiated (warps per instance, columns per lane) pairs
+#define LMPC_QP_DISPATCH(NWv, KPLv, CALL)                                            \
+  do {                                                                               \
+    if (NWv == 1) { if (KPLv <= 1) { CALL(1, 1); } else if (KPLv == 2) { CALL(1, 2); } else if (KPLv == 3) { CALL(1, 3); } else { CALL(1, 4); } } \
+    else if (NWv == 2) { if (KPLv <= 1) { CALL(2, 1); } else { CALL(2, 2); } }         \
+    else { CALL(4, 1); }                                                             \
+  } while (0)
+
 static int set_qp_attr(lmpc_handle* h) {
-  CK(cudaFuncSetAttribute(lmpc_qp_kernel<KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem));
+  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw));
+#define SETATTR(NW_, KPL_) CK(cudaFuncSetAttribute(lmpc_qp_kernel<NW_, KPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem))
+  LMPC_QP_DISPATCH(nw, kpl, SETATTR);
+#undef SETATTR
   return LMPC_OK;
 }
 
@@ -108,13 +118,17 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
   if (vehicle->integrator != 0 && vehicle->integrator != 1) return LMPC_ERR_INVALID;
   lmpc_handle* h = new lmpc_handle();
   h->cfg = *config; h->veh = *vehicle; h->device = device_ordinal; h->max_batch = max_batch;
-  int rc = lmpc_make_qp_params(*config, *vehicle, &h->P);
+  // warps per MPC instance: 1, 2 or 4 (LMPC_WARPS_PER_INSTANCE overrides; 4 needs K <= 128, 2 needs K <= 256)
+  int nw = 1;   // measured fastest on B200 at B = 1024 and 8192 (profiles/); 2 and 4 are kept selectable
+  if (const char* e = getenv("LMPC_WARPS_PER_INSTANCE")) nw = atoi(e);
+  if (nw != 1 && nw != 2 && nw != 4) nw = 1;
+  if (config->learning && nw == 4 && config->num_ss_pts > 128) nw = 2;
+  int rc = lmpc_make_qp_params(*config, *vehicle, &h->P, nw);
   if (rc != LMPC_OK) { delete h; return rc; }
   h->M = lmpc_make_model(*vehicle);
   if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return LMPC_ERR_NO_DEVICE; }
-  h->qp_smem = sizeof(double) * (size_t)(h->P.total + (h->P.learning ? h->P.K : 0));
-  const int kpl = (h->P.K + 31) / 32;
-  if (kpl <= 1) rc = set_qp_attr<1>(h); else if (kpl == 2) rc = set_qp_attr<2>(h); else if (kpl == 3) rc = set_qp_attr<3>(h); else rc = set_qp_attr<4>(h);
+  h->qp_smem = sizeof(double) * (size_t)h->P.total;
+  rc = set_qp_attr(h);
   if (rc != LMPC_OK) { fprintf(stderr, "lmpc_create: %s\n", h->err.c_str()); delete h; return rc; }
   const size_t B = (size_t)max_batch, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)std::max(h->P.K, 1);
   rc = dev_reserve(h, h->ws_abg, sizeof(double) * 54 * NS * B);
@@ -396,9 +410,11 @@ extern "C" int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, cons
 }
 
 // ------------------------------------------------------------------------------------------ solve
-template <int KPL>
 static void launch_qp(lmpc_handle* h, const LmpcQpBatch& a) {
-  lmpc_qp_kernel<KPL><<<a.B, 32, h->qp_smem, h->stream>>>(h->P, a);
+  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nblocks = a.B;
+#define LAUNCH(NW_, KPL_) lmpc_qp_kernel<NW_, KPL_><<<nblocks, 32 * NW_, h->qp_smem, h->stream>>>(h->P, a)
+  LMPC_QP_DISPATCH(nw, kpl, LAUNCH);
+#undef LAUNCH
 }
 
 extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int memspace) {
@@ -472,8 +488,7 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
   a.lam = (memspace == LMPC_MEM_HOST) ? (out->convex_combi_optm ? dout_d[3] : nullptr) : out->convex_combi_optm;
   a.cost = (memspace == LMPC_MEM_HOST) ? (out->cost ? dout_d[6] : nullptr) : out->cost;
   a.status = d_status; a.iters = d_iters; a.ss_count = tab.count; a.B = B;
-  const int kpl = (h->P.K + 31) / 32;
-  if (kpl <= 1) launch_qp<1>(h, a); else if (kpl == 2) launch_qp<2>(h, a); else if (kpl == 3) launch_qp<3>(h, a); else launch_qp<4>(h, a);
+  launch_qp(h, a);
   h->launches++;
   CK(cudaGetLastError());
   if (tev) { CK(cudaEventRecord(tev[3], h->stream)); h->tcount++; }

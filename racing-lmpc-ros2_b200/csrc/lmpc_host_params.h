@@ -23,7 +23,7 @@ static inline bool lmpc_finite_bound(double b) { return isfinite(b) && fabs(b) <
 
 // Validates the configuration and fills the kernel parameter block (row structure, merged boxes,
 // shared-memory layout).  Returns LMPC_OK or LMPC_ERR_INVALID.
-static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehicle_params& v, LmpcQpParams* out) {
+static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehicle_params& v, LmpcQpParams* out, int NW = 1) {
   LmpcQpParams P;
   memset(&P, 0, sizeof P);
   if (c.N < 3 || c.N > LMPC_MAX_N) return LMPC_ERR_INVALID;
@@ -46,8 +46,9 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   for (int k = 0; k < 6; k++) P.chs[k] = P.hull_slack ? c.convex_hull_slack[k] : 0.0;
   P.nxb = 0;
   for (int k = 0; k < 6; k++) {
-    if (lmpc_finite_bound(c.x_max[k])) { P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = 1.0; P.xb_h[P.nxb] = c.x_max[k]; P.nxb++; }
-    if (lmpc_finite_bound(c.x_min[k])) { P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = -1.0; P.xb_h[P.nxb] = -c.x_min[k]; P.nxb++; }
+    P.xslot[k][0] = P.xslot[k][1] = -1;
+    if (lmpc_finite_bound(c.x_max[k])) { P.xslot[k][0] = P.nxb; P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = 1.0; P.xb_h[P.nxb] = c.x_max[k]; P.nxb++; }
+    if (lmpc_finite_bound(c.x_min[k])) { P.xslot[k][1] = P.nxb; P.xb_c[P.nxb] = k; P.xb_sg[P.nxb] = -1.0; P.xb_h[P.nxb] = -c.x_min[k]; P.nxb++; }
   }
   P.RS = P.nxb + 10;
   // merged u box: RacingMPC primal bounds (racing_mpc.cpp:148) and the model's actuator rows
@@ -70,17 +71,21 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   P.max_iter = c.max_iter > 0 ? c.max_iter : 30;
   P.tol = c.tol > 0.0 ? c.tol : 1e-9;
   P.NSd = P.N | 1;
+  if (NW != 1 && NW != 2 && NW != 4) return LMPC_ERR_INVALID;
+  if (P.learning && (P.K + 32 * NW - 1) / (32 * NW) > LMPC_KPL_MAX) return LMPC_ERR_INVALID;
+  P.NW = NW;
   const int d = P.NSd;
   int o = 0;
   auto take = [&](int n) { const int at = o; o += (n + 1) & ~1; return at; };   // keep 16-byte alignment
   P.oABG = take(54 * P.NS);
-  P.oS = take(P.RS * d); P.oY = take(P.RS * d); P.oCR = take(P.RS * d);
-  P.oX = take(6 * d); P.oU = take(2 * d); P.oDX = take(6 * d); P.oDU = take(2 * d);
-  P.oHX = take(6 * d); P.oCZX = take(6 * d); P.oCZU = take(2 * d); P.oCZTH = take(d); P.oCW = take(2 * d);
-  P.oEE = take(3 * d); P.oUQ = take(3 * d);
+  P.oS = take(P.RS * d); P.oY = take(P.RS * d); P.oISY = take(P.RS * d);
+  P.oX = take(6 * d); P.oU = take(2 * d);
+  P.oDXA = take(6 * d); P.oDUA = take(2 * d); P.oDXF = take(6 * d); P.oDUF = take(2 * d);
+  P.oCZX = take(6 * d); P.oCZTH = take(d); P.oGUD = take(8 * d);
   P.oFAC = take(20 * P.NS); P.oKFF = take(6 * P.NS);
-  P.oBL = take(d); P.oBR = take(d); P.oVREF = take(d); P.oT = take(d);
+  P.oBL = take(d); P.oBR = take(d); P.oVREF = take(d); P.oIT = take(d); P.oT = P.oIT;
   P.oPM = take(64); P.oL1 = take(8); P.oLTH = take(8); P.oMAB = take(48); P.oAXBW = take(16); P.oYY = take(64);
+  P.oRED = take(NW > 1 ? NW * LMPC_NRED : 0);
   P.oTERM = take(TB_SIZE);
   P.total = o;
   *out = P;

@@ -2,7 +2,7 @@
 //
 //   K1 lmpc_linearise_kernel   thread per (instance, stage): abscissa alignment + RK4 Jacobians -> A,B,g
 //   K2 lmpc_ss_query_kernel    warp per (instance, lap): exact k-NN in the safe-set slab + cost-to-go gather
-//   K3 lmpc_qp_kernel          warp per instance: interior-point / Riccati solve in shared memory
+//   K3 lmpc_qp_kernel          warp group (1, 2 or 4 warps = one CTA) per instance: interior-point / Riccati solve in shared memory
 //
 // Batch arrays are instance-major, so a warp's (or thread's) reads of its own instance are contiguous.
 #pragma once
@@ -90,7 +90,7 @@ __global__ void lmpc_ss_query_kernel(LmpcLapTable tab, int B, const double* __re
                      j == tab.n_used - 1, tab.count, pad_to);
 }
 
-// ---- K3: one warp (= one CTA) per instance
+// ---- K3: one CTA of NW warps per instance
 struct LmpcQpBatch {
   const double *x_ic, *u_ic, *U0, *T_ref, *bl, *br, *vref, *ABg, *ssx, *ssj, *cen;
   double *X, *U, *dU, *lam, *cost;
@@ -99,30 +99,24 @@ struct LmpcQpBatch {
   int B;
 };
 
-template <int KPL>
-__global__ void __launch_bounds__(32) lmpc_qp_kernel(const __grid_constant__ LmpcQpParams P, const __grid_constant__ LmpcQpBatch a) {
+template <int NW, int KPL>
+__global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_constant__ LmpcQpParams P, const __grid_constant__ LmpcQpBatch a) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x;
   if (b >= a.B) return;
   const int N = P.N, NS = P.NS, K = P.K;
-  // J - J[0] (racing_mpc.cpp:280) staged in the tail of the scratch: the solver reads it once at start-up
-  double* ssc = sm + P.total;
-  if (P.learning) {
-    const double j0 = a.ssj[(size_t)K * b];
-    for (int k = threadIdx.x; k < K; k += 32) ssc[k] = a.ssj[(size_t)K * b + k] - j0;
-    __syncwarp();
-  }
   LmpcQpIn in;
   in.x_ic = a.x_ic + 6 * (size_t)b; in.u_ic = a.u_ic + 2 * (size_t)b;
   in.U0 = a.U0 + (2 * (size_t)NS) * b; in.T = a.T_ref + (size_t)NS * b;
   in.bl = a.bl + (size_t)N * b; in.br = a.br + (size_t)N * b; in.vref = a.vref + (size_t)N * b;
   in.ABg = a.ABg + (54 * (size_t)NS) * b;
   in.ssx = P.learning ? a.ssx + (6 * (size_t)K) * b : nullptr;
-  in.ssc = ssc; in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count;
+  in.ssj = P.learning ? a.ssj + (size_t)K * b : nullptr;
+  in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count;
   LmpcQpOut out;
   out.X = a.X + (6 * (size_t)N) * b; out.U = a.U + (2 * (size_t)NS) * b; out.dU = a.dU + (2 * (size_t)NS) * b;
   out.lam = (a.lam && P.learning) ? a.lam + (size_t)K * b : nullptr;
   out.cost = a.cost ? a.cost + b : nullptr;
   out.status = a.status + b; out.iters = a.iters + b;
-  lmpc_qp_solve_warp<KPL>(P, in, sm, out);
+  lmpc_qp_solve<NW, KPL>(P, in, sm, out);
 }

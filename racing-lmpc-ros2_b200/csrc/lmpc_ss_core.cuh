@@ -85,7 +85,7 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
     const int col = lap.out_off + r;
     if (col < max_total) {
       LANES_BEGIN
-        const int src = lap.canon[wi];
+        const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
         if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
         else if (lane == 6) ss_j[col] = lap.J[src];
       LANES_END
@@ -114,7 +114,7 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
       if (col < max_total) {
         const int wi = last_i;
         LANES_BEGIN
-          const int src = lap.canon[wi];
+          const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
           if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
           else if (lane == 6) ss_j[col] = lap.J[src];
         LANES_END

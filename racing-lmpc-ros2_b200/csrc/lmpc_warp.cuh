@@ -1,15 +1,16 @@
-// lmpc_warp.cuh -- warp-synchronous building blocks of the solver kernels.
+// lmpc_warp.cuh -- SIMT building blocks of the solver kernels.
 //
-// The QP kernel gives one warp to one MPC instance.  Its code is written as a sequence of
-// *phases*: inside LANES_BEGIN/LANES_END every lane runs the body with its own `lane`, then the
-// warp synchronises (shared memory written in one phase is read in the next).  Values that
-// live in a lane's registers across phases are LaneVar<T>.  Cross-lane reductions are the
-// warp_* collectives, called between phases.
+// The QP kernel gives one *warp group* (NW warps = NT threads, one CTA) to one MPC instance.  Its code
+// is a sequence of *phases*: inside GLANES_BEGIN/GLANES_END every thread of the group runs the body
+// with its own `lane` (0..NT-1), then the group synchronises (shared memory written in one phase is
+// read in the next).  Values that live in a thread's registers across phases are LaneVar<T, NT>.
+// Cross-lane reductions are the group_* collectives, called between phases.  Code outside phases is
+// group-uniform (every thread computes the same value).
 //
-// Under nvcc this is ordinary SIMT code (__syncwarp, shuffles).  With -DLMPC_EMULATE the same
-// source compiles with g++ into a lane-loop emulator (tests/emu) so that the kernel's logic can
-// be checked against the CPU oracle on a machine without a GPU.  The emulator is a test
-// artefact: it is never linked into liblmpc_b200.so and nothing in the product falls back to it.
+// Under nvcc this is ordinary SIMT code (__syncwarp / bar.sync, shuffles).  With -DLMPC_EMULATE the
+// same source compiles with g++ into a lane-loop emulator (tests/emu) so that the kernel's logic can
+// be checked against the CPU oracle on a machine without a GPU.  The emulator is a test artefact: it
+// is never linked into liblmpc_b200.so and nothing in the product falls back to it.
 #pragma once
 
 #include <math.h>
@@ -19,14 +20,16 @@
 // ------------------------------------------------------------------ lane-loop emulation (tests)
 #define LMPC_DEV static inline
 #define LMPC_HD static inline
-extern int g_lmpc_emu_reverse;  // run lanes 31..0 instead of 0..31 (order-independence check)
-#define LANES_BEGIN                                      \
-  for (int lane_it_ = 0; lane_it_ < 32; ++lane_it_) {    \
-    const int lane = g_lmpc_emu_reverse ? 31 - lane_it_ : lane_it_;
-#define LANES_END }
-template <class T>
+extern int g_lmpc_emu_reverse;  // run lanes NT-1..0 instead of 0..NT-1 (order-independence check)
+#define GLANES_BEGIN(NT)                                      \
+  for (int lane_it_ = 0; lane_it_ < (NT); ++lane_it_) {       \
+    const int lane = g_lmpc_emu_reverse ? (NT) - 1 - lane_it_ : lane_it_;
+#define GLANES_END(NW) }
+#define GROUP_SYNC(NW)
+#define LANE0_ONLY(stmt) { stmt; }
+template <class T, int NT = 32>
 struct LaneVar {
-  T v[32];
+  T v[NT];
   inline T& operator()(int l) { return v[l]; }
   inline const T& operator()(int l) const { return v[l]; }
 };
@@ -34,13 +37,18 @@ struct LaneVar {
 // ------------------------------------------------------------------ CUDA
 #define LMPC_DEV __device__ __forceinline__
 #define LMPC_HD __host__ __device__ __forceinline__
-#define LANES_BEGIN \
-  {                 \
-    const int lane = (int)(threadIdx.x & 31u);
-#define LANES_END \
-  }               \
-  __syncwarp();
-template <class T>
+#define GROUP_SYNC(NW)                       \
+  do {                                       \
+    if ((NW) == 1) __syncwarp(); else __syncthreads(); \
+  } while (0)
+#define GLANES_BEGIN(NT) \
+  {                      \
+    const int lane = (int)threadIdx.x;
+#define GLANES_END(NW) \
+  }                    \
+  GROUP_SYNC(NW);
+#define LANE0_ONLY(stmt) { if (threadIdx.x == 0u) { stmt; } }
+template <class T, int NT = 32>
 struct LaneVar {
   T v;
   __device__ __forceinline__ T& operator()(int) { return v; }
@@ -48,79 +56,134 @@ struct LaneVar {
 };
 #endif
 
-// ------------------------------------------------------------------ collectives
+// single-warp spellings (the safe-set kernel runs one independent item per warp, several warps per block)
 #if defined(LMPC_EMULATE)
-LMPC_DEV void warp_sum(LaneVar<double>& x) {
-  // same pairwise (butterfly) order as the shuffle version so that results are bit-identical
-  double t[32];
-  for (int l = 0; l < 32; ++l) t[l] = x.v[l];
-  for (int off = 16; off >= 1; off >>= 1) {
-    double n[32];
-    for (int l = 0; l < 32; ++l) n[l] = t[l] + t[l ^ off];
-    for (int l = 0; l < 32; ++l) t[l] = n[l];
+#define LANES_BEGIN GLANES_BEGIN(32)
+#define LANES_END GLANES_END(1)
+#else
+#define LANES_BEGIN \
+  {                 \
+    const int lane = (int)(threadIdx.x & 31u);
+#define LANES_END \
+  }               \
+  __syncwarp();
+#endif
+
+// ------------------------------------------------------------------ group collectives over NV values
+// Every thread ends with the reduction over all NT = 32*NW lanes.  Order of the additions: butterfly
+// inside each warp, then warps 0..NW-1 in sequence -- identical in the CUDA and the emulated build, so
+// results are bit-identical.  `scratch` needs NW*NV doubles of shared memory when NW > 1.
+enum { LMPC_RED_SUM = 0, LMPC_RED_MAX = 1, LMPC_RED_MIN = 2 };
+
+LMPC_HD double lmpc_red_op(int op, double a, double b) { return op == LMPC_RED_SUM ? a + b : (op == LMPC_RED_MAX ? fmax(a, b) : fmin(a, b)); }
+
+#if defined(LMPC_EMULATE)
+template <int NW, int NV>
+LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV], double* /*scratch*/) {
+  for (int q = 0; q < NV; q++) {
+    double wres[NW];
+    for (int w = 0; w < NW; w++) {
+      double t[32];
+      for (int l = 0; l < 32; ++l) t[l] = x[q].v[32 * w + l];
+      for (int off = 16; off >= 1; off >>= 1) {
+        double n[32];
+        for (int l = 0; l < 32; ++l) n[l] = lmpc_red_op(op[q], t[l], t[l ^ off]);
+        for (int l = 0; l < 32; ++l) t[l] = n[l];
+      }
+      wres[w] = t[0];
+    }
+    double r = wres[0];
+    for (int w = 1; w < NW; w++) r = lmpc_red_op(op[q], r, wres[w]);
+    for (int l = 0; l < 32 * NW; ++l) x[q].v[l] = r;
   }
-  for (int l = 0; l < 32; ++l) x.v[l] = t[l];
 }
-LMPC_DEV void warp_min(LaneVar<double>& x) {
-  double m = x.v[0];
-  for (int l = 1; l < 32; ++l) m = fmin(m, x.v[l]);
-  for (int l = 0; l < 32; ++l) x.v[l] = m;
+// arg-max / arg-min on (value, index), ties to the lowest index
+template <int NW>
+LMPC_DEV void group_argbest(LaneVar<double, 32 * NW>& val, LaneVar<int, 32 * NW>& idx, bool want_max, double* /*scratch*/) {
+  double bv = val.v[0]; int bi = idx.v[0];
+  for (int l = 1; l < 32 * NW; ++l) {
+    const bool better = want_max ? (val.v[l] > bv) : (val.v[l] < bv);
+    if (better || (val.v[l] == bv && idx.v[l] < bi)) { bv = val.v[l]; bi = idx.v[l]; }
+  }
+  for (int l = 0; l < 32 * NW; ++l) { val.v[l] = bv; idx.v[l] = bi; }
 }
-LMPC_DEV void warp_max(LaneVar<double>& x) {
-  double m = x.v[0];
-  for (int l = 1; l < 32; ++l) m = fmax(m, x.v[l]);
-  for (int l = 0; l < 32; ++l) x.v[l] = m;
-}
-LMPC_DEV void warp_or(LaneVar<int>& x) {
+template <int NW>
+LMPC_DEV void group_or(LaneVar<int, 32 * NW>& x, double* /*scratch*/) {
   int m = 0;
-  for (int l = 0; l < 32; ++l) m |= (x.v[l] != 0);
-  for (int l = 0; l < 32; ++l) x.v[l] = m;
-}
-// arg-max with ties to the lowest index: every lane ends with the winning (value, index)
-LMPC_DEV void warp_argmax(LaneVar<double>& val, LaneVar<int>& idx) {
-  double bv = val.v[0];
-  int bi = idx.v[0];
-  for (int l = 1; l < 32; ++l)
-    if (val.v[l] > bv || (val.v[l] == bv && idx.v[l] < bi)) { bv = val.v[l]; bi = idx.v[l]; }
-  for (int l = 0; l < 32; ++l) { val.v[l] = bv; idx.v[l] = bi; }
-}
-// arg-min on (value, index) with ties to the lowest index
-LMPC_DEV void warp_argmin(LaneVar<double>& val, LaneVar<int>& idx) {
-  double bv = val.v[0];
-  int bi = idx.v[0];
-  for (int l = 1; l < 32; ++l)
-    if (val.v[l] < bv || (val.v[l] == bv && idx.v[l] < bi)) { bv = val.v[l]; bi = idx.v[l]; }
-  for (int l = 0; l < 32; ++l) { val.v[l] = bv; idx.v[l] = bi; }
+  for (int l = 0; l < 32 * NW; ++l) m |= (x.v[l] != 0);
+  for (int l = 0; l < 32 * NW; ++l) x.v[l] = m;
 }
 #else
 LMPC_DEV double shfl_xor_f64(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
-LMPC_DEV void warp_sum(LaneVar<double>& x) {
+template <int NW, int NV>
+LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV], double* scratch) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) x.v += shfl_xor_f64(x.v, off);
-}
-LMPC_DEV void warp_min(LaneVar<double>& x) {
+  for (int q = 0; q < NV; q++) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) x.v = fmin(x.v, shfl_xor_f64(x.v, off));
-}
-LMPC_DEV void warp_max(LaneVar<double>& x) {
+    for (int off = 16; off >= 1; off >>= 1) x[q].v = lmpc_red_op(op[q], x[q].v, shfl_xor_f64(x[q].v, off));
+  }
+  if (NW > 1) {
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31u) == 0u) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) x.v = fmax(x.v, shfl_xor_f64(x.v, off));
+      for (int q = 0; q < NV; q++) scratch[w * NV + q] = x[q].v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      double r = scratch[q];
+#pragma unroll
+      for (int ww = 1; ww < NW; ww++) r = lmpc_red_op(op[q], r, scratch[ww * NV + q]);
+      x[q].v = r;
+    }
+    __syncthreads();
+  }
 }
-LMPC_DEV void warp_or(LaneVar<int>& x) { x.v = __any_sync(0xffffffffu, x.v != 0) ? 1 : 0; }
-LMPC_DEV void warp_argmax(LaneVar<double>& val, LaneVar<int>& idx) {
+template <int NW>
+LMPC_DEV void group_argbest(LaneVar<double, 32 * NW>& val, LaneVar<int, 32 * NW>& idx, bool want_max, double* scratch) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     const double ov = shfl_xor_f64(val.v, off);
     const int oi = __shfl_xor_sync(0xffffffffu, idx.v, off);
-    if (ov > val.v || (ov == val.v && oi < idx.v)) { val.v = ov; idx.v = oi; }
+    const bool better = want_max ? (ov > val.v) : (ov < val.v);
+    if (better || (ov == val.v && oi < idx.v)) { val.v = ov; idx.v = oi; }
+  }
+  if (NW > 1) {
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31u) == 0u) { scratch[2 * w] = val.v; scratch[2 * w + 1] = (double)idx.v; }
+    __syncthreads();
+    double bv = scratch[0]; int bi = (int)scratch[1];
+#pragma unroll
+    for (int ww = 1; ww < NW; ww++) {
+      const double ov = scratch[2 * ww]; const int oi = (int)scratch[2 * ww + 1];
+      const bool better = want_max ? (ov > bv) : (ov < bv);
+      if (better || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    val.v = bv; idx.v = bi;
+    __syncthreads();
   }
 }
-LMPC_DEV void warp_argmin(LaneVar<double>& val, LaneVar<int>& idx) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double ov = shfl_xor_f64(val.v, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx.v, off);
-    if (ov < val.v || (ov == val.v && oi < idx.v)) { val.v = ov; idx.v = oi; }
-  }
+template <int NW>
+LMPC_DEV void group_or(LaneVar<int, 32 * NW>& x, double* /*scratch*/) {
+  if (NW == 1) x.v = __any_sync(0xffffffffu, x.v != 0) ? 1 : 0;
+  else x.v = __syncthreads_or(x.v != 0) ? 1 : 0;
 }
 #endif
+
+// convenience single-value forms
+template <int NW>
+LMPC_DEV void group_sum(LaneVar<double, 32 * NW>& x, double* scratch) {
+  LaneVar<double, 32 * NW>(&a)[1] = reinterpret_cast<LaneVar<double, 32 * NW>(&)[1]>(x);
+  const int op[1] = {LMPC_RED_SUM};
+  group_reduce<NW, 1>(a, op, scratch);
+}
+template <int NW>
+LMPC_DEV void group_max(LaneVar<double, 32 * NW>& x, double* scratch) {
+  LaneVar<double, 32 * NW>(&a)[1] = reinterpret_cast<LaneVar<double, 32 * NW>(&)[1]>(x);
+  const int op[1] = {LMPC_RED_MAX};
+  group_reduce<NW, 1>(a, op, scratch);
+}
+
+// single-warp spellings used by the safe-set kernel
+LMPC_DEV void warp_argmin(LaneVar<double>& val, LaneVar<int>& idx) { group_argbest<1>(val, idx, false, nullptr); }
+LMPC_DEV void warp_or(LaneVar<int>& x) { group_or<1>(x, nullptr); }

@@ -24,25 +24,29 @@ extern "C" void emu_ss_query_lap(int m, const double* ps, const double* pe, cons
   lmpc_ss_query_warp(lap, qs, qe, max_total, ss_x, ss_j, last != 0, count, pad_to);
 }
 
-// full QP solve of one instance given its linearisation and safe-set columns
+// full QP solve of one instance given its linearisation and safe-set columns; nw = warps per instance
 extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params* v, const double* x_ic, const double* u_ic,
                             const double* U0, const double* T, const double* bl, const double* br, const double* vref,
                             const double* ABg, const double* ssx, const double* ssj_raw, const double* cen, int ss_count,
                             double* X, double* U, double* dU, double* lam, double* cost, int* status, int* iters,
-                            int* smem_doubles) {
+                            int* smem_doubles, int nw) {
   LmpcQpParams P;
-  int rc = lmpc_make_qp_params(*c, *v, &P);
+  int rc = lmpc_make_qp_params(*c, *v, &P, nw);
   if (rc != LMPC_OK) return rc;
   if (smem_doubles) *smem_doubles = P.total;
   std::vector<double> sm((size_t)P.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
-  std::vector<double> ssc((size_t)(P.K > 0 ? P.K : 1), 0.0);
-  for (int k = 0; k < P.K; k++) ssc[k] = ssj_raw[k] - ssj_raw[0];        // racing_mpc.cpp:280
-  LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssc.data(), cen, ss_count};
+  LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssj_raw, cen, ss_count};
   LmpcQpOut out = {X, U, dU, lam, cost, status, iters};
-  const int kpl = (P.K + 31) / 32;
-  if (kpl <= 1) lmpc_qp_solve_warp<1>(P, in, sm.data(), out);
-  else if (kpl == 2) lmpc_qp_solve_warp<2>(P, in, sm.data(), out);
-  else if (kpl == 3) lmpc_qp_solve_warp<3>(P, in, sm.data(), out);
-  else lmpc_qp_solve_warp<4>(P, in, sm.data(), out);
+  const int kpl = (P.K + 32 * nw - 1) / (32 * nw);
+  if (nw == 1) {
+    if (kpl <= 1) lmpc_qp_solve<1, 1>(P, in, sm.data(), out);
+    else if (kpl == 2) lmpc_qp_solve<1, 2>(P, in, sm.data(), out);
+    else if (kpl == 3) lmpc_qp_solve<1, 3>(P, in, sm.data(), out);
+    else lmpc_qp_solve<1, 4>(P, in, sm.data(), out);
+  } else if (nw == 2) {
+    if (kpl <= 1) lmpc_qp_solve<2, 1>(P, in, sm.data(), out); else lmpc_qp_solve<2, 2>(P, in, sm.data(), out);
+  } else {
+    lmpc_qp_solve<4, 1>(P, in, sm.data(), out);
+  }
   return LMPC_OK;
 }

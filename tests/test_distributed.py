@@ -1,0 +1,77 @@
+"""Host logic of the multi-GPU path on CPU: 2 ranks over gloo.  The rank-local solver is injected (here the CPU
+oracle port, tests only); on GPUs it is BatchedRacingMPC.solve and the backend is nccl (bench.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT, make_oracle
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    import warnings
+    warnings.filterwarnings("ignore")
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import racing_lmpc_ros2_b200 as pkg
+    from racing_lmpc_ros2_b200 import distributed as D
+    from oracle import Oracle
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    veh = pkg.configs.BARC_VEHICLE; cfg = pkg.configs.barc_lmpc_config(20)
+    track = pkg.workload.load_track("barc_center")
+    laps = pkg.workload.load_laps() if rank == 0 else []          # only rank 0 owns the laps
+    laps = D.broadcast_laps(laps, dist)
+    orc = Oracle(veh, cfg)
+    for l in laps:
+        orc.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 11, 0xD157, track, pkg.workload.load_laps(), mode="barc")   # odd size: uneven shards
+
+    def solve_fn(shard):
+        r = orc.step_batch(shard, impl="port", nthreads=1)
+        return dict(X_optm=r["X"], U_optm=r["U"], dU_optm=r["dU"], cost=r["cost"], status=r["status"])
+
+    out = D.solve_sharded(solve_fn, batch, cfg["N"], dist)
+    q.put((rank, len(laps), out["X_optm"], out["status"], out["cost"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds(pkg):
+    from racing_lmpc_ros2_b200.distributed import shard_bounds
+    for total in (1, 7, 8, 1024, 65536, 11):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [h - l for l, h in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_gloo_solve_matches_single_process(pkg):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc")
+    batch = pkg.workload.make_batch(veh, cfg, 11, 0xD157, track, pkg.workload.load_laps(), mode="barc")
+    ref = o.step_batch(batch, impl="port", nthreads=2)
+    for rank, nlaps, X, status, cost in res:
+        assert nlaps == 3                                   # rank 1 got the laps through the broadcast
+        assert X.shape == (11, 20, 6)
+        assert np.array_equal(status, ref["status"])
+        assert np.array_equal(X, ref["X"]) and np.array_equal(cost, ref["cost"])   # same code, same inputs: bit-exact

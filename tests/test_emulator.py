@@ -29,7 +29,7 @@ def emu():
     return C.CDLL(EMU_SO)
 
 
-def _emu_solve(emu, pkg, od, veh, cfg, inp, reverse=0):
+def _emu_solve(emu, pkg, od, veh, cfg, inp, reverse=0, nw=1):
     from racing_lmpc_ros2_b200 import binding as Bd
     emu.emu_set_reverse(reverse)
     vs = Bd.fill_struct(Bd.VehicleParams(), veh)
@@ -58,13 +58,14 @@ def _emu_solve(emu, pkg, od, veh, cfg, inp, reverse=0):
     rc = emu.emu_qp_solve(C.byref(cs), C.byref(vs), _p(inp["x_ic"]), _p(inp["u_ic"]), _p(np.ascontiguousarray(inp["U_ref"])),
                           _p(inp["T_ref"]), _p(inp["bound_left"]), _p(inp["bound_right"]), _p(inp["vel_ref"]), _p(ABg),
                           _p(ssx), _p(ssj), _p(cen), cnt, _p(X), _p(U), _p(dU), _p(lam), C.byref(cost), C.byref(st),
-                          C.byref(it), C.byref(smd))
+                          C.byref(it), C.byref(smd), int(nw))
     assert rc == 0
     return dict(X=X, U=U, dU=dU, lam=lam, cost=cost.value, status=st.value, iters=it.value, smem=smd.value * 8, ss_x=ssx)
 
 
+@pytest.mark.parametrize("nw", [1, 2, 4])
 @pytest.mark.parametrize("name", list(CASES))
-def test_emulated_qp_kernel_matches_dense_oracle(emu, pkg, name):
+def test_emulated_qp_kernel_matches_dense_oracle(emu, pkg, name, nw):
     od, veh, cfg, track, mode = make_oracle(pkg, name, tol=1e-11)
     cfgk = dict(cfg, tol=1e-13)
     batch = pkg.workload.make_batch(veh, cfg, 10, 0xE31 + len(name), track, pkg.workload.load_laps(), mode=mode)
@@ -74,7 +75,7 @@ def test_emulated_qp_kernel_matches_dense_oracle(emu, pkg, name):
         d = od.step(inp, impl="dense")
         if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
             continue
-        k = _emu_solve(emu, pkg, od, veh, cfgk, inp)
+        k = _emu_solve(emu, pkg, od, veh, cfgk, inp, nw=nw)
         assert k["status"] == 0
         worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"]))
         assert abs(k["cost"] - d["cost"]) < 1e-8 * max(1, abs(d["cost"]))
@@ -84,7 +85,8 @@ def test_emulated_qp_kernel_matches_dense_oracle(emu, pkg, name):
     assert worst < 1e-6, worst
 
 
-def test_emulated_qp_kernel_is_lane_order_independent(emu, pkg):
+@pytest.mark.parametrize("nw", [1, 2, 4])
+def test_emulated_qp_kernel_is_lane_order_independent(emu, pkg, nw):
     """Running the lanes of every phase in reverse order must give bit-identical results: a phase that
     read shared memory written by another lane in the same phase would differ."""
     od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc", tol=1e-11)
@@ -92,8 +94,8 @@ def test_emulated_qp_kernel_is_lane_order_independent(emu, pkg):
     batch = pkg.workload.make_batch(veh, cfg, 3, 0xAB, track, pkg.workload.load_laps(), mode=mode)
     for b in range(3):
         inp = pkg.workload.instance(batch, b)
-        f = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=0)
-        r = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=1)
+        f = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=0, nw=nw)
+        r = _emu_solve(emu, pkg, od, veh, cfgk, inp, reverse=1, nw=nw)
         for key in ("X", "U", "dU", "lam"):
             assert np.array_equal(f[key], r[key]), key
         assert f["iters"] == r["iters"] and f["cost"] == r["cost"]
@@ -103,8 +105,9 @@ def test_qp_shared_memory_budget(emu, pkg):
     """BASELINE config 2 (N=20, K=96) must fit 7 warps per SM: <= (228 KB - 7 KB reserved) / 7."""
     od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc")
     batch = pkg.workload.make_batch(veh, cfg, 1, 1, track, pkg.workload.load_laps(), mode=mode)
-    k = _emu_solve(emu, pkg, od, veh, cfg, pkg.workload.instance(batch, 0))
-    assert k["smem"] + 8 * cfg["num_ss_pts"] <= (228 * 1024 - 7 * 1024) // 7
+    for nw in (1, 2, 4):
+        k = _emu_solve(emu, pkg, od, veh, cfg, pkg.workload.instance(batch, 0), nw=nw)
+        assert k["smem"] <= (228 * 1024 - 7 * 1024) // 7, (nw, k["smem"])
 
 
 def test_emulated_ss_query_matches_oracle(emu, pkg, laps, barc_track):
