@@ -57,6 +57,14 @@ struct lmpc_handle {
 
 static const int kTimingRing = 1024;
 
+// compile-time-layout kernels exist for N in {20, 40} with 16 row slots per stage (LMPC_FIXED_LAYOUT=0 disables)
+static int qp_fixed_n(const lmpc_handle* h) {
+  const char* e = getenv("LMPC_FIXED_LAYOUT");
+  if (e && atoi(e) == 0) return 0;
+  if (h->P.NW == 1 && h->P.RS == 16 && (h->P.N == 20 || h->P.N == 40)) return h->P.N;
+  return 0;
+}
+
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -92,18 +100,22 @@ extern "C" const char* lmpc_status_string(int s) {
 extern "C" const char* lmpc_last_error(const lmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int64_t lmpc_launch_count(const lmpc_handle* h) { return h ? h->launches : 0; }
 
-// dispatch over the instantiated (warps per instance, columns per lane) pairs
-#define LMPC_QP_DISPATCH(NWv, KPLv, CALL)                                            \
+// dispatch over the instantiated kernels: (warps per instance, columns per lane) and, for the single-warp
+// default, the compile-time layouts of the named horizons (N = 20 / 40 with 16 row slots per stage)
+#define LMPC_QP_DISPATCH(NWv, KPLv, NFv, CALL)                                        \
   do {                                                                               \
-    if (NWv == 1) { if (KPLv <= 1) { CALL(1, 1); } else if (KPLv == 2) { CALL(1, 2); } else if (KPLv == 3) { CALL(1, 3); } else { CALL(1, 4); } } \
-    else if (NWv == 2) { if (KPLv <= 1) { CALL(2, 1); } else { CALL(2, 2); } }         \
-    else { CALL(4, 1); }                                                             \
+    if (NWv == 1) {                                                                  \
+      if (NFv == 20) { if (KPLv <= 1) { CALL(1, 1, 20, 16); } else if (KPLv == 2) { CALL(1, 2, 20, 16); } else if (KPLv == 3) { CALL(1, 3, 20, 16); } else { CALL(1, 4, 20, 16); } } \
+      else if (NFv == 40) { if (KPLv <= 1) { CALL(1, 1, 40, 16); } else if (KPLv == 2) { CALL(1, 2, 40, 16); } else if (KPLv == 3) { CALL(1, 3, 40, 16); } else { CALL(1, 4, 40, 16); } } \
+      else { if (KPLv <= 1) { CALL(1, 1, 0, 0); } else if (KPLv == 2) { CALL(1, 2, 0, 0); } else if (KPLv == 3) { CALL(1, 3, 0, 0); } else { CALL(1, 4, 0, 0); } } \
+    } else if (NWv == 2) { if (KPLv <= 1) { CALL(2, 1, 0, 0); } else { CALL(2, 2, 0, 0); } } \
+    else { CALL(4, 1, 0, 0); }                                                       \
   } while (0)
 
 static int set_qp_attr(lmpc_handle* h) {
-  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw));
-#define SETATTR(NW_, KPL_) CK(cudaFuncSetAttribute(lmpc_qp_kernel<NW_, KPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem))
-  LMPC_QP_DISPATCH(nw, kpl, SETATTR);
+  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nf = qp_fixed_n(h);
+#define SETATTR(NW_, KPL_, NF_, RS_) CK(cudaFuncSetAttribute(lmpc_qp_kernel<NW_, KPL_, NF_, RS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem))
+  LMPC_QP_DISPATCH(nw, kpl, nf, SETATTR);
 #undef SETATTR
   return LMPC_OK;
 }
@@ -127,7 +139,7 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
   if (rc != LMPC_OK) { delete h; return rc; }
   h->M = lmpc_make_model(*vehicle);
   if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return LMPC_ERR_NO_DEVICE; }
-  h->qp_smem = sizeof(double) * (size_t)h->P.total;
+  h->qp_smem = sizeof(double) * (size_t)h->P.lay.total;
   rc = set_qp_attr(h);
   if (rc != LMPC_OK) { fprintf(stderr, "lmpc_create: %s\n", h->err.c_str()); delete h; return rc; }
   const size_t B = (size_t)max_batch, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)std::max(h->P.K, 1);
@@ -411,9 +423,9 @@ extern "C" int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, cons
 
 // ------------------------------------------------------------------------------------------ solve
 static void launch_qp(lmpc_handle* h, const LmpcQpBatch& a) {
-  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nblocks = a.B;
-#define LAUNCH(NW_, KPL_) lmpc_qp_kernel<NW_, KPL_><<<nblocks, 32 * NW_, h->qp_smem, h->stream>>>(h->P, a)
-  LMPC_QP_DISPATCH(nw, kpl, LAUNCH);
+  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nblocks = a.B, nf = qp_fixed_n(h);
+#define LAUNCH(NW_, KPL_, NF_, RS_) lmpc_qp_kernel<NW_, KPL_, NF_, RS_><<<nblocks, 32 * NW_, h->qp_smem, h->stream>>>(h->P, a)
+  LMPC_QP_DISPATCH(nw, kpl, nf, LAUNCH);
 #undef LAUNCH
 }
 

@@ -74,20 +74,7 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   if (NW != 1 && NW != 2 && NW != 4) return LMPC_ERR_INVALID;
   if (P.learning && (P.K + 32 * NW - 1) / (32 * NW) > LMPC_KPL_MAX) return LMPC_ERR_INVALID;
   P.NW = NW;
-  const int d = P.NSd;
-  int o = 0;
-  auto take = [&](int n) { const int at = o; o += (n + 1) & ~1; return at; };   // keep 16-byte alignment
-  P.oABG = take(54 * P.NS);
-  P.oS = take(P.RS * d); P.oY = take(P.RS * d); P.oISY = take(P.RS * d);
-  P.oX = take(6 * d); P.oU = take(2 * d);
-  P.oDXA = take(6 * d); P.oDUA = take(2 * d); P.oDXF = take(6 * d); P.oDUF = take(2 * d);
-  P.oCZX = take(6 * d); P.oCZTH = take(d); P.oGUD = take(8 * d);
-  P.oFAC = take(20 * P.NS); P.oKFF = take(6 * P.NS);
-  P.oBL = take(d); P.oBR = take(d); P.oVREF = take(d); P.oIT = take(d); P.oT = P.oIT;
-  P.oPM = take(64); P.oL1 = take(8); P.oLTH = take(8); P.oMAB = take(48); P.oAXBW = take(16); P.oYY = take(64);
-  P.oRED = take(NW > 1 ? NW * LMPC_NRED : 0);
-  P.oTERM = take(TB_SIZE);
-  P.total = o;
+  P.lay = lmpc_layout(P.N, P.RS, NW);
   *out = P;
   return LMPC_OK;
 }

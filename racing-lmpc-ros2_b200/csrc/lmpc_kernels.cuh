@@ -99,7 +99,7 @@ struct LmpcQpBatch {
   int B;
 };
 
-template <int NW, int KPL>
+template <int NW, int KPL, int NTPL, int RSTPL>
 __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_constant__ LmpcQpParams P, const __grid_constant__ LmpcQpBatch a) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x;
@@ -118,5 +118,5 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
   out.lam = (a.lam && P.learning) ? a.lam + (size_t)K * b : nullptr;
   out.cost = a.cost ? a.cost + b : nullptr;
   out.status = a.status + b; out.iters = a.iters + b;
-  lmpc_qp_solve<NW, KPL>(P, in, sm, out);
+  lmpc_qp_solve<NW, KPL, NTPL, RSTPL>(P, in, sm, out);
 }

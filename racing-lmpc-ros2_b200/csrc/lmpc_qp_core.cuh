@@ -24,6 +24,35 @@
 #define LMPC_NQ (1 + LMPC_MB)   // + simplex multiplier
 #define LMPC_KPL_MAX 4          // safe-set columns per lane
 #define LMPC_NRED 36            // widest multi-value reduction
+// Qzw row r lives in YY: rows 0..5 are Yxu = YY[8r+6..7]; rows 6,7 (= -E) are parked in YY[8r+0..1]
+#define QZ0(r) (((r) < 6) ? (8 * (r) + 6) : (8 * (r)))
+
+// Shared-memory layout (offsets in doubles) as a function of (N, rows per stage, warps per instance).
+// constexpr so that the kernels instantiated for the named horizons fold every address into an immediate.
+struct LmpcLayout {
+  int oABG, oS, oY, oISY, oX, oU, oDXA, oDUA, oDXF, oDUF, oCZX, oCZTH, oGUD, oFAC, oKFF, oBL, oBR, oVREF, oIT,
+      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, total;
+};
+#define LMPC_TB_SIZE_ (36 + 6 * LMPC_NQ + LMPC_NQ * LMPC_NQ + 6 * LMPC_NQ + LMPC_NQ + 36 + 6 + 6 * LMPC_MB + LMPC_MB + LMPC_MB + LMPC_NQ + 1)
+LMPC_HD constexpr int lmpc_even(int n) { return (n + 1) & ~1; }   // keep 16-byte alignment
+LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
+  LmpcLayout L{};
+  const int NS = N - 1, d = N | 1;
+  int o = 0;
+  L.oABG = o; o += lmpc_even(54 * NS);
+  L.oS = o; o += lmpc_even(RS * d); L.oY = o; o += lmpc_even(RS * d); L.oISY = o; o += lmpc_even(RS * d);
+  L.oX = o; o += lmpc_even(6 * d); L.oU = o; o += lmpc_even(2 * d);
+  L.oDXA = o; o += lmpc_even(6 * d); L.oDUA = o; o += lmpc_even(2 * d);
+  L.oDXF = o; o += lmpc_even(6 * d); L.oDUF = o; o += lmpc_even(2 * d);
+  L.oCZX = o; o += lmpc_even(6 * d); L.oCZTH = o; o += lmpc_even(d); L.oGUD = o; o += lmpc_even(8 * d);
+  L.oFAC = o; o += lmpc_even(20 * NS); L.oKFF = o; o += lmpc_even(6 * NS);
+  L.oBL = o; o += lmpc_even(d); L.oBR = o; o += lmpc_even(d); L.oVREF = o; o += lmpc_even(d); L.oIT = o; o += lmpc_even(d);
+  L.oPM = o; o += 64; L.oL1 = o; o += 8; L.oLTH = o; o += 8; L.oMAB = o; o += 48; L.oAXBW = o; o += 16; L.oYY = o; o += 64;
+  L.oRED = o; o += lmpc_even(NW > 1 ? NW * LMPC_NRED : 0);
+  L.oTERM = o; o += lmpc_even(LMPC_TB_SIZE_);
+  L.total = o;
+  return L;
+}
 
 struct LmpcQpParams {
   int N, NS, K, learning, soft, hull_slack;
@@ -42,9 +71,7 @@ struct LmpcQpParams {
   double tol;
   int NSd;                       // odd stage stride of the [.][stage] arrays
   int NW;                        // warps per instance the layout was sized for
-  // shared-memory offsets (doubles)
-  int oABG, oS, oY, oISY, oX, oU, oDXA, oDUA, oDXF, oDUF, oCZX, oCZTH, oGUD, oFAC, oKFF, oBL, oBR, oVREF, oT, oIT,
-      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, total;
+  LmpcLayout lay;                // shared-memory offsets (doubles)
 };
 
 // terminal-block scratch layout inside oTERM (doubles)
@@ -60,6 +87,7 @@ struct LmpcQpParams {
 #define TB_BG (TB_BD + LMPC_MB)        // MB      g_lambda of basic columns
 #define TB_PIV (TB_BG + LMPC_MB)       // NQ (as doubles)
 #define TB_SIZE (TB_PIV + LMPC_NQ + 1)
+static_assert(TB_SIZE == LMPC_TB_SIZE_, "terminal scratch size");
 
 struct LmpcQpIn {
   const double* x_ic;    // 6
@@ -91,24 +119,34 @@ struct ArrKx6 { double a[LMPC_KPL_MAX][6]; };
 struct ArrKi { int a[LMPC_KPL_MAX]; };
 
 // ---------------------------------------------------------------------------------------- rows
-struct RowDesc { int rtype, slot, c; double sg; bool act; };
+// A row of group g (uniform across the lanes: every lane works on the same group, its own stage i):
+// type, slot, component, sign and the stage range [i0, i1] on which the row exists.
+struct RowDesc { int rtype, slot, c, i0, i1; double sg; };
 // group g in [0,10): 0..5 GX(c), 6..7 GU(c), 8..9 GD(c); r in [0, rows_of(g))
 LMPC_DEV int group_rows(int g) { return g == 1 ? 4 : 2; }
-LMPC_DEV RowDesc row_desc(const LmpcQpParams& P, int g, int r, int i) {
+LMPC_DEV RowDesc row_desc(const LmpcQpParams& P, int g, int r) {
   RowDesc q;
   q.sg = (r & 1) ? -1.0 : 1.0;
+  q.i0 = 0; q.i1 = -1;   // empty range = row absent
   if (g < 6) {
     q.c = g;
-    if (r < 2) { q.rtype = 0; q.slot = P.xslot[g][r]; q.act = q.slot >= 0 && i >= 1 && i <= P.N - 2; }
-    else { q.rtype = 1; q.slot = P.nxb + 8 + (r - 2); q.act = P.soft || i >= 1; }
+    if (r < 2) { q.rtype = 0; q.slot = P.xslot[g][r]; if (q.slot >= 0) { q.i0 = 1; q.i1 = P.N - 2; } }
+    else { q.rtype = 1; q.slot = P.nxb + 8 + (r - 2); q.i0 = P.soft ? 0 : 1; q.i1 = P.N - 1; }
   } else if (g < 8) {
-    q.c = g - 6; q.rtype = 2; q.slot = P.nxb + 2 * q.c + r; q.act = i <= P.N - 2 && P.ub_act[2 * q.c + r];
+    q.c = g - 6; q.rtype = 2; q.slot = P.nxb + 2 * q.c + r; if (P.ub_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; }
   } else {
-    q.c = g - 8; q.rtype = 3; q.slot = P.nxb + 4 + 2 * q.c + r; q.act = i <= P.N - 2 && P.db_act[2 * q.c + r];
+    q.c = g - 8; q.rtype = 3; q.slot = P.nxb + 4 + 2 * q.c + r; if (P.db_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; }
   }
   if (q.slot < 0) q.slot = 0;
   return q;
 }
+// iterate: for every group g (uniform), every stage i owned by this lane, every existing row q of g
+#define FOR_GROUPS(g) for (int g = 0; g < 10; g++)
+#define FOR_MY_STAGES(i) for (int i = lane; i < N; i += NT)
+#define FOR_ROWS(q, g, i)                                        \
+  for (int rr_ = 0; rr_ < group_rows(g); rr_++)                  \
+    for (RowDesc q = row_desc(P, g, rr_); q.i1 >= q.i0; q.i1 = -2) \
+      if (i >= q.i0 && i <= q.i1)
 // G v of the row for the vectors (xs, us, thv); up0 = u_{-1} component (u_ic for the iterate, 0 for a step)
 LMPC_DEV double row_val(const RowDesc& q, int i, int d, const double* xs, const double* us, const double* IT, double thv, const double* up0) {
   switch (q.rtype) {
@@ -128,32 +166,35 @@ LMPC_DEV double row_bound(const LmpcQpParams& P, const RowDesc& q, int i, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// NW warps per instance, KPL = ceil(K / (32 NW)) safe-set columns per lane (registers)
-template <int NW, int KPL>
+// NW warps per instance, KPL = ceil(K / (32 NW)) safe-set columns per lane (registers).
+// NTPL / RSTPL > 0: horizon and rows-per-stage are compile-time (addresses fold to immediates); 0 = runtime.
+template <int NW, int KPL, int NTPL, int RSTPL>
 LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* sm, const LmpcQpOut& out) {
   constexpr int NT = 32 * NW;
-  const int N = P.N, NS = P.NS, d = P.NSd;
+  constexpr bool FIXED = NTPL > 0;
+  constexpr LmpcLayout LC = lmpc_layout(FIXED ? NTPL : 4, FIXED ? RSTPL : 10, NW);
+#define LO(f) (FIXED ? LC.f : P.lay.f)
+  const int N = FIXED ? NTPL : P.N, NS = N - 1, d = N | 1;
   const bool learn = P.learning != 0, soft = P.soft != 0;
   // Columns beyond the number actually found are copies of the last one (racing_mpc.cpp:263-272); they are
   // dropped here (their lambda stays 0): same optimum in X, U, dU, SS*lambda, and the explicit-column
   // system stays non-singular.
   const int K = learn ? ((in.ss_count > 0 && in.ss_count < P.K) ? in.ss_count : P.K) : 0;
   const int nh = P.nh;
-  double* ABG = sm + P.oABG;
-  double* RSs = sm + P.oS; double* RSy = sm + P.oY; double* RSi = sm + P.oISY;
-  double* X = sm + P.oX; double* U = sm + P.oU;
-  double* DXA = sm + P.oDXA; double* DUA = sm + P.oDUA; double* DXF = sm + P.oDXF; double* DUF = sm + P.oDUF;
+  double* ABG = sm + LO(oABG);
+  double* RSs = sm + LO(oS); double* RSy = sm + LO(oY); double* RSi = sm + LO(oISY);
+  double* X = sm + LO(oX); double* U = sm + LO(oU);
+  double* DXA = sm + LO(oDXA); double* DUA = sm + LO(oDUA); double* DXF = sm + LO(oDXF); double* DUF = sm + LO(oDUF);
   double* HX = DXF;   // alias: the Hessian diagonal is dead once the pass-0 factorisation is done
-  double* CZX = sm + P.oCZX; double* CZTH = sm + P.oCZTH; double* GUD = sm + P.oGUD;
-  double* FAC = sm + P.oFAC;   // per stage: Kz[16] (2x8 row-major), Sinv[3], pad
-  double* KFF = sm + P.oKFF;   // per stage: kff1[2], kffth[2], Cwth[2]
-  double* BL = sm + P.oBL; double* BR = sm + P.oBR; double* VREF = sm + P.oVREF; double* IT = sm + P.oIT;
-  double* PM = sm + P.oPM; double* L1 = sm + P.oL1; double* LTH = sm + P.oLTH;
-  double* MAB = sm + P.oMAB; double* AXBW = sm + P.oAXBW; double* YY = sm + P.oYY;
-  double* RED = sm + P.oRED;
-  double* TB = sm + P.oTERM;
+  double* CZX = sm + LO(oCZX); double* CZTH = sm + LO(oCZTH); double* GUD = sm + LO(oGUD);
+  double* FAC = sm + LO(oFAC);   // per stage: Kz[16] (2x8 row-major), Sinv[3], pad
+  double* KFF = sm + LO(oKFF);   // per stage: kff1[2], kffth[2], Cwth[2]
+  double* BL = sm + LO(oBL); double* BR = sm + LO(oBR); double* VREF = sm + LO(oVREF); double* IT = sm + LO(oIT);
+  double* PM = sm + LO(oPM); double* L1 = sm + LO(oL1); double* LTH = sm + LO(oLTH);
+  double* MAB = sm + LO(oMAB); double* AXBW = sm + LO(oAXBW); double* YY = sm + LO(oYY);
+  double* RED = sm + LO(oRED);
+  double* TB = sm + LO(oTERM);
   const double sfloor = 1e-2, mu0 = 0.1, th0 = 0.01;
-  const int NG = 10 * N;   // (group, stage) work items
 
   // ---------------------------------------------------------------- load
   GLANES_BEGIN(NT)
@@ -205,17 +246,12 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     LaneVar<double, NT> r[12];
     GLANES_BEGIN(NT)
       double r0 = 1.0, cnt = 0.0;
-      for (int idx = lane; idx < NG; idx += NT) {
-        const int g = idx / N, i = idx - g * N;
-        for (int rr = 0; rr < group_rows(g); rr++) {
-          const RowDesc q = row_desc(P, g, rr, i);
-          if (!q.act) continue;
-          const double slack = row_bound(P, q, i, BL, BR) - row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic);
-          const double s = slack > sfloor ? slack : sfloor;
-          const double y = mu0 / s;
-          RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
-          r0 = fmax(r0, y); cnt += 1.0;
-        }
+      FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+        const double slack = row_bound(P, q, i, BL, BR) - row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic);
+        const double s = slack > sfloor ? slack : sfloor;
+        const double y = mu0 / s;
+        RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
+        r0 = fmax(r0, y); cnt += 1.0;
       }
       const double j0 = (learn && K > 0) ? in.ssj[0] : 0.0;
       for (int p = 0; p < KPL; p++) {
@@ -263,13 +299,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       LaneVar<double, NT> rs[12];
       GLANES_BEGIN(NT)
         double dth_acc = 0.0, cth_acc = 0.0, msum = 0.0, rpm = 0.0;
-        for (int idx = lane; idx < NG; idx += NT) {
-          const int g = idx / N, i = idx - g * N;
+        FOR_GROUPS(g) FOR_MY_STAGES(i) {
           double hsum = 0.0, gsum = 0.0, cz_th = 0.0;
           if (g < 6 && !learn) { const double w = (i == N - 1) ? P.qxN[g] : P.qx[g]; hsum = 2.0 * w; gsum = 2.0 * w * (X[g * d + i] - (g == 3 ? VREF[i] : 0.0)); }
-          for (int rr = 0; rr < group_rows(g); rr++) {
-            const RowDesc q = row_desc(P, g, rr, i);
-            if (!q.act) continue;
+          FOR_ROWS(q, g, i) {
             const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
             const double is = y * isy;
             const double dj = y * is;
@@ -621,14 +654,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               if (o < 48) {
                 const int r = o >> 3, c = o & 7;
                 double a = (c < 6) ? 0.0 : PM[8 * r + c];
-                const double* col = (c < 6) ? (A + 6 * c) : (B + 6 * (c - 6));
+                const double* col = A + 6 * c;   // [A | B] is contiguous: column c of B follows A's six columns
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += PM[8 * r + k] * col[k];
                 MAB[o] = a;
               } else {
                 const int q = o - 48, e = q & 7; const double* l = (q < 8) ? L1 : LTH;
                 double a = (e < 6) ? 0.0 : l[e];
-                const double* col = (e < 6) ? (A + 6 * e) : (B + 6 * (e - 6));
+                const double* col = A + 6 * e;
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += col[k] * l[k];
                 AXBW[q] = a;
@@ -649,6 +682,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += B[k + 6 * (r - 6)] * MAB[8 * k + c] + PM[8 * k + r] * B[k + 6 * (c - 6)];
                 YY[o] = a;
+              } else if (c < 2) {
+                // rows 6,7 of Qzw = -E, parked in the unused (r >= 6, c < 2) slots so that phase c reads
+                // Qzw[r][j] = QZ(r, j) without selecting between Yxu and -E
+                YY[o] = (r == 6) ? (c == 0 ? -e0 : -e1) : (c == 0 ? -e1 : -e2);
               }
             }
           GLANES_END(NW)
@@ -678,10 +715,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
                   const double p10 = q1_ * se00 + q2_ * se10, p11 = q1_ * se01 + q2_ * se11;
                   pv = (r == 6 && c == 6) ? p00 : ((r == 7 && c == 7) ? p11 : 0.5 * (p01 + p10));
                 } else {
-                  const double qr0 = (r < 6) ? YY[8 * r + 6] : ((r == 6) ? -e0 : -e1);
-                  const double qr1 = (r < 6) ? YY[8 * r + 7] : ((r == 6) ? -e1 : -e2);
-                  const double qc0 = (c < 6) ? YY[8 * c + 6] : ((c == 6) ? -e0 : -e1);
-                  const double qc1 = (c < 6) ? YY[8 * c + 7] : ((c == 6) ? -e1 : -e2);
+                  const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1], qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
                   double qzz = 0.0;
                   if (r < 6 && c < 6) qzz = YY[8 * r + c] + (r == c ? HX[r * d + i] : 0.0);
                   pv = qzz - (qr0 * (i0 * qc0 + i1 * qc1) + qr1 * (i1 * qc0 + i2_ * qc1));
@@ -689,13 +723,11 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
                 PM[o] = pv;
               } else if (o < 80) {   // Kz (2x8): Kz[j][c] = Sinv[j][:] . Qzw[c][:]
                 const int q = o - 64, j = q >> 3, c = q & 7;
-                const double qc0 = (c < 6) ? YY[8 * c + 6] : ((c == 6) ? -e0 : -e1);
-                const double qc1 = (c < 6) ? YY[8 * c + 7] : ((c == 6) ? -e1 : -e2);
+                const double qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
                 fac[q] = (j == 0) ? (i0 * qc0 + i1 * qc1) : (i1 * qc0 + i2_ * qc1);
               } else if (o < 96) {   // l1 and lth:  l = Cz' - Qzw kff
                 const int q = o - 80, r = q & 7; const bool isth = q >= 8;
-                const double qr0 = (r < 6) ? YY[8 * r + 6] : ((r == 6) ? -e0 : -e1);
-                const double qr1 = (r < 6) ? YY[8 * r + 7] : ((r == 6) ? -e1 : -e2);
+                const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1];
                 const double kk0 = isth ? kt_0 : k1_0, kk1 = isth ? kt_1 : k1_1;
                 double cz;
                 if (isth) cz = (r == 1) ? CZTH[i] : 0.0;
@@ -809,23 +841,18 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       LaneVar<double, NT> ra[2];
       GLANES_BEGIN(NT)
         double rmax = 0.0, cross = 0.0;   // rmax = max over rows of (-ds/s, -dy/y)  ->  amax = 1 / rmax
-        for (int idx = lane; idx < NG; idx += NT) {
-          const int g = idx / N, i = idx - g * N;
-          for (int rr = 0; rr < group_rows(g); rr++) {
-            const RowDesc q = row_desc(P, g, rr, i);
-            if (!q.act) continue;
-            const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
-            const double is = y * isy, iy = s * isy;
-            const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
-            const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
-            const double dya_ = -y - y * is * dsa;
-            double ds = dsa, dy = dya_;
-            if (pass) {
-              ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
-              dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
-            } else cross += dsa * dya_;
-            rmax = fmax(rmax, fmax(-ds * is, -dy * iy));
-          }
+        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
+          const double is = y * isy, iy = s * isy;
+          const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
+          const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
+          const double dya_ = -y - y * is * dsa;
+          double ds = dsa, dy = dya_;
+          if (pass) {
+            ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
+            dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
+          } else cross += dsa * dya_;
+          rmax = fmax(rmax, fmax(-ds * is, -dy * iy));
         }
 #pragma unroll
         for (int p = 0; p < KPL; p++) {
@@ -873,21 +900,16 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       const double smu = sigma * mu;
       LaneVar<double, NT> rstep;
       GLANES_BEGIN(NT)
-        for (int idx = lane; idx < NG; idx += NT) {
-          const int g = idx / N, i = idx - g * N;
-          for (int rr = 0; rr < group_rows(g); rr++) {
-            const RowDesc q = row_desc(P, g, rr, i);
-            if (!q.act) continue;
-            const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
-            const double is = y * isy;
-            const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
-            const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
-            const double dya_ = -y - y * is * dsa;
-            const double ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
-            const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
-            const double sn = s + alpha * ds, yn = y + alpha * dy;
-            RSs[q.slot * d + i] = sn; RSy[q.slot * d + i] = yn; RSi[q.slot * d + i] = 1.0 / (sn * yn);
-          }
+        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
+          const double is = y * isy;
+          const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
+          const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
+          const double dya_ = -y - y * is * dsa;
+          const double ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
+          const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
+          const double sn = s + alpha * ds, yn = y + alpha * dy;
+          RSs[q.slot * d + i] = sn; RSy[q.slot * d + i] = yn; RSi[q.slot * d + i] = 1.0 / (sn * yn);
         }
 #pragma unroll
         for (int p = 0; p < KPL; p++) {
@@ -977,4 +999,5 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   if (learn && P.hull_slack)
     for (int a = 0; a < nh; a++) { const int c = P.hidx[a]; const double sh = X[c * d + N - 1] - in.cen[c] - ro[1 + a](0); cost += P.chs[c] * sh * sh; }
   LANE0_ONLY(if (out.cost) *out.cost = cost; *out.status = status; *out.iters = it;)
+#undef LO
 }

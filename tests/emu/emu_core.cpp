@@ -33,20 +33,24 @@ extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params*
   LmpcQpParams P;
   int rc = lmpc_make_qp_params(*c, *v, &P, nw);
   if (rc != LMPC_OK) return rc;
-  if (smem_doubles) *smem_doubles = P.total;
-  std::vector<double> sm((size_t)P.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
+  if (smem_doubles) *smem_doubles = P.lay.total;
+  std::vector<double> sm((size_t)P.lay.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
   LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssj_raw, cen, ss_count};
   LmpcQpOut out = {X, U, dU, lam, cost, status, iters};
   const int kpl = (P.K + 32 * nw - 1) / (32 * nw);
+  const bool fixed = (nw & 0x100) == 0 && P.RS == 16 && (P.N == 20 || P.N == 40);   // same rule as the C ABI
   if (nw == 1) {
-    if (kpl <= 1) lmpc_qp_solve<1, 1>(P, in, sm.data(), out);
-    else if (kpl == 2) lmpc_qp_solve<1, 2>(P, in, sm.data(), out);
-    else if (kpl == 3) lmpc_qp_solve<1, 3>(P, in, sm.data(), out);
-    else lmpc_qp_solve<1, 4>(P, in, sm.data(), out);
+    if (fixed && P.N == 20 && kpl == 3) lmpc_qp_solve<1, 3, 20, 16>(P, in, sm.data(), out);
+    else if (fixed && P.N == 40 && kpl <= 1) lmpc_qp_solve<1, 1, 40, 16>(P, in, sm.data(), out);
+    else if (fixed && P.N == 20 && kpl <= 1) lmpc_qp_solve<1, 1, 20, 16>(P, in, sm.data(), out);
+    else if (kpl <= 1) lmpc_qp_solve<1, 1, 0, 0>(P, in, sm.data(), out);
+    else if (kpl == 2) lmpc_qp_solve<1, 2, 0, 0>(P, in, sm.data(), out);
+    else if (kpl == 3) lmpc_qp_solve<1, 3, 0, 0>(P, in, sm.data(), out);
+    else lmpc_qp_solve<1, 4, 0, 0>(P, in, sm.data(), out);
   } else if (nw == 2) {
-    if (kpl <= 1) lmpc_qp_solve<2, 1>(P, in, sm.data(), out); else lmpc_qp_solve<2, 2>(P, in, sm.data(), out);
+    if (kpl <= 1) lmpc_qp_solve<2, 1, 0, 0>(P, in, sm.data(), out); else lmpc_qp_solve<2, 2, 0, 0>(P, in, sm.data(), out);
   } else {
-    lmpc_qp_solve<4, 1>(P, in, sm.data(), out);
+    lmpc_qp_solve<4, 1, 0, 0>(P, in, sm.data(), out);
   }
   return LMPC_OK;
 }
