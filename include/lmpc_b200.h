@@ -96,9 +96,10 @@ typedef struct lmpc_mpc_config {
   double convex_hull_slack[6];
   int32_t num_ss_pts, num_ss_pts_per_lap, max_lap_stored;
   int32_t max_iter;          /* interior-point iteration cap (default 30 when <= 0) */
-  double tol;                /* target accuracy of the returned X/U/dU, per channel relative to
-                              * max(1, |channel|) (default 1e-9 when <= 0); the complementarity
-                              * floor is 1e-4 * tol */
+  double tol;                /* interior-point stage tolerance: primal step per channel relative to
+                              * max(1, |channel|) (default 1e-7 when <= 0; complementarity floor
+                              * 1e-4 * tol).  The active-set polish that follows (the counterpart of
+                              * OSQP's polish=true) then lands on the optimum to ~1e-12. */
 } lmpc_mpc_config;
 
 typedef struct lmpc_handle lmpc_handle;

@@ -19,6 +19,7 @@
 
 #define NS ORC_NMAX
 #define QMAX 9              /* 1 + max explicit (basic) safe-set columns */
+#define PMAX 4               /* active-set refinement rounds of the polish */
 #define MAXROW 22            /* per-stage row slots: 12 x-box + 4 u-box + 4 du-box + 2 boundary */
 
 typedef struct {
@@ -42,7 +43,9 @@ typedef struct {
   int nh, hidx[6]; double Einv[6];
   double PT[36], pT[6], Phi[36], Phia[6], nu0, nvec[6], kap, W[36], avec[6], om1;
   double sig[6];
-  double om[ORC_KMAX], gl[ORC_KMAX]; int isB[ORC_KMAX], Bidx[QMAX], mB, S2piv[QMAX];
+  double om[ORC_KMAX], gl[ORC_KMAX], Dk[ORC_KMAX];
+  int pact[NS * MAXROW], pact_th, pnb[ORC_KMAX];
+  double xsave[6 * NS], usave[2 * NS], lsave[ORC_KMAX], thsave, ysave[NS * MAXROW], ylsave[ORC_KMAX], ythsave;   /* polish: active rows / sigma_b bound / non-basic columns */ int isB[ORC_KMAX], Bidx[QMAX], mB, S2piv[QMAX];
   double PhiC[6 * QMAX], S2[QMAX * QMAX], Xq[QMAX * 6], q0[QMAX];
   int m_total;
 } port_ws;
@@ -89,7 +92,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
   if (st != ORC_OK) { out->status = st; free(p); return st; }
   port_ws* w = (port_ws*)calloc(1, sizeof *w);
   const int N = p->N, K = p->K, soft = p->soft_boundary, learn = p->learning;
-  const double step_tol = c->tol > 0 ? c->tol : 1e-9;   /* target accuracy of the returned trajectory */
+  const double step_tol = c->tol > 0 ? c->tol : 1e-7;   /* interior-point stage tolerance (the polish follows) */
   const double tol = 1e-4 * step_tol;                  /* complementarity / residual floor */
   const int max_iter = c->max_iter > 0 ? c->max_iter : 60;
   const double Rm[3] = {c->R[0], 0.5 * (c->R[1] + c->R[2]), c->R[3]};
@@ -188,7 +191,14 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
   double rho_d = 1.0, prev_stepn = 0.0;
   int it, status = ORC_MAX_ITER;
 
-  for (it = 0; it < max_iter; it++) {
+  /* Active-set polish (what OSQP's polish=true does for the reference, racing_mpc.cpp:90-95), as one
+   * augmented-Lagrangian Newton step on the active set the interior point identified: active rows get the
+   * weight rho and the gradient y + rho (g'v - h), inactive rows are dropped, basic safe-set columns are free. */
+  const int do_polish = getenv("ORC_POLISH") ? atoi(getenv("ORC_POLISH")) : 1;
+  const double prho = getenv("ORC_PRHO") ? atof(getenv("ORC_PRHO")) : 1e8;
+  int polishing = 0, polish_tries = 0;
+  double step_tol2 = step_tol, tol2 = tol;
+  for (it = 0; it < max_iter || polishing; it++) {
     /* ---------- residuals, mu ---------- */
     double mu = 0.0, rpn = 0.0;
     for (int i = 0; i < N; i++) {
@@ -211,7 +221,37 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     for (int j = 0; j < K; j++) { mu += w->lam[j] * w->ylam[j]; rnu += w->lam[j]; }
     if (!learn) rnu = 0.0;
     mu /= (double)m_total;
-    if (mu < tol && rpn < tol && rho_d * R0 < tol && fabs(rnu) < tol) { status = ORC_OK; break; }
+    if (!polishing && mu < tol2 && rpn < tol2 && rho_d * R0 < tol2 && fabs(rnu) < tol2) {
+      if (!do_polish) { status = ORC_OK; break; }
+      polishing = 1;
+    }
+    if (polishing == 1) {   /* first polish round: classify from the interior-point iterate */
+      memcpy(w->xsave, w->x, sizeof w->xsave); memcpy(w->usave, w->u, sizeof w->usave); memcpy(w->lsave, w->lam, sizeof w->lsave); w->thsave = w->th;
+      memcpy(w->ysave, w->y, sizeof w->y); memcpy(w->ylsave, w->ylam, sizeof w->ylam); w->ythsave = w->yth; polish_tries++;
+      for (int j = 0; j < N * MAXROW; j++) w->pact[j] = w->act[j] && w->y[j] > w->s[j];
+      w->pact_th = soft && w->yth > w->th;
+      for (int j = 0; j < K; j++) w->pnb[j] = !(w->lam[j] >= w->ylam[j]);
+      for (int j = 0; j < N * MAXROW; j++) if (w->act[j] && !w->pact[j]) w->y[j] = 0.0;
+      if (soft && !w->pact_th) w->yth = 0.0;
+      for (int j = 0; j < K; j++) if (!w->pnb[j]) w->ylam[j] = 0.0;
+    }
+    if (polishing && learn) {   /* the explicit-column system holds at most MB free columns */
+      int nb = 0;
+      for (int j = 0; j < K; j++) if (!w->pnb[j]) nb++;
+      if (nb > MB || nb < 1) goto polish_failed;
+    }
+    if (0) {
+polish_failed:
+      /* no consistent active set: restore the interior-point iterate; the first time, keep iterating with a
+       * 100x tighter tolerance and try once more, the second time return the interior-point solution */
+      memcpy(w->x, w->xsave, sizeof(double) * 6 * (size_t)N); memcpy(w->u, w->usave, sizeof(double) * 2 * (size_t)N);
+      memcpy(w->lam, w->lsave, sizeof(double) * (size_t)(K > 0 ? K : 1)); w->th = w->thsave;
+      memcpy(w->y, w->ysave, sizeof w->y); memcpy(w->ylam, w->ylsave, sizeof w->ylam); w->yth = w->ythsave;
+      polishing = 0;
+      if (polish_tries >= 2 || it >= max_iter) { status = ORC_OK; break; }
+      step_tol2 *= 1e-2; tol2 *= 1e-2;
+      continue;
+    }
 
     /* hull residual sigma = x_{N-1} - c - St lam (the slack sigma_h by definition) */
     if (learn) {
@@ -224,11 +264,15 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     }
 
     double sigma = 0.0, alpha = 1.0, Pithth_keep = 0.0;
-    for (int pass = 0; pass < 2; pass++) {
+    for (int pass = 0; pass < (polishing ? 1 : 2); pass++) {
       const double smu = sigma * mu;
       /* ---------- assemble stage data ---------- */
       double Dthth = 0.0, cth = 0.0;
       if (soft) { Dthth = 2.0 * qb + w->yth / w->th; cth = 2.0 * qb * w->th - (smu - (pass ? w->corr_th : 0.0)) / w->th; }
+      if (soft && polishing) {
+        Dthth = 2.0 * qb; cth = 2.0 * qb * w->th;
+        if (w->pact_th) { Dthth += prho; cth += -w->yth + prho * w->th; }
+      }
       for (int i = 0; i < N; i++) {
         double* hx = w->hx + 6 * i; double* czx = w->czx + 6 * i;
         for (int k = 0; k < 6; k++) { hx[k] = 0.0; czx[k] = 0.0; }
@@ -242,8 +286,11 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         for (int sl = 0; sl < MAXROW; sl++) {
           const int j = RID(w, i, sl);
           if (!w->act[j]) continue;
-          const double d = w->y[j] / w->s[j];
-          const double t = (smu - (pass ? w->corr[j] : 0.0)) / w->s[j] + d * w->rp[j];
+          double d = w->y[j] / w->s[j];
+          double t = (smu - (pass ? w->corr[j] : 0.0)) / w->s[j] + d * w->rp[j];
+          if (polishing) {
+            if (w->pact[j]) { d = prho; t = w->y[j] + prho * (w->rp[j] - w->s[j]); } else { d = 0.0; t = 0.0; }
+          }
           const double sg = (sl < 12) ? w->xb_sg[sl] : ((sl & 1) ? -1.0 : 1.0);
           if (sl < 12) { hx[w->xb_c[sl]] += d; czx[w->xb_c[sl]] += sg * t; }
           else if (sl < 16) { dub[(sl - 12) >> 1] += d; tub[(sl - 12) >> 1] += sg * t; }
@@ -284,7 +331,10 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         double bvec[6] = {0, 0, 0, 0, 0, 0}, omg = 0.0;
         if (pass == 0) {
           memset(w->W, 0, sizeof w->W); memset(w->avec, 0, sizeof w->avec); w->om1 = 0.0;
-          for (int j = 0; j < K; j++) { w->om[j] = w->lam[j] / w->ylam[j]; w->isB[j] = 0; }
+          for (int j = 0; j < K; j++) {
+            w->om[j] = w->lam[j] / w->ylam[j]; w->isB[j] = 0; w->Dk[j] = w->ylam[j] / w->lam[j];
+            if (polishing) { const int basic = !w->pnb[j]; w->Dk[j] = basic ? 0.0 : prho; w->om[j] = basic ? 1e300 : 1.0 / prho; }
+          }
           w->mB = MB < K ? MB : K;
           for (int q = 0; q < w->mB; q++) {            /* top-MB by Omega, ties -> lowest index */
             int best = -1; double bv = -1.0;
@@ -294,7 +344,8 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         }
         const int mB = w->mB, nq = 1 + mB;
         for (int j = 0; j < K; j++) {
-          const double gl = p->ssc[j] - (smu - (pass ? w->corr_lam[j] : 0.0)) / w->lam[j];
+          double gl = p->ssc[j] - (smu - (pass ? w->corr_lam[j] : 0.0)) / w->lam[j];
+          if (polishing) gl = (w->Dk[j] > 0.0) ? p->ssc[j] - w->ylam[j] + prho * w->lam[j] : p->ssc[j];
           w->gl[j] = gl;
           if (w->isB[j]) continue;
           const double om = w->om[j];
@@ -309,7 +360,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         if (pass == 0) {
           double Lc[36];
           for (int a = 0; a < nh; a++) for (int b = 0; b <= a; b++) { Lc[6 * a + b] = w->W[6 * a + b] + (a == b ? w->Einv[a] : 0.0); }
-          if (chol6(Lc, nh)) { status = ORC_NUMERIC; goto done; }
+          if (chol6(Lc, nh)) { if (polishing) goto polish_failed; status = ORC_NUMERIC; goto done; }
           for (int col = 0; col < nh; col++) { double e[6] = {0, 0, 0, 0, 0, 0}; e[col] = 1.0; chol6_solve(Lc, nh, e); for (int a = 0; a < nh; a++) w->Phi[6 * a + col] = e[a]; }
           /* C = [-a_N, St_B]  (nh x nq);  PhiC = Phi C */
           double Cm[6 * QMAX];
@@ -318,7 +369,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
           /* S2 = Z - C' Phi C */
           for (int q = 0; q < nq; q++) for (int r = 0; r < nq; r++) {
             double z = 0.0;
-            if (q == 0 && r == 0) z = w->om1; else if (q == 0 || r == 0) z = -1.0; else if (q == r) z = -(w->ylam[w->Bidx[q - 1]] / w->lam[w->Bidx[q - 1]]);
+            if (q == 0 && r == 0) z = w->om1; else if (q == 0 || r == 0) z = -1.0; else if (q == r) z = -w->Dk[w->Bidx[q - 1]];
             double s2 = 0.0; for (int a = 0; a < nh; a++) s2 += Cm[a * QMAX + q] * w->PhiC[a * QMAX + r];
             w->S2[q * QMAX + r] = z - s2;
           }
@@ -327,7 +378,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
             int pk = k; double mx = fabs(w->S2[k * QMAX + k]);
             for (int i2 = k + 1; i2 < nq; i2++) if (fabs(w->S2[i2 * QMAX + k]) > mx) { mx = fabs(w->S2[i2 * QMAX + k]); pk = i2; }
             w->S2piv[k] = pk;
-            if (mx == 0.0) { status = ORC_NUMERIC; goto done; }
+            if (mx == 0.0) { if (polishing) goto polish_failed; status = ORC_NUMERIC; goto done; }
             if (pk != k) for (int c2 = 0; c2 < nq; c2++) { double t = w->S2[k * QMAX + c2]; w->S2[k * QMAX + c2] = w->S2[pk * QMAX + c2]; w->S2[pk * QMAX + c2] = t; }
             for (int i2 = k + 1; i2 < nq; i2++) { const double f = w->S2[i2 * QMAX + k] / w->S2[k * QMAX + k]; w->S2[i2 * QMAX + k] = f; for (int c2 = k + 1; c2 < nq; c2++) w->S2[i2 * QMAX + c2] -= f * w->S2[k * QMAX + c2]; }
           }
@@ -387,6 +438,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
           const double Qww[3] = {Yuu[0] + E[0] + Uq[0], Yuu[1] + E[1] + Uq[1], Yuu[2] + E[2] + Uq[2]};
           if (!(Qww[0] > 0.0) || !(Qww[0] * Qww[2] - Qww[1] * Qww[1] > 0.0)) {
             /* numerical floor of the barrier-weighted recursion: accept the iterate if already converged enough */
+            if (polishing) goto polish_failed;
             status = (mu < 1e-9 && rpn < 1e-9) ? ORC_OK : ORC_NUMERIC; goto done;
           }
           sym2_inv(Qww, Sinv);
@@ -533,6 +585,43 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         { const double eta = getenv("ORC_ETA") ? atof(getenv("ORC_ETA")) : 1.0; double tau = 1.0 - fmin(0.005, eta * mu); alpha = tau * amax; if (alpha > 1.0) alpha = 1.0; }
       }
     }
+    if (polishing) {
+      /* Full Newton step of the augmented-Lagrangian model on the primal, multiplier update y += rho r on the
+       * active rows, then one active-set refinement: active rows whose multiplier turned negative are released,
+       * violated inactive rows are activated, and the step is repeated (at most PMAX rounds). */
+      const double ftol = 1e-10, dtol = 1e-9;
+      int changed = 0, viol = 0;
+      for (int i = 0; i < N - 1; i++) for (int k = 0; k < 2; k++) w->u[2 * i + k] += w->du[2 * i + k];
+      for (int i = 1; i < N; i++) for (int k = 0; k < 6; k++) w->x[6 * i + k] += w->dx[6 * i + k];
+      if (soft) {
+        w->th += w->dth;
+        if (w->pact_th) { w->yth += prho * (-w->th); if (w->yth < -dtol) { w->pact_th = 0; w->yth = 0.0; changed++; } }
+        else if (w->th < -ftol) { w->pact_th = 1; changed++; }
+      }
+      for (int j = 0; j < K; j++) {
+        w->lam[j] += w->dlam[j];
+        if (w->pnb[j]) { w->ylam[j] += prho * (-w->lam[j]); if (w->ylam[j] < -dtol) { w->pnb[j] = 0; w->ylam[j] = 0.0; changed++; } }
+        else if (w->lam[j] < -ftol) { w->pnb[j] = 1; changed++; }
+      }
+      for (int i = 0; i < N; i++)
+        for (int sl = 0; sl < MAXROW; sl++) {
+          const int j = RID(w, i, sl);
+          if (!w->act[j]) continue;
+          double gv;
+          if (sl < 12) gv = w->xb_sg[sl] * w->x[6 * i + w->xb_c[sl]];
+          else if (sl < 16) { const int k = (sl - 12) >> 1; gv = ((sl & 1) ? -1.0 : 1.0) * w->u[2 * i + k]; }
+          else if (sl < 20) { const int k = (sl - 16) >> 1; const double up = i ? w->u[2 * (i - 1) + k] : p->u_ic[k]; gv = ((sl & 1) ? -1.0 : 1.0) * (w->u[2 * i + k] - up) / p->T[i]; }
+          else gv = ((sl & 1) ? -1.0 : 1.0) * w->x[6 * i + 1] - (soft ? w->th : 0.0);
+          const double r = gv - w->rh[j];
+          if (w->pact[j]) { w->y[j] += prho * r; if (w->y[j] < -dtol * fmax(1.0, fabs(w->y[j]))) { w->pact[j] = 0; w->y[j] = 0.0; changed++; } }
+          else if (r > ftol) { w->pact[j] = 1; changed++; }
+          if (!w->pact[j] && r > 1e-9) viol++;
+        }
+      if (changed && polishing < PMAX) { polishing++; continue; }
+      out->polished = (changed == 0 && viol == 0) ? polishing : 0;
+      if (out->polished) { status = ORC_OK; break; }
+      goto polish_failed;
+    }
     /* ---------- update ---------- */
     for (int i = 0; i < N - 1; i++) for (int k = 0; k < 2; k++) w->u[2 * i + k] += alpha * w->du[2 * i + k];
     for (int i = 1; i < N; i++) for (int k = 0; k < 6; k++) w->x[6 * i + k] += alpha * w->dx[6 * i + k];
@@ -557,7 +646,10 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       const double ratio = (prev_stepn > 0.0) ? stepn / prev_stepn : 1.0;
       const double est = (ratio < 0.9) ? stepn * ratio / (1.0 - ratio) : 1e300;
       prev_stepn = stepn;
-      if (!getenv("ORC_NOSTEP") && stepn < step_tol && est < step_tol && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) { status = ORC_OK; it++; break; }
+      if (!getenv("ORC_NOSTEP") && stepn < step_tol2 && est < step_tol2 && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) {
+        if (!do_polish) { status = ORC_OK; it++; break; }
+        polishing = 1;
+      }
     }
     if (getenv("ORC_PORT_DEBUG")) fprintf(stderr, "it %2d mu %.3e rp %.3e sigma %.3e alpha %.4f th %.3e rnu %.2e\n", it, mu, rpn, sigma, alpha, w->th, rnu);
   }
@@ -577,7 +669,7 @@ done:
   out->sigma_b = soft ? w->th : 0.0;
   memset(out->sigma_h, 0, sizeof out->sigma_h);
   if (learn) {
-    if (out->lambda) memcpy(out->lambda, w->lam, sizeof(double) * (size_t)K);
+    if (out->lambda) for (int j = 0; j < K; j++) out->lambda[j] = w->lam[j] > 0.0 ? w->lam[j] : 0.0;
     for (int k = 0; k < 6; k++) { double a = w->x[6 * (N - 1) + k]; for (int j = 0; j < K; j++) a -= p->ssx[6 * j + k] * w->lam[j]; out->sigma_h[k] = a; }
     if (out->ss_x) memcpy(out->ss_x, p->ssx, sizeof(double) * 6 * (size_t)K);
     if (out->ss_cost) memcpy(out->ss_cost, p->ssc, sizeof(double) * (size_t)K);
@@ -607,7 +699,7 @@ static void* batch_worker(void* arg) {
     out.lambda = j->lambda ? j->lambda + (size_t)K * b : NULL;
     const int st = j->impl ? orc_step_dense(j->v, j->c, j->ss, &in, &out) : orc_step_port(j->v, j->c, j->ss, &in, &out);
     if (j->cost) j->cost[b] = out.cost;
-    if (j->kkt) j->kkt[b] = out.kkt;
+    if (j->kkt) j->kkt[b] = j->impl ? out.kkt : (double)out.polished;   /* port: 1 = polish accepted */
     if (j->status) j->status[b] = st;
     if (j->iters) j->iters[b] = out.iters;
     if (st != ORC_OK) j->nfail++;

@@ -36,7 +36,7 @@ def barc_lmpc_config(N=20):
         x_max=[INF, INF, INF, 3.0, 1.0, 3.0], x_min=[-INF, -INF, -INF, 0.1, -1.0, -3.0],
         u_max=[0.01, 0.33], u_min=[-0.01, -0.33],
         convex_hull_slack=[40.0, 40.0, 4.0, 40.0, 40.0, 4.0],
-        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-9)
+        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-7)
 
 
 def barc_tracking_config(N=20):
@@ -47,7 +47,7 @@ def barc_tracking_config(N=20):
         x_max=[INF, INF, INF, 6.0, 1.0, 3.0], x_min=[-INF, -INF, -INF, 0.1, -1.0, -3.0],
         u_max=[0.01, 0.33], u_min=[-0.01, -0.33],
         convex_hull_slack=[20.0, 20.0, 2.0, 20.0, 20.0, 2.0],
-        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-9)
+        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-7)
 
 
 def iac_tracking_config(N=40):
@@ -58,7 +58,7 @@ def iac_tracking_config(N=40):
         x_max=[INF, INF, INF, 100.0, 15.0, 2.0], x_min=[-INF, -INF, -INF, 3.0, -15.0, -2.0],
         u_max=[5.0, 0.314159], u_min=[-10.0, -0.314159],
         convex_hull_slack=[20.0, 20.0, 2.0, 20.0, 20.0, 2.0],
-        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-9)
+        num_ss_pts=96, num_ss_pts_per_lap=32, max_lap_stored=3, max_iter=30, tol=1e-7)
 
 
 BARC_DT = 0.025           # launch/barc/sim_barc_lmpc.launch.py:81

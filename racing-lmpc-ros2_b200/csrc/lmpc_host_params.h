@@ -69,7 +69,7 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   P.Rm[0] = c.R[0]; P.Rm[1] = 0.5 * (c.R[1] + c.R[2]); P.Rm[2] = c.R[3];
   P.Rd[0] = c.R_d[0]; P.Rd[1] = 0.5 * (c.R_d[1] + c.R_d[2]); P.Rd[2] = c.R_d[3];
   P.max_iter = c.max_iter > 0 ? c.max_iter : 30;
-  P.tol = c.tol > 0.0 ? c.tol : 1e-9;
+  P.tol = c.tol > 0.0 ? c.tol : 1e-7;
   P.NSd = P.N | 1;
   if (NW != 1 && NW != 2 && NW != 4) return LMPC_ERR_INVALID;
   if (P.learning && (P.K + 32 * NW - 1) / (32 * NW) > LMPC_KPL_MAX) return LMPC_ERR_INVALID;

@@ -24,6 +24,8 @@
 #define LMPC_NQ (1 + LMPC_MB)   // + simplex multiplier
 #define LMPC_KPL_MAX 4          // safe-set columns per lane
 #define LMPC_NRED 36            // widest multi-value reduction
+#define LMPC_PMAX 4             // active-set refinement rounds of the polish
+#define LMPC_PRHO 1e8           // augmented-Lagrangian weight of the polish
 // Qzw row r lives in YY: rows 0..5 are Yxu = YY[8r+6..7]; rows 6,7 (= -E) are parked in YY[8r+0..1]
 #define QZ0(r) (((r) < 6) ? (8 * (r) + 6) : (8 * (r)))
 
@@ -286,14 +288,46 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   if (soft) R0 = fmax(R0, 2.0 * P.qb * th);
   double rho_d = 1.0, prev_stepn = 0.0;
   const double inv_m = 1.0 / (double)m_total;
-  const double mu_floor = 1e-4 * P.tol;
+  // Active-set polish (what OSQP's polish=true does for the reference, racing_mpc.cpp:90-95): once the interior
+  // point has identified the active set, one augmented-Lagrangian Newton step on it -- active rows get the
+  // weight rho and the gradient y + rho (g'v - h), inactive rows are dropped, basic safe-set columns are free --
+  // followed by up to PMAX active-set refinements.  During the polish the row arrays are re-purposed:
+  // sign(RSs) < 0 marks an active row, RSy holds the multiplier estimate, RSi keeps the saved y.
+  int polishing = 0, polish_tries = 0, classified = 0;
+  double tol_step = P.tol, tol_mu = 1e-4 * P.tol;
+  double xus[(LMPC_MAX_N + NT - 1) / NT][8];   // saved iterate of this lane's stages (restored if the polish fails)
+  double th_save = 0.0, yth_save = 0.0;
+  int pact_th = 0;
+  LaneVar<ArrK, NT> lsave, ylsave;
+  LaneVar<ArrKi, NT> pnb;
 
   // ================================================================ interior-point iterations
-  for (; status == LMPC_MAX_ITER && it < P.max_iter; it++) {
+  for (; status == LMPC_MAX_ITER && (it < P.max_iter || polishing); it++) {
     double sigma = 0.0, alpha = 1.0, Pithth_keep = 0.0, csc = 1.0, mu = 0.0, rpn = 0.0, rnu = 0.0;
     double sig[6] = {0, 0, 0, 0, 0, 0};
-    bool fail = false, converged = false;
-    for (int pass = 0; pass < 2 && !fail; pass++) {
+    bool fail = false, converged = false, restart = false;
+    if (polishing && !classified) {
+      // ---------- classify from the interior-point iterate, save what a failed polish must restore
+      GLANES_BEGIN(NT)
+        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i];
+          RSi[q.slot * d + i] = y;
+          if (y > s) RSs[q.slot * d + i] = -s; else RSy[q.slot * d + i] = 0.0;
+        }
+        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) xus[sidx][c] = X[c * d + i]; for (int c = 0; c < 2; c++) xus[sidx][6 + c] = (i < NS) ? U[c * d + i] : 0.0; sidx++; } }
+        for (int p = 0; p < KPL; p++) {
+          lsave(lane).a[p] = lam(lane).a[p]; ylsave(lane).a[p] = ylam(lane).a[p];
+          const bool basic = lam(lane).a[p] >= ylam(lane).a[p];
+          pnb(lane).a[p] = basic ? 0 : 1;
+          if (basic) ylam(lane).a[p] = 0.0;
+        }
+      GLANES_END(NW)
+      th_save = th; yth_save = yth;
+      pact_th = (soft && yth > th) ? 1 : 0;
+      if (soft && !pact_th) yth = 0.0;
+      classified = 1; polish_tries++;
+    }
+    for (int pass = 0; pass < (polishing ? 1 : 2) && !fail; pass++) {
       const double smu = sigma * mu;
       // ---------- rows -> per-stage Hessian / gradient pieces (one lane per (group, stage))
       LaneVar<double, NT> rs[12];
@@ -305,10 +339,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           FOR_ROWS(q, g, i) {
             const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
             const double is = y * isy;
-            const double dj = y * is;
+            double dj = y * is;
             const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
             double t = dj * rp;
-            if (pass) {
+            if (polishing) {
+              const bool act = s < 0.0;
+              dj = act ? LMPC_PRHO : 0.0;
+              t = act ? y + LMPC_PRHO * (rp - s) : 0.0;
+            } else if (pass) {
               // second-order term from the affine step: ds_a * dy_a with dy_a = -y - y ds_a / s
               const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
               const double dya_ = -y - dj * dsa;
@@ -328,15 +366,16 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
             GUD[(base + 2 + c) * d + i] = gsum;
           }
         }
-        double lsum = 0.0, sg6[6] = {0, 0, 0, 0, 0, 0};
+        double lsum = 0.0, sg6[6] = {0, 0, 0, 0, 0, 0}, nbasic = 0.0;
         if (!pass) for (int p = 0; p < KPL; p++) {
           const double l = lam(lane).a[p];
           msum += l * ylam(lane).a[p]; lsum += l;
           for (int a = 0; a < 6; a++) sg6[a] += St(lane).a[p][a] * l;
+          if (polishing && lane + NT * p < K && !pnb(lane).a[p]) nbasic += 1.0;
         }
         rs[0](lane) = dth_acc; rs[1](lane) = cth_acc; rs[2](lane) = msum; rs[3](lane) = rpm; rs[4](lane) = lsum;
         for (int a = 0; a < 6; a++) rs[5 + a](lane) = sg6[a];
-        rs[11](lane) = 0.0;
+        rs[11](lane) = nbasic;
       GLANES_END(NW)
       {
         const int ops[12] = {LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_MAX, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM,
@@ -349,12 +388,21 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         rpn = rs[3](0);
         rnu = learn ? rs[4](0) - 1.0 : 0.0;
         if (learn) for (int a = 0; a < 6; a++) sig[a] = (a < nh) ? X[P.hidx[a] * d + N - 1] - in.cen[P.hidx[a]] - rs[5 + a](0) : 0.0;
-        if (mu < mu_floor && rpn < mu_floor && rho_d * R0 < mu_floor && fabs(rnu) < mu_floor) { converged = true; break; }
+        if (!polishing && mu < tol_mu && rpn < tol_mu && rho_d * R0 < tol_mu && fabs(rnu) < tol_mu) {
+          // complementarity floor reached: polish from here (restart the trip so that the rows are re-assembled)
+          polishing = 1; classified = 0; restart = true; break;
+        }
+        if (polishing && learn && (rs[11](0) > LMPC_MB + 0.5 || rs[11](0) < 0.5)) { fail = true; break; }   // at most MB free columns
       }
       double corr_th = 0.0;
       if (soft) {
-        if (pass) corr_th = csc * dtha * dytha;
-        Dthth += 2.0 * P.qb + yth / th; cth += 2.0 * P.qb * th - (smu - corr_th) / th;
+        if (polishing) {
+          Dthth += 2.0 * P.qb; cth += 2.0 * P.qb * th;
+          if (pact_th) { Dthth += LMPC_PRHO; cth += -yth + LMPC_PRHO * th; }
+        } else {
+          if (pass) corr_th = csc * dtha * dytha;
+          Dthth += 2.0 * P.qb + yth / th; cth += 2.0 * P.qb * th - (smu - corr_th) / th;
+        }
       }
 
       // ---------- terminal value  P_{N-1}, l_{N-1}
@@ -366,7 +414,12 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         // ---- per-column weights; pass 0: the MB largest Omega become explicit columns
         if (pass == 0) {
           GLANES_BEGIN(NT)
-            for (int p = 0; p < KPL; p++) { const int k = lane + NT * p; omg_(lane).a[p] = (k < K) ? lam(lane).a[p] / ylam(lane).a[p] : -1.0; isB(lane).a[p] = 0; }
+            for (int p = 0; p < KPL; p++) {
+              const int k = lane + NT * p;
+              double om = (k < K) ? lam(lane).a[p] / ylam(lane).a[p] : -1.0;
+              if (polishing && k < K) om = pnb(lane).a[p] ? 1.0 / LMPC_PRHO : 1e300;   // free (basic) columns must be explicit
+              omg_(lane).a[p] = om; isB(lane).a[p] = 0;
+            }
           GLANES_END(NW)
           for (int q = 0; q < LMPC_MB; q++) {
             LaneVar<double, NT> bv; LaneVar<int, NT> bi;
@@ -381,7 +434,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               for (int p = 0; p < KPL; p++) if (lane + NT * p == kb) {
                 isB(lane).a[p] = 1 + q;
                 for (int a = 0; a < 6; a++) TB[TB_BCOL + 6 * q + a] = St(lane).a[p][a];
-                TB[TB_BD + q] = ylam(lane).a[p] / lam(lane).a[p];
+                TB[TB_BD + q] = polishing ? (pnb(lane).a[p] ? LMPC_PRHO : 0.0) : ylam(lane).a[p] / lam(lane).a[p];
               }
             GLANES_END(NW)
           }
@@ -401,7 +454,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               const double l = lam(lane).a[p];
               double tl = smu;
               if (pass) tl -= csc * dla(lane).a[p] * dya(lane).a[p];
-              const double gl = sscv(lane).a[p] - tl / l;
+              double gl = sscv(lane).a[p] - tl / l;
+              if (polishing) gl = pnb(lane).a[p] ? sscv(lane).a[p] - ylam(lane).a[p] + LMPC_PRHO * l : sscv(lane).a[p];
               glam(lane).a[p] = gl;
               if (isB(lane).a[p]) TB[TB_BG + isB(lane).a[p] - 1] = gl;
               else {
@@ -834,6 +888,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         GLANES_END(NW)
       }
       double dthc = dthp, dythc = 0.0;
+      if (polishing) { dtha = dthc; break; }   // the polish takes the full step below, no ratio test
       if (soft) { const double tt = (smu - corr_th) / th; dythc = tt - yth - (yth / th) * dthc; }
       if (pass) { dth = dthc; dyth = dythc; } else { dtha = dthc; dytha = dythc; }
 
@@ -890,10 +945,78 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         alpha = tau * amax; if (alpha > 1.0) alpha = 1.0;
       }
     }  // pass
-    if (converged) { status = LMPC_SOLVED; break; }
-    if (fail) {
+    if (restart) { it--; continue; }
+    bool polish_failed = false;
+    if (polishing && fail) polish_failed = true;
+    else if (fail) {
       status = (mu < 1e-9 && rpn < 1e-9) ? LMPC_SOLVED : LMPC_NUMERIC;   // numerical floor of the recursion
       break;
+    }
+    if (polishing && !polish_failed) {
+      // ---------- full Newton step of the augmented-Lagrangian model, multiplier update, active-set refinement
+      const double ftol = 1e-10, dtol = 1e-9;
+      GLANES_BEGIN(NT)
+        FOR_MY_STAGES(i) {
+          if (i >= 1) for (int c = 0; c < 6; c++) X[c * d + i] += DXA[c * d + i];
+          if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] += DUA[c * d + i];
+        }
+      GLANES_END(NW)
+      double changed = 0.0;
+      if (soft) {
+        th += dtha;
+        if (pact_th) { yth += LMPC_PRHO * (-th); if (yth < -dtol) { pact_th = 0; yth = 0.0; changed += 1.0; } }
+        else if (th < -ftol) { pact_th = 1; changed += 1.0; }
+      }
+      LaneVar<double, NT> rc2[2];
+      GLANES_BEGIN(NT)
+        double ch = 0.0, viol = 0.0;
+        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+          const double s = RSs[q.slot * d + i];
+          const double r = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) - row_bound(P, q, i, BL, BR);
+          bool act = s < 0.0;
+          if (act) {
+            const double yn = RSy[q.slot * d + i] + LMPC_PRHO * r;
+            if (yn < -dtol * fmax(1.0, fabs(yn))) { act = false; RSs[q.slot * d + i] = -s; RSy[q.slot * d + i] = 0.0; ch += 1.0; }
+            else RSy[q.slot * d + i] = yn;
+          } else if (r > ftol) { act = true; RSs[q.slot * d + i] = -s; ch += 1.0; }
+          if (!act && r > 1e-9) viol += 1.0;
+        }
+        for (int p = 0; p < KPL; p++) {
+          const int k = lane + NT * p;
+          if (k < K) {
+            const double l = lam(lane).a[p] + dla(lane).a[p];
+            lam(lane).a[p] = l;
+            if (pnb(lane).a[p]) { const double yn = ylam(lane).a[p] + LMPC_PRHO * (-l); if (yn < -dtol) { pnb(lane).a[p] = 0; ylam(lane).a[p] = 0.0; ch += 1.0; } else ylam(lane).a[p] = yn; }
+            else if (l < -ftol) { pnb(lane).a[p] = 1; ch += 1.0; }
+          }
+        }
+        rc2[0](lane) = ch; rc2[1](lane) = viol;
+      GLANES_END(NW)
+      {
+        const int ops[2] = {LMPC_RED_SUM, LMPC_RED_SUM};
+        group_reduce<NW, 2>(rc2, ops, RED);
+      }
+      changed += rc2[0](0);
+      if (changed > 0.5 && polishing < LMPC_PMAX) { polishing++; continue; }
+      if (changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }
+      polish_failed = true;
+    }
+    if (polish_failed) {
+      // no consistent active set: restore the interior-point iterate; the first time keep iterating with a
+      // 100x tighter tolerance and try once more, the second time return the interior-point solution
+      GLANES_BEGIN(NT)
+        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
+          const double s = fabs(RSs[q.slot * d + i]), y = RSi[q.slot * d + i];
+          RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
+        }
+        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = xus[sidx][c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = xus[sidx][6 + c]; sidx++; } }
+        for (int p = 0; p < KPL; p++) { lam(lane).a[p] = lsave(lane).a[p]; ylam(lane).a[p] = ylsave(lane).a[p]; }
+      GLANES_END(NW)
+      th = th_save; yth = yth_save;
+      polishing = 0; classified = 0;
+      if (polish_tries >= 2 || it >= P.max_iter) { status = LMPC_SOLVED; it++; break; }
+      tol_step *= 1e-2; tol_mu *= 1e-2;
+      continue;
     }
     // ---------- update the iterate: rows first (they read X/U of neighbouring stages), then the primal
     {
@@ -944,7 +1067,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #ifdef LMPC_DEBUG_TRACE
       LANE0_ONLY(if (LMPC_TRACE_COND) printf("it %2d mu %.6e rp %.3e sigma %.6e alpha %.6f th %.6e stepn %.3e csc %.3f\n", it, mu, rpn, sigma, alpha, th, stepn, csc);)
 #endif
-      if (stepn < P.tol && est < P.tol && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) { status = LMPC_SOLVED; it++; break; }
+      if (stepn < tol_step && est < tol_step && alpha > 0.5 && mu < 1e-6 && rpn < 1e-9 && fabs(rnu) < 1e-9) { polishing = 1; classified = 0; }
     }
   }  // iterations
 
@@ -985,7 +1108,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         cst += sscv(lane).a[p] * l;
         for (int a = 0; a < 6; a++) sg[a] += St(lane).a[p][a] * l;
       }
-      if (out.lam && k < P.K) out.lam[k] = (k < K) ? lam(lane).a[p] : 0.0;
+      if (out.lam && k < P.K) out.lam[k] = (k < K) ? fmax(lam(lane).a[p], 0.0) : 0.0;   // polished non-basic columns sit at -y/rho ~ 1e-20
     }
     ro[0](lane) = cst;
     for (int a = 0; a < 6; a++) ro[1 + a](lane) = sg[a];
