@@ -19,7 +19,7 @@
 
 #define NS ORC_NMAX
 #define QMAX 9              /* 1 + max explicit (basic) safe-set columns */
-#define PMAX 4               /* active-set refinement rounds of the polish */
+#define PMAX 6               /* active-set refinement rounds of the polish */
 #define MAXROW 22            /* per-stage row slots: 12 x-box + 4 u-box + 4 du-box + 2 boundary */
 
 typedef struct {
@@ -93,7 +93,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
   port_ws* w = (port_ws*)calloc(1, sizeof *w);
   const int N = p->N, K = p->K, soft = p->soft_boundary, learn = p->learning;
   const double step_tol = c->tol > 0 ? c->tol : 1e-7;   /* interior-point stage tolerance (the polish follows) */
-  const double tol = 1e-4 * step_tol;                  /* complementarity / residual floor */
+  const double tol = 0.1 * step_tol;                   /* complementarity level at which the polish takes over */
   const int max_iter = c->max_iter > 0 ? c->max_iter : 60;
   const double Rm[3] = {c->R[0], 0.5 * (c->R[1] + c->R[2]), c->R[3]};
   const double Rd[3] = {c->R_d[0], 0.5 * (c->R_d[1] + c->R_d[2]), c->R_d[3]};
@@ -195,8 +195,8 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
    * augmented-Lagrangian Newton step on the active set the interior point identified: active rows get the
    * weight rho and the gradient y + rho (g'v - h), inactive rows are dropped, basic safe-set columns are free. */
   const int do_polish = getenv("ORC_POLISH") ? atoi(getenv("ORC_POLISH")) : 1;
-  const double prho = getenv("ORC_PRHO") ? atof(getenv("ORC_PRHO")) : 1e8;
-  int polishing = 0, polish_tries = 0;
+  const double prho = getenv("ORC_PRHO") ? atof(getenv("ORC_PRHO")) : 1e7;
+  int polishing = 0, polish_tries = 0, numfail_polish = 0;
   double step_tol2 = step_tol, tol2 = tol;
   for (it = 0; it < max_iter || polishing; it++) {
     /* ---------- residuals, mu ---------- */
@@ -248,6 +248,7 @@ polish_failed:
       memcpy(w->lam, w->lsave, sizeof(double) * (size_t)(K > 0 ? K : 1)); w->th = w->thsave;
       memcpy(w->y, w->ysave, sizeof w->y); memcpy(w->ylam, w->ylsave, sizeof w->ylam); w->yth = w->ythsave;
       polishing = 0;
+      if (numfail_polish) { status = ORC_NUMERIC; break; }
       if (polish_tries >= 2 || it >= max_iter) { status = ORC_OK; break; }
       step_tol2 *= 1e-2; tol2 *= 1e-2;
       continue;
@@ -439,7 +440,8 @@ polish_failed:
           if (!(Qww[0] > 0.0) || !(Qww[0] * Qww[2] - Qww[1] * Qww[1] > 0.0)) {
             /* numerical floor of the barrier-weighted recursion: accept the iterate if already converged enough */
             if (polishing) goto polish_failed;
-            status = (mu < 1e-9 && rpn < 1e-9) ? ORC_OK : ORC_NUMERIC; goto done;
+            if (do_polish && !numfail_polish && mu < 1e-5) { numfail_polish = 1; polishing = 1; polish_tries = 1; it--; goto next_trip; }
+            status = ORC_NUMERIC; goto done;
           }
           sym2_inv(Qww, Sinv);
           /* Qzw = [Yxu; -E],  Kz = Sinv Qzw' (2x8) */
@@ -591,16 +593,17 @@ polish_failed:
        * violated inactive rows are activated, and the step is repeated (at most PMAX rounds). */
       const double ftol = 1e-10, dtol = 1e-9;
       int changed = 0, viol = 0;
+      double dymax = 0.0;   /* largest relative multiplier update: a second AL step removes the remaining bias */
       for (int i = 0; i < N - 1; i++) for (int k = 0; k < 2; k++) w->u[2 * i + k] += w->du[2 * i + k];
       for (int i = 1; i < N; i++) for (int k = 0; k < 6; k++) w->x[6 * i + k] += w->dx[6 * i + k];
       if (soft) {
         w->th += w->dth;
-        if (w->pact_th) { w->yth += prho * (-w->th); if (w->yth < -dtol) { w->pact_th = 0; w->yth = 0.0; changed++; } }
+        if (w->pact_th) { dymax = fmax(dymax, fabs(prho * w->th) / (1.0 + fabs(w->yth))); w->yth += prho * (-w->th); if (w->yth < -dtol) { w->pact_th = 0; w->yth = 0.0; changed++; } }
         else if (w->th < -ftol) { w->pact_th = 1; changed++; }
       }
       for (int j = 0; j < K; j++) {
         w->lam[j] += w->dlam[j];
-        if (w->pnb[j]) { w->ylam[j] += prho * (-w->lam[j]); if (w->ylam[j] < -dtol) { w->pnb[j] = 0; w->ylam[j] = 0.0; changed++; } }
+        if (w->pnb[j]) { dymax = fmax(dymax, fabs(prho * w->lam[j]) / (1.0 + fabs(w->ylam[j]))); w->ylam[j] += prho * (-w->lam[j]); if (w->ylam[j] < -dtol) { w->pnb[j] = 0; w->ylam[j] = 0.0; changed++; } }
         else if (w->lam[j] < -ftol) { w->pnb[j] = 1; changed++; }
       }
       for (int i = 0; i < N; i++)
@@ -613,11 +616,11 @@ polish_failed:
           else if (sl < 20) { const int k = (sl - 16) >> 1; const double up = i ? w->u[2 * (i - 1) + k] : p->u_ic[k]; gv = ((sl & 1) ? -1.0 : 1.0) * (w->u[2 * i + k] - up) / p->T[i]; }
           else gv = ((sl & 1) ? -1.0 : 1.0) * w->x[6 * i + 1] - (soft ? w->th : 0.0);
           const double r = gv - w->rh[j];
-          if (w->pact[j]) { w->y[j] += prho * r; if (w->y[j] < -dtol * fmax(1.0, fabs(w->y[j]))) { w->pact[j] = 0; w->y[j] = 0.0; changed++; } }
+          if (w->pact[j]) { dymax = fmax(dymax, fabs(prho * r) / (1.0 + fabs(w->y[j]))); w->y[j] += prho * r; if (w->y[j] < -dtol * fmax(1.0, fabs(w->y[j]))) { w->pact[j] = 0; w->y[j] = 0.0; changed++; } }
           else if (r > ftol) { w->pact[j] = 1; changed++; }
           if (!w->pact[j] && r > 1e-9) viol++;
         }
-      if (changed && polishing < PMAX) { polishing++; continue; }
+      if ((changed || dymax > 1e-4) && polishing < PMAX) { polishing++; continue; }
       out->polished = (changed == 0 && viol == 0) ? polishing : 0;
       if (out->polished) { status = ORC_OK; break; }
       goto polish_failed;
@@ -652,6 +655,7 @@ polish_failed:
       }
     }
     if (getenv("ORC_PORT_DEBUG")) fprintf(stderr, "it %2d mu %.3e rp %.3e sigma %.3e alpha %.4f th %.3e rnu %.2e\n", it, mu, rpn, sigma, alpha, w->th, rnu);
+    if (0) { next_trip: ; }
   }
 done:
   out->iters = it;

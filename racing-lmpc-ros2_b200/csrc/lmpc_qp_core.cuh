@@ -24,8 +24,15 @@
 #define LMPC_NQ (1 + LMPC_MB)   // + simplex multiplier
 #define LMPC_KPL_MAX 4          // safe-set columns per lane
 #define LMPC_NRED 36            // widest multi-value reduction
-#define LMPC_PMAX 4             // active-set refinement rounds of the polish
-#define LMPC_PRHO 1e8           // augmented-Lagrangian weight of the polish
+#ifndef LMPC_PMAX
+#define LMPC_PMAX 6             // active-set refinement rounds of the polish
+#endif
+#ifndef LMPC_PDY
+#define LMPC_PDY 1e-4           // relative multiplier change below which the augmented-Lagrangian iteration stops
+#endif
+#ifndef LMPC_PRHO
+#define LMPC_PRHO 1e7           // augmented-Lagrangian weight of the polish
+#endif
 // Qzw row r lives in YY: rows 0..5 are Yxu = YY[8r+6..7]; rows 6,7 (= -E) are parked in YY[8r+0..1]
 #define QZ0(r) (((r) < 6) ? (8 * (r) + 6) : (8 * (r)))
 
@@ -294,8 +301,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // followed by up to PMAX active-set refinements.  During the polish the row arrays are re-purposed:
   // sign(RSs) < 0 marks an active row, RSy holds the multiplier estimate, RSi keeps the saved y.
   int polishing = 0, polish_tries = 0, classified = 0;
-  double tol_step = P.tol, tol_mu = 1e-4 * P.tol;
-  double xus[(LMPC_MAX_N + NT - 1) / NT][8];   // saved iterate of this lane's stages (restored if the polish fails)
+  double tol_step = P.tol, tol_mu = 0.1 * P.tol;   // complementarity level at which the polish takes over
+  int numfail_polish = 0;
+  struct XuSave { double v[(LMPC_MAX_N + NT - 1) / NT][8]; };
+  LaneVar<XuSave, NT> xus_;                    // saved iterate of this lane's stages (restored if the polish fails)
   double th_save = 0.0, yth_save = 0.0;
   int pact_th = 0;
   LaneVar<ArrK, NT> lsave, ylsave;
@@ -314,7 +323,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           RSi[q.slot * d + i] = y;
           if (y > s) RSs[q.slot * d + i] = -s; else RSy[q.slot * d + i] = 0.0;
         }
-        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) xus[sidx][c] = X[c * d + i]; for (int c = 0; c < 2; c++) xus[sidx][6 + c] = (i < NS) ? U[c * d + i] : 0.0; sidx++; } }
+        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) xus_(lane).v[sidx][c] = X[c * d + i]; for (int c = 0; c < 2; c++) xus_(lane).v[sidx][6 + c] = (i < NS) ? U[c * d + i] : 0.0; sidx++; } }
         for (int p = 0; p < KPL; p++) {
           lsave(lane).a[p] = lam(lane).a[p]; ylsave(lane).a[p] = ylam(lane).a[p];
           const bool basic = lam(lane).a[p] >= ylam(lane).a[p];
@@ -743,11 +752,19 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               }
             }
           GLANES_END(NW)
+#ifdef LMPC_DEBUG_TRACE
+          if (polishing) { LANE0_ONLY(if (LMPC_TRACE_COND) printf("   st %2d Pdiag %.3e %.3e %.3e %.3e %.3e %.3e %.3e %.3e | hx %.2e %.2e %.2e %.2e %.2e | Yuu %.3e %.3e uq %.2e %.2e e %.2e %.2e\n", i, PM[0], PM[9], PM[18], PM[27], PM[36], PM[45], PM[54], PM[63], HX[1*d+i], HX[2*d+i], HX[3*d+i], HX[4*d+i], HX[5*d+i], YY[8*6+6], YY[8*7+7], uq0, uq2, e0, e2);) }
+#endif
           // phase c (uniform part): S = Yuu + E + Uq, its inverse, feed-forward terms
           const double q0_ = YY[8 * 6 + 6] + uq0, q1_ = 0.5 * (YY[8 * 6 + 7] + YY[8 * 7 + 6]) + uq1, q2_ = YY[8 * 7 + 7] + uq2;
           const double s0 = q0_ + e0, s1 = q1_ + e1, s2_ = q2_ + e2;
           const double det = s0 * s2_ - s1 * s1;
-          if (!(s0 > 0.0) || !(det > 0.0)) { fail = true; break; }
+          if (!(s0 > 0.0) || !(det > 0.0)) {
+#ifdef LMPC_DEBUG_TRACE
+            LANE0_ONLY(if (LMPC_TRACE_COND) printf("  S not PD at stage %d: s %.6e %.6e %.6e det %.3e | q %.6e %.6e %.6e e %.6e %.6e %.6e uq %.3e %.3e Yuu %.6e %.6e %.6e\n", i, s0, s1, s2_, det, q0_, q1_, q2_, e0, e1, e2, uq0, uq2, YY[8*6+6], YY[8*6+7], YY[8*7+7]);)
+#endif
+            fail = true; break;
+          }
           const double idet = 1.0 / det;
           const double i0 = s2_ * idet, i1 = -s1 * idet, i2_ = s0 * idet;
           const double cw1_0 = cwc0 + AXBW[6], cw1_1 = cwc1 + AXBW[7];
@@ -949,7 +966,9 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     bool polish_failed = false;
     if (polishing && fail) polish_failed = true;
     else if (fail) {
-      status = (mu < 1e-9 && rpn < 1e-9) ? LMPC_SOLVED : LMPC_NUMERIC;   // numerical floor of the recursion
+      // numerical floor of the barrier-weighted recursion: the iterate is intact, let the polish finish from it
+      if (!numfail_polish && mu < 1e-5) { numfail_polish = 1; polishing = 1; classified = 0; polish_tries = 0; continue; }
+      status = LMPC_NUMERIC;
       break;
     }
     if (polishing && !polish_failed) {
@@ -961,21 +980,23 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] += DUA[c * d + i];
         }
       GLANES_END(NW)
-      double changed = 0.0;
+      double changed = 0.0, dymax_u = 0.0;
       if (soft) {
         th += dtha;
-        if (pact_th) { yth += LMPC_PRHO * (-th); if (yth < -dtol) { pact_th = 0; yth = 0.0; changed += 1.0; } }
+        if (pact_th) { dymax_u = fabs(LMPC_PRHO * th) / (1.0 + fabs(yth)); yth += LMPC_PRHO * (-th); if (yth < -dtol) { pact_th = 0; yth = 0.0; changed += 1.0; } }
         else if (th < -ftol) { pact_th = 1; changed += 1.0; }
       }
-      LaneVar<double, NT> rc2[2];
+      LaneVar<double, NT> rc2[3];
       GLANES_BEGIN(NT)
-        double ch = 0.0, viol = 0.0;
+        double ch = 0.0, viol = 0.0, dym = 0.0;
         FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
           const double s = RSs[q.slot * d + i];
           const double r = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) - row_bound(P, q, i, BL, BR);
           bool act = s < 0.0;
           if (act) {
-            const double yn = RSy[q.slot * d + i] + LMPC_PRHO * r;
+            const double yo = RSy[q.slot * d + i];
+            const double yn = yo + LMPC_PRHO * r;
+            dym = fmax(dym, fabs(LMPC_PRHO * r) / (1.0 + fabs(yo)));
             if (yn < -dtol * fmax(1.0, fabs(yn))) { act = false; RSs[q.slot * d + i] = -s; RSy[q.slot * d + i] = 0.0; ch += 1.0; }
             else RSy[q.slot * d + i] = yn;
           } else if (r > ftol) { act = true; RSs[q.slot * d + i] = -s; ch += 1.0; }
@@ -986,22 +1007,29 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           if (k < K) {
             const double l = lam(lane).a[p] + dla(lane).a[p];
             lam(lane).a[p] = l;
-            if (pnb(lane).a[p]) { const double yn = ylam(lane).a[p] + LMPC_PRHO * (-l); if (yn < -dtol) { pnb(lane).a[p] = 0; ylam(lane).a[p] = 0.0; ch += 1.0; } else ylam(lane).a[p] = yn; }
+            if (pnb(lane).a[p]) { dym = fmax(dym, fabs(LMPC_PRHO * l) / (1.0 + fabs(ylam(lane).a[p]))); const double yn = ylam(lane).a[p] + LMPC_PRHO * (-l); if (yn < -dtol) { pnb(lane).a[p] = 0; ylam(lane).a[p] = 0.0; ch += 1.0; } else ylam(lane).a[p] = yn; }
             else if (l < -ftol) { pnb(lane).a[p] = 1; ch += 1.0; }
           }
         }
-        rc2[0](lane) = ch; rc2[1](lane) = viol;
+        rc2[0](lane) = ch; rc2[1](lane) = viol; rc2[2](lane) = dym;
       GLANES_END(NW)
       {
-        const int ops[2] = {LMPC_RED_SUM, LMPC_RED_SUM};
-        group_reduce<NW, 2>(rc2, ops, RED);
+        const int ops[3] = {LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_MAX};
+        group_reduce<NW, 3>(rc2, ops, RED);
       }
       changed += rc2[0](0);
-      if (changed > 0.5 && polishing < LMPC_PMAX) { polishing++; continue; }
+      const double dymax = fmax(dymax_u, rc2[2](0));   // a second AL step removes the bias left by inexact multipliers
+#ifdef LMPC_DEBUG_TRACE
+      LANE0_ONLY(if (LMPC_TRACE_COND) printf("  polish round %d: changed %.0f viol %.0f th %.3e pact_th %d\n", polishing, changed, rc2[1](0), th, pact_th);)
+#endif
+      if ((changed > 0.5 || dymax > LMPC_PDY) && polishing < LMPC_PMAX) { polishing++; continue; }
       if (changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }
       polish_failed = true;
     }
     if (polish_failed) {
+#ifdef LMPC_DEBUG_TRACE
+      LANE0_ONLY(if (LMPC_TRACE_COND) printf("  polish FAILED (fail=%d) tries %d it %d\n", (int)fail, polish_tries, it);)
+#endif
       // no consistent active set: restore the interior-point iterate; the first time keep iterating with a
       // 100x tighter tolerance and try once more, the second time return the interior-point solution
       GLANES_BEGIN(NT)
@@ -1009,11 +1037,12 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const double s = fabs(RSs[q.slot * d + i]), y = RSi[q.slot * d + i];
           RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
         }
-        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = xus[sidx][c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = xus[sidx][6 + c]; sidx++; } }
+        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = xus_(lane).v[sidx][c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = xus_(lane).v[sidx][6 + c]; sidx++; } }
         for (int p = 0; p < KPL; p++) { lam(lane).a[p] = lsave(lane).a[p]; ylam(lane).a[p] = ylsave(lane).a[p]; }
       GLANES_END(NW)
       th = th_save; yth = yth_save;
       polishing = 0; classified = 0;
+      if (numfail_polish) { status = LMPC_NUMERIC; it++; break; }
       if (polish_tries >= 2 || it >= P.max_iter) { status = LMPC_SOLVED; it++; break; }
       tol_step *= 1e-2; tol_mu *= 1e-2;
       continue;
