@@ -171,6 +171,10 @@ int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_
  * returns the summed milliseconds {linearise, safe-set query, QP} over the recorded solves. */
 int lmpc_set_timing(lmpc_handle* h, int enable);
 int lmpc_get_kernel_ms(lmpc_handle* h, double* ms3, int* nsolves);
+/* Measurement aid for the fp64 roofline: runs a register-resident chain of independent DFMAs on every
+ * SM of the handle's device and returns the sustained rate in TFLOP/s (2 flop per DFMA lane).  This is the
+ * denominator of the fp64-pipe fraction bench.py reports; MEASURED_PEAKS.json carries no fp64 figure. */
+int lmpc_measure_fp64_peak(lmpc_handle* h, double* tflops);
 /* Blocks until everything enqueued on the handle's stream has finished. */
 int lmpc_synchronize(lmpc_handle* h);
 

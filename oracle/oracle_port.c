@@ -188,7 +188,8 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     for (int j = 0; j < K; j++) if (fabs(p->ssc[j]) > R0) R0 = fabs(p->ssc[j]);
     if (2.0 * qb * w->th > R0) R0 = 2.0 * qb * w->th;
   }
-  double rho_d = 1.0, prev_stepn = 0.0;
+  double rho_d = 1.0, prev_stepn = 0.0, mu_m1 = 1e300, mu_m2 = 1e300, mu_m3 = 1e300;
+  const double stall_frac = getenv("ORC_STALL") ? atof(getenv("ORC_STALL")) : 0.5;
   int it, status = ORC_MAX_ITER;
 
   /* Active-set polish (what OSQP's polish=true does for the reference, racing_mpc.cpp:90-95), as one
@@ -225,6 +226,11 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       if (!do_polish) { status = ORC_OK; break; }
       polishing = 1;
     }
+    /* stalled interior point (Mehrotra limit cycle at a badly centred iterate: mu has not halved over
+     * three iterations although the iterate is primal feasible): let the active-set polish decide from here */
+    if (!polishing && do_polish && polish_tries < 2 && it >= 3 && mu < 1e-5 && rpn < 1e-8 && fabs(rnu) < 1e-8 &&
+        mu > stall_frac * mu_m3) polishing = 1;
+    if (!polishing) { mu_m3 = mu_m2; mu_m2 = mu_m1; mu_m1 = mu; }
     if (polishing == 1) {   /* first polish round: classify from the interior-point iterate */
       memcpy(w->xsave, w->x, sizeof w->xsave); memcpy(w->usave, w->u, sizeof w->usave); memcpy(w->lsave, w->lam, sizeof w->lsave); w->thsave = w->th;
       memcpy(w->ysave, w->y, sizeof w->y); memcpy(w->ylsave, w->ylam, sizeof w->ylam); w->ythsave = w->yth; polish_tries++;

@@ -69,7 +69,7 @@ EXPORTS = [
     "lmpc_last_error", "lmpc_launch_count", "lmpc_safe_set_add_lap", "lmpc_safe_set_load",
     "lmpc_safe_set_clear", "lmpc_safe_set_num_laps", "lmpc_safe_set_query_batch",
     "lmpc_discrete_dynamics_batch", "lmpc_linearise_batch", "lmpc_solve_batch", "lmpc_synchronize",
-    "lmpc_set_timing", "lmpc_get_kernel_ms",
+    "lmpc_set_timing", "lmpc_get_kernel_ms", "lmpc_measure_fp64_peak",
 ]
 
 _lib = None
@@ -108,6 +108,7 @@ def load_library(path=None):
     L.lmpc_synchronize.argtypes = [vp]
     L.lmpc_set_timing.argtypes = [vp, C.c_int]
     L.lmpc_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.lmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     if path is None:
         _lib = L
     return L

@@ -197,6 +197,45 @@ extern "C" int lmpc_get_kernel_ms(lmpc_handle* h, double* ms3, int* nsolves) {
   return LMPC_OK;
 }
 
+// fp64 FMA throughput probe: 8 independent accumulator chains per thread, no memory traffic in the loop
+__global__ void __launch_bounds__(256) lmpc_dfma_probe_kernel(double* sink, double a, double b, int iters) {
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = (double)(threadIdx.x + k);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = fma(acc[k], a, b);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) t += acc[k];
+  if (t == 123.456) sink[0] = t;   // never true: keeps the chains alive
+}
+
+extern "C" int lmpc_measure_fp64_peak(lmpc_handle* h, double* tflops) {
+  if (!h || !tflops) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  DevBuf sink;
+  const int rc = dev_reserve(h, sink, sizeof(double));
+  if (rc != LMPC_OK) return rc;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  lmpc_dfma_probe_kernel<<<blocks, threads, 0, h->stream>>>((double*)sink.p, 0.999999, 1e-9, 256);   // warm-up
+  CK(cudaEventRecord(e0, h->stream));
+  lmpc_dfma_probe_kernel<<<blocks, threads, 0, h->stream>>>((double*)sink.p, 0.999999, 1e-9, iters);
+  CK(cudaEventRecord(e1, h->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink.p);
+  *tflops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads / ((double)ms * 1e-3) * 1e-12;
+  return LMPC_OK;
+}
+
 extern "C" int lmpc_synchronize(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));

@@ -293,7 +293,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     for (int q = 0; q < 10; q++) chs_[q] = 1.0 / r[2 + q](0);
   }
   if (soft) R0 = fmax(R0, 2.0 * P.qb * th);
-  double rho_d = 1.0, prev_stepn = 0.0;
+  double rho_d = 1.0, prev_stepn = 0.0, mu_m1 = 1e300, mu_m2 = 1e300, mu_m3 = 1e300;
   const double inv_m = 1.0 / (double)m_total;
   // Active-set polish (what OSQP's polish=true does for the reference, racing_mpc.cpp:90-95): once the interior
   // point has identified the active set, one augmented-Lagrangian Newton step on it -- active rows get the
@@ -401,6 +401,12 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           // complementarity floor reached: polish from here (restart the trip so that the rows are re-assembled)
           polishing = 1; classified = 0; restart = true; break;
         }
+        // stalled interior point (Mehrotra limit cycle at a badly centred iterate: mu has not halved over three
+        // iterations although the iterate is primal feasible): let the active-set polish decide from here
+        if (!polishing && polish_tries < 2 && it >= 3 && mu < 1e-5 && rpn < 1e-8 && fabs(rnu) < 1e-8 && mu > 0.5 * mu_m3) {
+          polishing = 1; classified = 0; restart = true; break;
+        }
+        if (!polishing) { mu_m3 = mu_m2; mu_m2 = mu_m1; mu_m1 = mu; }
         if (polishing && learn && (rs[11](0) > LMPC_MB + 0.5 || rs[11](0) < 0.5)) { fail = true; break; }   // at most MB free columns
       }
       double corr_th = 0.0;

@@ -84,6 +84,12 @@ class BatchedRacingMPC:
         _check(self.lib, self._h, self.lib.lmpc_get_kernel_ms(self._h, ms, C.byref(n)), "lmpc_get_kernel_ms")
         return (ms[0], ms[1], ms[2]), n.value
 
+    def measure_fp64_peak(self):
+        """Sustained DFMA rate of this device in TFLOP/s (denominator of the fp64-pipe fraction)."""
+        v = C.c_double()
+        _check(self.lib, self._h, self.lib.lmpc_measure_fp64_peak(self._h, C.byref(v)), "lmpc_measure_fp64_peak")
+        return v.value
+
     @property
     def launch_count(self):
         return int(self.lib.lmpc_launch_count(self._h))

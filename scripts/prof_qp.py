@@ -7,7 +7,9 @@ import racing_lmpc_ros2_b200 as P
 from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
 Bn = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-veh = P.configs.BARC_VEHICLE; cfg = P.configs.barc_lmpc_config(20); cfg["tol"] = float(os.environ.get("LMPC_TOL", "1e-13")); cfg["max_iter"] = int(os.environ.get("LMPC_MAXIT", "60"))
+veh = P.configs.BARC_VEHICLE; cfg = P.configs.barc_lmpc_config(20)
+if "LMPC_TOL" in os.environ: cfg["tol"] = float(os.environ["LMPC_TOL"])
+if "LMPC_MAXIT" in os.environ: cfg["max_iter"] = int(os.environ["LMPC_MAXIT"])
 laps = P.workload.load_laps(); tr = P.workload.load_track("barc_center")
 mpc = BatchedRacingMPC(veh, cfg, max_batch=Bn)
 for l in laps: mpc.add_lap(l["x"], l["u"], l["k"], l["t"], tr["length"])
