@@ -80,7 +80,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("LMPC_B200_LIB") or LIB_PATH   # LMPC_B200_LIB: an alternate build of the same ABI
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} is missing: the CUDA library is not built (run `python -c 'import __graft_entry__ as g; "

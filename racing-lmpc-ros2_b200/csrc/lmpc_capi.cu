@@ -62,6 +62,7 @@ static int qp_fixed_n(const lmpc_handle* h) {
   const char* e = getenv("LMPC_FIXED_LAYOUT");
   if (e && atoi(e) == 0) return 0;
   if (h->P.NW == 1 && h->P.RS == 16 && (h->P.N == 20 || h->P.N == 40)) return h->P.N;
+  if (h->P.NW == 2 && h->P.RS == 16 && h->P.N == 20) return h->P.N;
   return 0;
 }
 
@@ -108,7 +109,8 @@ extern "C" int64_t lmpc_launch_count(const lmpc_handle* h) { return h ? h->launc
       if (NFv == 20) { if (KPLv <= 1) { CALL(1, 1, 20, 16); } else if (KPLv == 2) { CALL(1, 2, 20, 16); } else if (KPLv == 3) { CALL(1, 3, 20, 16); } else { CALL(1, 4, 20, 16); } } \
       else if (NFv == 40) { if (KPLv <= 1) { CALL(1, 1, 40, 16); } else if (KPLv == 2) { CALL(1, 2, 40, 16); } else if (KPLv == 3) { CALL(1, 3, 40, 16); } else { CALL(1, 4, 40, 16); } } \
       else { if (KPLv <= 1) { CALL(1, 1, 0, 0); } else if (KPLv == 2) { CALL(1, 2, 0, 0); } else if (KPLv == 3) { CALL(1, 3, 0, 0); } else { CALL(1, 4, 0, 0); } } \
-    } else if (NWv == 2) { if (KPLv <= 1) { CALL(2, 1, 0, 0); } else { CALL(2, 2, 0, 0); } } \
+    } else if (NWv == 2) { if (NFv == 20) { if (KPLv <= 1) { CALL(2, 1, 20, 16); } else { CALL(2, 2, 20, 16); } } \
+                           else if (KPLv <= 1) { CALL(2, 1, 0, 0); } else { CALL(2, 2, 0, 0); } } \
     else { CALL(4, 1, 0, 0); }                                                       \
   } while (0)
 
@@ -355,10 +357,14 @@ extern "C" int lmpc_safe_set_num_laps(const lmpc_handle* h) { return h ? (int)h-
 
 // newest -> oldest while num_total < max_total (safe_set.cpp:164); the columns a lap contributes and
 // where they land do not depend on the query
-static void make_lap_table(const lmpc_handle* h, int max_total, int per_lap, LmpcLapTable* tab) {
+static int make_lap_table(lmpc_handle* h, int max_total, int per_lap, LmpcLapTable* tab) {
   tab->n_used = 0; tab->count = 0;
   int total = 0;
-  for (size_t j = 0; j < h->dev_laps.size() && total < max_total && tab->n_used < LMPC_MAX_LAPS_USED; j++) {
+  for (size_t j = 0; j < h->dev_laps.size() && total < max_total; j++) {
+    if (tab->n_used >= LMPC_MAX_LAPS_USED) {   // never truncate silently: the result would differ from the reference's
+      h->err = "safe-set query needs more than " + std::to_string(LMPC_MAX_LAPS_USED) + " laps (num_ss_pts / num_ss_pts_per_lap too large)";
+      return LMPC_ERR_INVALID;
+    }
     LmpcLapView v = h->dev_laps[j];
     v.take = std::min(per_lap, v.m);
     v.out_off = total;
@@ -366,6 +372,7 @@ static void make_lap_table(const lmpc_handle* h, int max_total, int per_lap, Lmp
     tab->lap[tab->n_used++] = v;
   }
   tab->count = std::min(total, max_total);
+  return LMPC_OK;
 }
 
 static int launch_ss_query(lmpc_handle* h, const LmpcLapTable& tab, int B, const double* d_query, int qstride,
@@ -384,7 +391,7 @@ extern "C" int lmpc_safe_set_query_batch(lmpc_handle* h, int B, const double* qu
   if (!h || B < 1 || !query || !ss_x || !ss_j || max_total < 1 || max_per_lap < 1) return LMPC_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   LmpcLapTable tab;
-  make_lap_table(h, max_total, max_per_lap, &tab);
+  { const int rc = make_lap_table(h, max_total, max_per_lap, &tab); if (rc != LMPC_OK) return rc; }
   const size_t nq = 2 * (size_t)B, nx = 6 * (size_t)max_total * B, nj = (size_t)max_total * B;
   const double* dq = query; double* dx = ss_x; double* dj = ss_j;
   if (memspace == LMPC_MEM_HOST) {
@@ -526,8 +533,9 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
   LmpcLapTable tab;
   tab.n_used = 0; tab.count = 0;
   if (learn) {
-    make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
-    int rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, ssx, ssj);
+    int rc = make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
+    if (rc != LMPC_OK) return rc;
+    rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, ssx, ssj);
     if (rc != LMPC_OK) return rc;
   }
   if (tev) CK(cudaEventRecord(tev[2], h->stream));

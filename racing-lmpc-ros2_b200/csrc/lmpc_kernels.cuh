@@ -11,7 +11,7 @@
 #include "lmpc_qp_core.cuh"
 #include "lmpc_ss_core.cuh"
 
-#define LMPC_MAX_LAPS_USED 16
+#define LMPC_MAX_LAPS_USED 64   // laps one query can draw from (the table travels as a kernel parameter, 3.6 KB)
 
 struct LmpcLapTable {
   LmpcLapView lap[LMPC_MAX_LAPS_USED];

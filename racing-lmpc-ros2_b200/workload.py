@@ -17,6 +17,20 @@ def load_laps():
             for i in (1, 2, 3)]
 
 
+def synthesise_laps(laps, n_laps, seed=0xB200 + 4, sigma_ey=0.02, sigma_vx=0.05):
+    """BASELINE configs[3]'s "50-lap learned safe set" (SURVEY.md 8d): the recorded laps cycled and perturbed
+    (e_y and v_x, per-sample Gaussian, fixed seed) -> n_laps laps of ~440 samples, ~66 k tripled points for 50."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    out = []
+    for j in range(n_laps):
+        src = laps[j % len(laps)]
+        x = src["x"].copy()
+        x[:, 1] += rng.standard_normal(x.shape[0]) * sigma_ey
+        x[:, 3] += rng.standard_normal(x.shape[0]) * sigma_vx
+        out.append(dict(x=x, u=src["u"].copy(), k=src["k"].copy(), t=src["t"].copy()))
+    return out
+
+
 def load_track(name):
     z = np.load(os.path.join(_GOLD, "tracks.npz"))
     return dict(s=z[f"{name}_s"], speed=z[f"{name}_speed"], curvature=z[f"{name}_curvature"],

@@ -158,3 +158,23 @@ def test_emulated_ss_query_exact_fallback(emu, pkg):
                          C.c_double(5.0), C.c_double(0.0), 32, _p(sx), _p(sj), 1, 32, 32)
     ox, oj = o.ss_query(5.0, 0.0, max_total=32, per_lap=32)
     assert np.array_equal(sx, ox) and np.array_equal(sj, oj)
+
+
+def test_emulated_qp_kernel_fifty_lap_variant(emu, pkg, laps, barc_track):
+    """configs[3] with 2 points per lap: the 96 columns come from 48 different laps (spread-out hull)."""
+    from oracle import Oracle
+    veh = pkg.configs.BARC_VEHICLE
+    many = pkg.workload.synthesise_laps(laps, 50)
+    cfg = dict(pkg.configs.barc_lmpc_config(20), max_lap_stored=50, num_ss_pts_per_lap=2)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    for l in many:
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], barc_track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 6, 0xB200 + 4, barc_track, many, mode="barc")
+    worst = 0.0; n = 0
+    for b in range(6):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        k = _emu_solve(emu, pkg, od, veh, cfg, inp)
+        if d["status"] == 0 and d["kkt"] < 1e-10 and k["status"] == 0:
+            worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"])); n += 1
+    assert n >= 4 and worst < 1e-6, (n, worst)

@@ -230,3 +230,42 @@ def test_horizon_is_a_runtime_parameter(pkg):
         assert sel.sum() >= 4
         e = max(relerr(out["X_optm"][sel], ref["X"][sel]), relerr(out["U_optm"][sel], ref["U"][sel]), relerr(out["dU_optm"][sel], ref["dU"][sel]))
         assert e < TOL, (name, N, e)
+
+
+def test_fifty_lap_safe_set_config4(pkg, laps, barc_track):
+    """BASELINE configs[3]: 50 stored laps (~66 k tripled points).  (a) the reference's semantic -- only the newest
+    ceil(96/32) = 3 laps are searched (safe_set.cpp:164); (b) the num_ss_pts_per_lap = 2 variant that really draws
+    from 48 laps.  Query bit-exact, solve within TOL of the oracle."""
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    from oracle import Oracle
+    veh = pkg.configs.BARC_VEHICLE
+    L = barc_track["length"]
+    many = pkg.workload.synthesise_laps(laps, 50)
+    assert sum(3 * l["x"].shape[0] for l in many) > 50000
+    rng = np.random.default_rng(11)
+    q = np.column_stack([rng.uniform(-5, 25, 64), rng.uniform(-.5, .5, 64)])
+    for per_lap in (32, 2):
+        cfg = dict(pkg.configs.barc_lmpc_config(20), max_lap_stored=50, num_ss_pts_per_lap=per_lap)
+        m = BatchedRacingMPC(veh, cfg, max_batch=64); o = Oracle(veh, cfg)
+        for l in many:
+            m.add_lap(l["x"], l["u"], l["k"], l["t"], L); o.add_lap(l["x"], l["u"], l["k"], l["t"], L)
+        assert m.num_laps() == 50
+        sx, sj = m.ss_query(q)
+        for i in range(len(q)):
+            ox, oj = o.ss_query(q[i, 0], q[i, 1])
+            assert np.array_equal(sx[i], ox) and np.array_equal(sj[i], oj), (per_lap, i)
+        batch = pkg.workload.make_batch(veh, cfg, 64, 0xB200 + 4, barc_track, many, mode="barc")
+        out = m.solve(batch)
+        ref = o.step_batch(batch, impl="port", nthreads=8)
+        sel = (out["status"] == 0) & (ref["status"] == 0)
+        assert sel.sum() >= 60, (per_lap, np.bincount(out["status"], minlength=5), np.bincount(ref["status"], minlength=5))
+        e = max(max(relerr(out["X_optm"][b], ref["X"][b]), relerr(out["U_optm"][b], ref["U"][b]), relerr(out["dU_optm"][b], ref["dU"][b]))
+                for b in np.where(sel)[0])
+        assert e < TOL, (per_lap, e)
+    # a query that would need more laps than one launch can draw from is refused, not truncated
+    cfg = dict(pkg.configs.barc_lmpc_config(20), max_lap_stored=100, num_ss_pts_per_lap=1)
+    m = BatchedRacingMPC(veh, cfg, max_batch=4)
+    for l in pkg.workload.synthesise_laps(laps, 70):
+        m.add_lap(l["x"], l["u"], l["k"], l["t"], L)
+    with pytest.raises(RuntimeError):
+        m.ss_query(q[:2])

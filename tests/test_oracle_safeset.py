@@ -89,3 +89,23 @@ def test_duplicate_keys_resolve_to_first_index(pkg):
     sx, sj = o.ss_query(1.0, 0.0, max_total=2, per_lap=2)
     # both nearest points share the key (1, 0): the coordinate hash returns the first inserted index twice
     assert np.all(sx[:, 3] == 11) and np.all(sj == 3)
+
+
+def test_fifty_lap_safe_set_config4(pkg, laps, barc_track):
+    """BASELINE configs[3]: 50 laps stored; 32 per lap searches the newest 3 only (safe_set.cpp:164), 2 per lap
+    draws from 48 laps."""
+    from oracle import Oracle
+    veh = pkg.configs.BARC_VEHICLE
+    L = barc_track["length"]
+    many = pkg.workload.synthesise_laps(laps, 50)
+    rng = np.random.default_rng(3)
+    for per_lap in (32, 2):
+        cfg = dict(pkg.configs.barc_lmpc_config(20), max_lap_stored=50, num_ss_pts_per_lap=per_lap)
+        o = Oracle(veh, cfg)
+        for l in many:
+            o.add_lap(l["x"], l["u"], l["k"], l["t"], L)
+        for _ in range(10):
+            qs, qe = rng.uniform(-3, 20), rng.uniform(-0.4, 0.4)
+            sx, sj = o.ss_query(qs, qe)
+            bx, bj = _brute(many, L, qs, qe, 96, per_lap)
+            assert np.array_equal(sx, bx) and np.array_equal(sj, bj)
