@@ -35,6 +35,9 @@
 #endif
 // Qzw row r lives in YY: rows 0..5 are Yxu = YY[8r+6..7]; rows 6,7 (= -E) are parked in YY[8r+0..1]
 #define QZ0(r) (((r) < 6) ? (8 * (r) + 6) : (8 * (r)))
+// 8x8 block phases: LMPC_L8 rows of 8 outputs per round, LMPC_R8 rounds (NT = 32: 4 x 2; 64: 8 x 1; 128: 8 x 1, half idle)
+#define LMPC_L8 ((NT) >= 64 ? 8 : (NT) / 8)
+#define LMPC_R8 (8 / LMPC_L8)
 
 // Shared-memory layout (offsets in doubles) as a function of (N, rows per stage, warps per instance).
 // constexpr so that the kernels instantiated for the named horizons fold every address into an immediate.
@@ -701,60 +704,78 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #endif
       if (fail) break;
 
+      // ---------- per-stage control pieces of the sweep, one lane per stage (they do not depend on the recursion):
+      // GUD rows 2,3 <- cw, 6,7 <- ev (every pass); 0,1 <- Uq diagonal, 4,5 <- E diagonal (when the factors are built)
+      GLANES_BEGIN(NT)
+        FOR_MY_STAGES(i) if (i < NS) {
+          const double iT = IT[i];
+          const double u0 = U[i], u1 = U[d + i];
+          const double dc0 = (u0 - (i ? U[i - 1] : uic[0])) * iT, dc1 = (u1 - (i ? U[d + i - 1] : uic[1])) * iT;
+          const double ev0 = (2.0 * (P.Rd[0] * dc0 + P.Rd[1] * dc1) + GUD[6 * d + i]) * iT;
+          const double ev1 = (2.0 * (P.Rd[1] * dc0 + P.Rd[2] * dc1) + GUD[7 * d + i]) * iT;
+          const double cwc0 = 2.0 * (P.Rm[0] * u0 + P.Rm[1] * u1) + GUD[2 * d + i] + ev0;
+          const double cwc1 = 2.0 * (P.Rm[1] * u0 + P.Rm[2] * u1) + GUD[3 * d + i] + ev1;
+          GUD[6 * d + i] = ev0; GUD[7 * d + i] = ev1; GUD[2 * d + i] = cwc0; GUD[3 * d + i] = cwc1;
+          if (pass == 0) {
+            GUD[4 * d + i] = (2.0 * P.Rd[0] + GUD[4 * d + i]) * iT * iT; GUD[5 * d + i] = (2.0 * P.Rd[2] + GUD[5 * d + i]) * iT * iT;
+            GUD[i] = 2.0 * P.Rm[0] + GUD[i]; GUD[d + i] = 2.0 * P.Rm[2] + GUD[d + i];
+          }
+        }
+      GLANES_END(NW)
       // ---------- backward Riccati sweep
       double Pi1th = cth, Pithth = Dthth;
       for (int i = NS - 1; i >= 0; i--) {
         const double* A = ABG + 54 * i; const double* B = A + 36;
         double* fac = FAC + 20 * i; double* kf = KFF + 6 * i;
-        // stage control pieces from the row groups: E (rate Hessian), Uq, cw, czu   (uniform)
-        const double iT = IT[i];
-        const double u0 = U[i], u1 = U[d + i];
-        const double dc0 = (u0 - (i ? U[i - 1] : uic[0])) * iT, dc1 = (u1 - (i ? U[d + i - 1] : uic[1])) * iT;
-        const double ev0 = (2.0 * (P.Rd[0] * dc0 + P.Rd[1] * dc1) + GUD[6 * d + i]) * iT;
-        const double ev1 = (2.0 * (P.Rd[1] * dc0 + P.Rd[2] * dc1) + GUD[7 * d + i]) * iT;
-        const double cwc0 = 2.0 * (P.Rm[0] * u0 + P.Rm[1] * u1) + GUD[2 * d + i] + ev0;
-        const double cwc1 = 2.0 * (P.Rm[1] * u0 + P.Rm[2] * u1) + GUD[3 * d + i] + ev1;
+        // stage control pieces (prepared per stage before the sweep): E (rate Hessian), Uq, cw, czu
+        const double ev0 = GUD[6 * d + i], ev1 = GUD[7 * d + i], cwc0 = GUD[2 * d + i], cwc1 = GUD[3 * d + i];
         if (pass == 0) {
-          const double e0 = (2.0 * P.Rd[0] + GUD[4 * d + i]) * iT * iT, e1 = 2.0 * P.Rd[1] * iT * iT, e2 = (2.0 * P.Rd[2] + GUD[5 * d + i]) * iT * iT;
-          const double uq0 = 2.0 * P.Rm[0] + GUD[i], uq1 = 2.0 * P.Rm[1], uq2 = 2.0 * P.Rm[2] + GUD[d + i];
-          // phase a: [M_xx A | M_xx B + M_xu] (6x8) and A' l_x, B' l_x + l_u for both rhs columns
+          const double iT = IT[i];
+          const double e0 = GUD[4 * d + i], e1 = 2.0 * P.Rd[1] * iT * iT, e2 = GUD[5 * d + i];
+          const double uq0 = GUD[i], uq1 = 2.0 * P.Rm[1], uq2 = GUD[d + i];
+          // phases a-c produce 8x8 blocks: output (r, c) with c = lane & 7 and r = (lane >> 3) + (NT / 8) * round.
+          // The rounds are unrolled with r's range visible to the compiler, so the row tests of the first round fold.
+          // phase a: [M_xx A | M_xx B + M_xu] (rows 0..5) and, in rows 6,7, A' l_x | B' l_x + l_u for the two rhs columns
           GLANES_BEGIN(NT)
-            for (int o = lane; o < 64; o += NT) {
-              if (o < 48) {
-                const int r = o >> 3, c = o & 7;
+#pragma unroll
+            for (int rd = 0; rd < LMPC_R8; rd++) {
+              const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
+              if (NT > 64 && lane >= 64) break;
+              const double* col = A + 6 * c;   // [A | B] is contiguous: column c of B follows A's six columns
+              if (r < 6) {
                 double a = (c < 6) ? 0.0 : PM[8 * r + c];
-                const double* col = A + 6 * c;   // [A | B] is contiguous: column c of B follows A's six columns
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += PM[8 * r + k] * col[k];
-                MAB[o] = a;
+                MAB[8 * r + c] = a;
               } else {
-                const int q = o - 48, e = q & 7; const double* l = (q < 8) ? L1 : LTH;
-                double a = (e < 6) ? 0.0 : l[e];
-                const double* col = A + 6 * e;
+                const double* l = (r == 6) ? L1 : LTH;
+                double a = (c < 6) ? 0.0 : l[c];
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += col[k] * l[k];
-                AXBW[q] = a;
+                AXBW[8 * (r - 6) + c] = a;
               }
             }
           GLANES_END(NW)
           // phase b: Yxx = A' MA, Yxu = A' MB, Yuu = B' MB + M_ux B + M_uu
           GLANES_BEGIN(NT)
-            for (int o = lane; o < 64; o += NT) {
-              const int r = o >> 3, c = o & 7;
+#pragma unroll
+            for (int rd = 0; rd < LMPC_R8; rd++) {
+              const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
+              if (NT > 64 && lane >= 64) break;
               if (r < 6) {
                 double a = 0.0;
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += A[k + 6 * r] * MAB[8 * k + c];
-                YY[o] = a;
+                YY[8 * r + c] = a;
               } else if (c >= 6) {
                 double a = PM[8 * r + c];
 #pragma unroll
                 for (int k = 0; k < 6; k++) a += B[k + 6 * (r - 6)] * MAB[8 * k + c] + PM[8 * k + r] * B[k + 6 * (c - 6)];
-                YY[o] = a;
+                YY[8 * r + c] = a;
               } else if (c < 2) {
                 // rows 6,7 of Qzw = -E, parked in the unused (r >= 6, c < 2) slots so that phase c reads
                 // Qzw[r][j] = QZ(r, j) without selecting between Yxu and -E
-                YY[o] = (r == 6) ? (c == 0 ? -e0 : -e1) : (c == 0 ? -e1 : -e2);
+                YY[8 * r + c] = (r == 6) ? (c == 0 ? -e0 : -e1) : (c == 0 ? -e1 : -e2);
               }
             }
           GLANES_END(NW)
@@ -779,40 +800,44 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const double kt_0 = i0 * cwt_0 + i1 * cwt_1, kt_1 = i1 * cwt_0 + i2_ * cwt_1;
           Pithth -= cwt_0 * kt_0 + cwt_1 * kt_1;
           Pi1th -= cwt_0 * k1_0 + cwt_1 * k1_1;
+          // P_uu = Q Sinv E  (product form, no cancellation), symmetrised
+          const double se00 = i0 * e0 + i1 * e1, se01 = i0 * e1 + i1 * e2, se10 = i1 * e0 + i2_ * e1, se11 = i1 * e1 + i2_ * e2;
+          const double p00 = q0_ * se00 + q1_ * se10, p01 = q0_ * se01 + q1_ * se11;
+          const double p10 = q1_ * se00 + q2_ * se10, p11 = q1_ * se01 + q2_ * se11;
+          const double p01s = 0.5 * (p01 + p10);
           GLANES_BEGIN(NT)
-            // outputs 0..63: P;  64..79: Kz;  80..95: l1 / lth;  96: scalars
-            for (int o = lane; o < 97; o += NT) {
-              if (o < 64) {
-                const int r = o >> 3, c = o & 7;
-                double pv;
-                if (r >= 6 && c >= 6) {
-                  // P_uu = Q Sinv E  (product form, no cancellation), symmetrised
-                  const double se00 = i0 * e0 + i1 * e1, se01 = i0 * e1 + i1 * e2, se10 = i1 * e0 + i2_ * e1, se11 = i1 * e1 + i2_ * e2;
-                  const double p00 = q0_ * se00 + q1_ * se10, p01 = q0_ * se01 + q1_ * se11;
-                  const double p10 = q1_ * se00 + q2_ * se10, p11 = q1_ * se01 + q2_ * se11;
-                  pv = (r == 6 && c == 6) ? p00 : ((r == 7 && c == 7) ? p11 : 0.5 * (p01 + p10));
-                } else {
-                  const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1], qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
-                  double qzz = 0.0;
-                  if (r < 6 && c < 6) qzz = YY[8 * r + c] + (r == c ? HX[r * d + i] : 0.0);
-                  pv = qzz - (qr0 * (i0 * qc0 + i1 * qc1) + qr1 * (i1 * qc0 + i2_ * qc1));
-                }
-                PM[o] = pv;
-              } else if (o < 80) {   // Kz (2x8): Kz[j][c] = Sinv[j][:] . Qzw[c][:]
-                const int q = o - 64, j = q >> 3, c = q & 7;
-                const double qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
-                fac[q] = (j == 0) ? (i0 * qc0 + i1 * qc1) : (i1 * qc0 + i2_ * qc1);
-              } else if (o < 96) {   // l1 and lth:  l = Cz' - Qzw kff
-                const int q = o - 80, r = q & 7; const bool isth = q >= 8;
-                const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1];
+            // P (8x8), then one more 4x8 block: rows 0,1 Kz, row 2 l1, row 3 lth; lane 0 stores the stage scalars
+#pragma unroll
+            for (int rd = 0; rd < LMPC_R8; rd++) {
+              const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
+              if (NT > 64 && lane >= 64) break;
+              double pv;
+              if (r >= 6 && c >= 6) {
+                pv = (r == 6 && c == 6) ? p00 : ((r == 7 && c == 7) ? p11 : p01s);
+              } else {
+                const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1], qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
+                double qzz = 0.0;
+                if (r < 6 && c < 6) qzz = YY[8 * r + c] + (r == c ? HX[r * d + i] : 0.0);
+                pv = qzz - (qr0 * (i0 * qc0 + i1 * qc1) + qr1 * (i1 * qc0 + i2_ * qc1));
+              }
+              PM[8 * r + c] = pv;
+            }
+            if (lane < 32) {
+              const int c = lane & 7, j = (lane >> 3) & 3;
+              const double qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
+              if (j < 2) {            // Kz (2x8): Kz[j][c] = Sinv[j][:] . Qzw[c][:]
+                fac[8 * j + c] = (j == 0) ? (i0 * qc0 + i1 * qc1) : (i1 * qc0 + i2_ * qc1);
+              } else {                // l1 and lth:  l = Cz' - Qzw kff
+                const bool isth = (j == 3);
                 const double kk0 = isth ? kt_0 : k1_0, kk1 = isth ? kt_1 : k1_1;
                 double cz;
-                if (isth) cz = (r == 1) ? CZTH[i] : 0.0;
-                else cz = (r < 6) ? CZX[r * d + i] : ((r == 6) ? -ev0 : -ev1);
-                const double ax = (r < 6) ? AXBW[(isth ? 8 : 0) + r] : 0.0;
-                (isth ? LTH : L1)[r] = cz + ax - (qr0 * kk0 + qr1 * kk1);
-              } else { fac[16] = i0; fac[17] = i1; fac[18] = i2_; kf[0] = k1_0; kf[1] = k1_1; kf[2] = kt_0; kf[3] = kt_1; kf[4] = cwt_0; kf[5] = cwt_1; }
+                if (isth) cz = (c == 1) ? CZTH[i] : 0.0;
+                else cz = (c < 6) ? CZX[c * d + i] : ((c == 6) ? -ev0 : -ev1);
+                const double ax = (c < 6) ? AXBW[(isth ? 8 : 0) + c] : 0.0;
+                (isth ? LTH : L1)[c] = cz + ax - (qc0 * kk0 + qc1 * kk1);
+              }
             }
+            if (lane == 0) { fac[16] = i0; fac[17] = i1; fac[18] = i2_; kf[0] = k1_0; kf[1] = k1_1; kf[2] = kt_0; kf[3] = kt_1; kf[4] = cwt_0; kf[5] = cwt_1; }
           GLANES_END(NW)
         } else {
           // pass 1: right-hand side "1" column only (factors unchanged)
