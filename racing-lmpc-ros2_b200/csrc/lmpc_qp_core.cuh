@@ -43,8 +43,10 @@
 // constexpr so that the kernels instantiated for the named horizons fold every address into an immediate.
 struct LmpcLayout {
   int oABG, oS, oY, oISY, oX, oU, oDXA, oDUA, oDXF, oDUF, oCZX, oCZTH, oGUD, oFAC, oKFF, oBL, oBR, oVREF, oIT,
-      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, total;
+      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, total;
 };
+#define LMPC_MAX_ROWS 22   // 6 x 2 state boxes + 2 boundary + 4 control boxes + 4 rate boxes
+#define LMPC_ROWS_DOUBLES (5 * LMPC_MAX_ROWS + 6)   // RowDesc[LMPC_MAX_ROWS] (40 B each) + row_begin[11] (+ pad)
 #define LMPC_TB_SIZE_ (36 + 6 * LMPC_NQ + LMPC_NQ * LMPC_NQ + 6 * LMPC_NQ + LMPC_NQ + 36 + 6 + 6 * LMPC_MB + LMPC_MB + LMPC_MB + LMPC_NQ + 1)
 LMPC_HD constexpr int lmpc_even(int n) { return (n + 1) & ~1; }   // keep 16-byte alignment
 LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
@@ -62,9 +64,16 @@ LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
   L.oPM = o; o += 64; L.oL1 = o; o += 8; L.oLTH = o; o += 8; L.oMAB = o; o += 48; L.oAXBW = o; o += 16; L.oYY = o; o += 64;
   L.oRED = o; o += lmpc_even(NW > 1 ? NW * LMPC_NRED : 0);
   L.oTERM = o; o += lmpc_even(LMPC_TB_SIZE_);
+  L.oROWS = o; o += lmpc_even(LMPC_ROWS_DOUBLES);   // row table (copied from the parameters: constant-bank indexing is slow)
   L.total = o;
   return L;
 }
+
+// A row of group g (uniform across the lanes: every lane works on the same group, its own stage i):
+// type, slot, component, sign, constant bound (types 0, 2, 3) and the stage range [i0, i1] on which the row exists.
+// The table is built once on the host (lmpc_host_params.h) -- it depends on the configuration only.
+struct RowDesc { int rtype, slot, c, i0, i1; double sg, bnd; };
+static_assert(sizeof(RowDesc) == 40, "row table layout");
 
 struct LmpcQpParams {
   int N, NS, K, learning, soft, hull_slack;
@@ -83,6 +92,8 @@ struct LmpcQpParams {
   double tol;
   int NSd;                       // odd stage stride of the [.][stage] arrays
   int NW;                        // warps per instance the layout was sized for
+  int row_begin[11];             // rows of group g are rows[row_begin[g] .. row_begin[g+1])
+  RowDesc rows[LMPC_MAX_ROWS];   // existing rows only, group-major: 0..5 GX(c), 6..7 GU(c), 8..9 GD(c)
   LmpcLayout lay;                // shared-memory offsets (doubles)
 };
 
@@ -131,33 +142,12 @@ struct ArrKx6 { double a[LMPC_KPL_MAX][6]; };
 struct ArrKi { int a[LMPC_KPL_MAX]; };
 
 // ---------------------------------------------------------------------------------------- rows
-// A row of group g (uniform across the lanes: every lane works on the same group, its own stage i):
-// type, slot, component, sign and the stage range [i0, i1] on which the row exists.
-struct RowDesc { int rtype, slot, c, i0, i1; double sg; };
-// group g in [0,10): 0..5 GX(c), 6..7 GU(c), 8..9 GD(c); r in [0, rows_of(g))
-LMPC_DEV int group_rows(int g) { return g == 1 ? 4 : 2; }
-LMPC_DEV RowDesc row_desc(const LmpcQpParams& P, int g, int r) {
-  RowDesc q;
-  q.sg = (r & 1) ? -1.0 : 1.0;
-  q.i0 = 0; q.i1 = -1;   // empty range = row absent
-  if (g < 6) {
-    q.c = g;
-    if (r < 2) { q.rtype = 0; q.slot = P.xslot[g][r]; if (q.slot >= 0) { q.i0 = 1; q.i1 = P.N - 2; } }
-    else { q.rtype = 1; q.slot = P.nxb + 8 + (r - 2); q.i0 = P.soft ? 0 : 1; q.i1 = P.N - 1; }
-  } else if (g < 8) {
-    q.c = g - 6; q.rtype = 2; q.slot = P.nxb + 2 * q.c + r; if (P.ub_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; }
-  } else {
-    q.c = g - 8; q.rtype = 3; q.slot = P.nxb + 4 + 2 * q.c + r; if (P.db_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; }
-  }
-  if (q.slot < 0) q.slot = 0;
-  return q;
-}
 // iterate: for every group g (uniform), every stage i owned by this lane, every existing row q of g
 #define FOR_GROUPS(g) for (int g = 0; g < 10; g++)
 #define FOR_MY_STAGES(i) for (int i = lane; i < N; i += NT)
-#define FOR_ROWS(q, g, i)                                        \
-  for (int rr_ = 0; rr_ < group_rows(g); rr_++)                  \
-    for (RowDesc q = row_desc(P, g, rr_); q.i1 >= q.i0; q.i1 = -2) \
+#define FOR_ROWS(q, g, i)                                                  \
+  for (int rr_ = ROWB[g]; rr_ < ROWB[(g) + 1]; rr_++)                      \
+    for (RowDesc q = ROWS[rr_]; q.i1 >= q.i0; q.i1 = -2)                   \
       if (i >= q.i0 && i <= q.i1)
 // G v of the row for the vectors (xs, us, thv); up0 = u_{-1} component (u_ic for the iterate, 0 for a step)
 LMPC_DEV double row_val(const RowDesc& q, int i, int d, const double* xs, const double* us, const double* IT, double thv, const double* up0) {
@@ -169,12 +159,8 @@ LMPC_DEV double row_val(const RowDesc& q, int i, int d, const double* xs, const 
   }
 }
 LMPC_DEV double row_bound(const LmpcQpParams& P, const RowDesc& q, int i, const double* BL, const double* BR) {
-  switch (q.rtype) {
-    case 0: return P.xb_h[q.slot];
-    case 1: return q.sg > 0.0 ? (BL[i] - P.margin) : -(BR[i] + P.margin);
-    case 2: return q.sg > 0.0 ? P.uhi[q.c] : -P.ulo[q.c];
-    default: return q.sg > 0.0 ? P.dhi[q.c] : -P.dlo[q.c];
-  }
+  if (q.rtype == 1) return q.sg > 0.0 ? (BL[i] - P.margin) : -(BR[i] + P.margin);
+  return q.bnd;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,6 +185,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   double* DXA = sm + LO(oDXA); double* DUA = sm + LO(oDUA); double* DXF = sm + LO(oDXF); double* DUF = sm + LO(oDUF);
   double* HX = DXF;   // alias: the Hessian diagonal is dead once the pass-0 factorisation is done
   double* CZX = sm + LO(oCZX); double* CZTH = sm + LO(oCZTH); double* GUD = sm + LO(oGUD);
+  const RowDesc* ROWS = reinterpret_cast<const RowDesc*>(sm + LO(oROWS));
+  const int* ROWB = reinterpret_cast<const int*>(sm + LO(oROWS) + 5 * LMPC_MAX_ROWS);
   double* FAC = sm + LO(oFAC);   // per stage: Kz[16] (2x8 row-major), Sinv[3], pad
   double* KFF = sm + LO(oKFF);   // per stage: kff1[2], kffth[2], Cwth[2]
   double* BL = sm + LO(oBL); double* BR = sm + LO(oBR); double* VREF = sm + LO(oVREF); double* IT = sm + LO(oIT);
@@ -211,6 +199,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // ---------------------------------------------------------------- load
   GLANES_BEGIN(NT)
     for (int idx = lane; idx < 54 * NS; idx += NT) ABG[idx] = in.ABg[idx];
+    for (int idx = lane; idx < 5 * LMPC_MAX_ROWS; idx += NT) (sm + LO(oROWS))[idx] = reinterpret_cast<const double*>(P.rows)[idx];
+    for (int idx = lane; idx < 11; idx += NT) reinterpret_cast<int*>(sm + LO(oROWS) + 5 * LMPC_MAX_ROWS)[idx] = P.row_begin[idx];
     for (int i = lane; i < N; i += NT) {
       BL[i] = in.bl[i]; BR[i] = in.br[i]; VREF[i] = in.vref[i];
       if (i < NS) {
