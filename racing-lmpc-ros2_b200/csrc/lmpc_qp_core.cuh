@@ -155,7 +155,7 @@ LMPC_DEV double row_val(const RowDesc& q, int i, int d, const double* xs, const 
     case 0: return q.sg * xs[q.c * d + i];
     case 1: return q.sg * xs[d + i] - thv;
     case 2: return q.sg * us[q.c * d + i];
-    default: return q.sg * (us[q.c * d + i] - (i ? us[q.c * d + i - 1] : up0[q.c])) * IT[i];
+    default: return q.sg * (us[q.c * d + i] - (i ? us[q.c * d + i - 1] : (q.c ? up0[1] : up0[0]))) * IT[i];   // select, not an indexed load: up0 stays in registers
   }
 }
 LMPC_DEV double row_bound(const LmpcQpParams& P, const RowDesc& q, int i, const double* BL, const double* BR) {
