@@ -59,3 +59,23 @@ def src(ln):
     return ""
 for ln, (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{100*n/tot[0]:5.2f}% inst {100*s/max(tot[1],1):5.2f}% samples  {ln}  {src(ln)}")
+
+# ---- section totals (line ranges of lmpc_qp_core.cuh; everything from other files = collectives / intrinsics)
+SECTIONS = [("load + initial point", 199, 305), ("iteration control / classify", 306, 333), ("row assembly (Hessian/gradient)", 334, 415),
+            ("terminal block (safe-set simplex)", 416, 696), ("stage control pieces", 697, 714), ("backward sweep, factor pass", 715, 831),
+            ("backward sweep, rhs-only pass", 832, 862), ("forward sweep", 863, 888), ("lambda directions", 889, 927),
+            ("row directions / step length", 928, 986), ("polish update", 987, 1070), ("iterate update", 1071, 1123), ("outputs", 1124, 1180)]
+sec = collections.OrderedDict((name, [0, 0]) for name, _, _ in SECTIONS)
+sec["row helpers (row_val/row_bound/FOR_ROWS)"] = [0, 0]
+sec["collectives / shuffles (other files)"] = [0, 0]
+for ln, (n, s) in agg.items():
+    key = "collectives / shuffles (other files)"
+    if ln is not None and ln[0] == "lmpc_qp_core.cuh":
+        if ln[1] < 199: key = "row helpers (row_val/row_bound/FOR_ROWS)"
+        else:
+            for name, a, b in SECTIONS:
+                if a <= ln[1] <= b: key = name; break
+    sec[key][0] += n; sec[key][1] += s
+print("\nsections (share of executed warp instructions / of stall samples):")
+for name, (n, s) in sec.items():
+    print(f"{100*n/tot[0]:6.2f}% inst {100*s/max(tot[1],1):6.2f}% samples  {name}")
