@@ -9,6 +9,9 @@
  *                                       vehicle_model_factory.cpp:31-50 ("single_track_planar_model")
  *   lmpc_solve_batch                    RacingMPC::solve(in, out, stats)   racing_mpc.hpp:52,
  *                                       racing_mpc.cpp:209-372  (B independent ticks per call)
+ *   lmpc_solve_sqp_batch                RacingMPC(config, model, full_dynamics=true)::solve -- the one-off IPOPT
+ *                                       solve of the nonlinear-dynamics problem, racing_mpc.cpp:67-84,162-166,
+ *                                       racing_mpc_node.cpp:299-314
  *   lmpc_linearise_batch                BaseVehicleModel::discrete_dynamics_jacobian() {x,u,k,dt}->{A,B,g}
  *                                       single_track_planar_model.cpp:377-387
  *   lmpc_discrete_dynamics_batch        BaseVehicleModel::discrete_dynamics() {x,u,k,dt}->{xip1}
@@ -166,6 +169,17 @@ int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, const double* u
 /* ---- the hot path: B independent MPC ticks ---- */
 int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out,
                      int memspace);
+/* Full-dynamics variant (RacingMPC(..., full_dynamics = true), racing_mpc.cpp:67-84,162-166): the same cost and rows
+ * with the NONLINEAR discrete dynamics x_{i+1} = f_d(x_i, u_i, curvatures_i, T_i) as equality constraints, which the
+ * reference hands to IPOPT once per run (racing_mpc_node.cpp:299-314).  Here: sequential quadratic programming on the
+ * tick's own kernels -- linearise at the current trajectory, solve the QP, take the full step, repeat until the step
+ * max |new - old| / max(1, |new|) over X and U is below sqp_tol (or max_sqp_iter passes).  A fixed point of this
+ * iteration satisfies the KKT conditions of the nonlinear problem.  The safe-set columns are queried once, at the
+ * caller's X_ref[:, N-1] (racing_mpc.cpp:249-255), exactly as the reference's solve() does before calling IPOPT.
+ * sqp_iters [B] (optional): QP solves spent per instance.  defect [B] (optional): max |x_{i+1} - f_d(x_i, u_i)| of the
+ * returned trajectory (the nonlinear constraint violation).  out->status is the status of the last QP of the instance. */
+int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int max_sqp_iter,
+                         double sqp_tol, int32_t* sqp_iters, double* defect, int memspace);
 /* Per-kernel device timing (measurement aid): when enabled, CUDA events are recorded on the handle's
  * stream around the three kernels of every lmpc_solve_batch; lmpc_get_kernel_ms synchronises and
  * returns the summed milliseconds {linearise, safe-set query, QP} over the recorded solves. */

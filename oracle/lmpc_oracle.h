@@ -110,6 +110,7 @@ typedef struct orc_step_in {
   const double* curvatures;  /* N */
   const double* vel_ref;     /* N */
   double total_length;
+  const double* ss_query_point; /* optional (s, e_y): safe-set query point; NULL => aligned X_ref(:, N-1) (racing_mpc.cpp:249-255) */
 } orc_step_in;
 
 typedef struct orc_step_out {
@@ -144,6 +145,13 @@ int orc_step_batch(const orc_vehicle* v, const orc_config* c, const orc_safe_set
                    const double* kap, const double* vref, const double* total_length,
                    double* X, double* U, double* dU, double* lambda, double* cost, int* status,
                    int* iters, double* kkt, int impl, int nthreads);
+/* Full-dynamics variant (RacingMPC(..., full_dynamics=true), racing_mpc.cpp:67-84,162-166): the reference gives the
+ * problem with the nonlinear dynamics constraint to IPOPT once per run (racing_mpc_node.cpp:299-314).  Restated here as
+ * full-step SQP: solve the tick's QP (impl 0 = port, 1 = dense), re-linearise at its solution, repeat until
+ * max |new - old| / max(1, |new|) over X and U < tol.  The safe set is queried once at the caller's X_ref(:, N-1).
+ * Returns the status of the last QP; *sqp_iters = QP solves, *defect = max |x_{i+1} - f_d(x_i, u_i, k_i, T_i)|. */
+int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss, const orc_step_in* in,
+                 orc_step_out* out, int max_sqp_iter, double tol, int impl, int* sqp_iters, double* defect);
 /* KKT certificate of an arbitrary candidate (X,U,dU[,lambda]) against the dense QP:
  * returns max(primal infeasibility, projected-gradient optimality gap) -- see .c */
 double orc_check_candidate(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss,

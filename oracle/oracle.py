@@ -52,7 +52,7 @@ class Config(C.Structure):
 class StepIn(C.Structure):
     _fields_ = [(n, C.POINTER(C.c_double)) for n in (
         "x_ic", "u_ic", "X_ref", "U_ref", "T_ref", "bound_left", "bound_right", "curvatures",
-        "vel_ref")] + [("total_length", C.c_double)]
+        "vel_ref")] + [("total_length", C.c_double), ("ss_query_point", C.POINTER(C.c_double))]
 
 
 class StepOut(C.Structure):
@@ -104,6 +104,8 @@ def lib():
                            C.POINTER(StepOut)]
         L.orc_step_batch.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p, C.c_int] + \
             [dp] * 10 + [dp] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), dp, C.c_int, C.c_int]
+        L.orc_step_sqp.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p, C.POINTER(StepIn),
+                                   C.POINTER(StepOut), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp]
         L.orc_check_candidate.restype = C.c_double
         L.orc_check_candidate.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p,
                                           C.POINTER(StepIn), dp, dp, dp, dp, dp, dp]
@@ -194,6 +196,9 @@ class Oracle:
             keep[key] = _f64(inp[key]).ravel()
             setattr(si, key, _p(keep[key]))
         si.total_length = float(inp["total_length"])
+        if inp.get("ss_query_point") is not None:
+            keep["ss_query_point"] = _f64(inp["ss_query_point"]).ravel()
+            si.ss_query_point = _p(keep["ss_query_point"])
         return si, keep
 
     def step(self, inp, impl="dense"):
@@ -210,6 +215,22 @@ class Oracle:
         return dict(X=X, U=U, dU=dU, lam=lam, ss_x=ssx, ss_cost=ssc, cost=so.cost, sigma_b=so.sigma_b,
                     sigma_h=np.array(list(so.sigma_h)), kkt=so.kkt, status=st, iters=so.iters,
                     polished=so.polished)
+
+    def step_sqp(self, inp, max_sqp_iter=20, tol=1e-9, impl="port"):
+        """Full-dynamics variant (racing_mpc.cpp:67-84): SQP to convergence.  Returns the step() dict plus
+        sqp_iters and defect (max nonlinear-dynamics violation of the returned trajectory)."""
+        N, K = self.N, self.K
+        si, keep = self._mk_in(inp)
+        X = np.zeros((N, 6)); U = np.zeros((N - 1, 2)); dU = np.zeros((N - 1, 2))
+        lam = np.zeros(max(K, 1)); ssx = np.zeros((max(K, 1), 6)); ssc = np.zeros(max(K, 1))
+        so = StepOut()
+        so.X, so.U, so.dU, so.lambda_, so.ss_x, so.ss_cost = _p(X), _p(U), _p(dU), _p(lam), _p(ssx), _p(ssc)
+        its = C.c_int(0); dfc = C.c_double(0.0)
+        st = self.L.orc_step_sqp(C.byref(self.veh), C.byref(self.cfg), self.ss, C.byref(si), C.byref(so),
+                                 int(max_sqp_iter), float(tol), 0 if impl == "port" else 1, C.byref(its),
+                                 C.cast(C.byref(dfc), C.POINTER(C.c_double)))
+        return dict(X=X, U=U, dU=dU, lam=lam, cost=so.cost, status=st, iters=so.iters, sqp_iters=its.value,
+                    defect=dfc.value, kkt=so.kkt)
 
     def check_candidate(self, inp, X, U, dU, lam=None):
         si, keep = self._mk_in(inp)

@@ -703,7 +703,7 @@ static void* batch_worker(void* arg) {
   for (int b = j->tid; b < j->B; b += j->nth) {
     orc_step_in in = {j->x_ic + 6 * (size_t)b, j->u_ic + 2 * (size_t)b, j->X_ref + 6 * (size_t)N * b,
                       j->U_ref + 2 * (size_t)(N - 1) * b, j->T_ref + (size_t)(N - 1) * b, j->bl + (size_t)N * b,
-                      j->br + (size_t)N * b, j->kap + (size_t)N * b, j->vref + (size_t)N * b, j->L[b]};
+                      j->br + (size_t)N * b, j->kap + (size_t)N * b, j->vref + (size_t)N * b, j->L[b], NULL};
     orc_step_out out; memset(&out, 0, sizeof out);
     out.X = j->X + 6 * (size_t)N * b; out.U = j->U + 2 * (size_t)(N - 1) * b; out.dU = j->dU + 2 * (size_t)(N - 1) * b;
     out.lambda = j->lambda ? j->lambda + (size_t)K * b : NULL;
@@ -735,4 +735,59 @@ int orc_step_batch(const orc_vehicle* v, const orc_config* c, const orc_safe_set
   int nfail = jobs[0].nfail;
   for (int t = 1; t < nthreads; t++) { pthread_join(th[t], NULL); nfail += jobs[t].nfail; }
   return nfail;
+}
+
+/* ---------------------------------------------------------------------------------- SQP to convergence */
+/* Damped fixed-point iteration on "linearise at (Xk, Uk) -> solve the QP".  The relaxation factor alpha follows the
+ * angle between successive QP displacements d_k = QP(Xk, Uk) - (Xk, Uk): cos < -0.25 (oscillating: the Gauss-Newton
+ * model has no constraint curvature and the LMPC terminal cost is linear) halves alpha (>= 1/8), cos > 0.25 doubles it
+ * (<= 1).  Converged when the undamped displacement max |d| / max(1, |QP|) < tol; the QP solution is returned. */
+int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss, const orc_step_in* in,
+                 orc_step_out* out, int max_sqp_iter, double tol, int impl, int* sqp_iters, double* defect) {
+  const int N = c->N, nst = N - 1, nd = 6 * N + 2 * nst;
+  double* Xk = (double*)malloc(sizeof(double) * 6 * (size_t)N);
+  double* Uk = (double*)malloc(sizeof(double) * 2 * (size_t)nst);
+  double* dprev = (double*)calloc((size_t)nd, sizeof(double));
+  for (int i = 0; i < N; i++) {
+    Xk[6 * i] = orc_align_abscissa(in->X_ref[6 * i], in->x_ic[0], in->total_length);
+    for (int k = 1; k < 6; k++) Xk[6 * i + k] = in->X_ref[6 * i + k];
+  }
+  memcpy(Uk, in->U_ref, sizeof(double) * 2 * (size_t)nst);
+  const double qp[2] = {Xk[6 * (N - 1)], Xk[6 * (N - 1) + 1]};
+  int st = ORC_MAX_ITER, its = 0;
+  double alpha = 1.0;
+  for (int k = 0; k < max_sqp_iter; k++) {
+    orc_step_in ik = *in;
+    ik.X_ref = Xk; ik.U_ref = Uk; ik.ss_query_point = in->ss_query_point ? in->ss_query_point : qp;
+    st = impl ? orc_step_dense(v, c, ss, &ik, out) : orc_step_port(v, c, ss, &ik, out);
+    its++;
+    if (st != ORC_OK) break;
+    double step = 0.0, dd = 0.0, dp = 0.0, pp = 0.0;
+    for (int q = 0; q < nd; q++) {
+      const double nv = q < 6 * N ? out->X[q] : out->U[q - 6 * N], ov = q < 6 * N ? Xk[q] : Uk[q - 6 * N];
+      const double d = nv - ov;
+      step = fmax(step, fabs(d) / fmax(1.0, fabs(nv)));
+      dd += d * d; dp += d * dprev[q]; pp += dprev[q] * dprev[q];
+      dprev[q] = d;
+    }
+    if (step < tol) break;
+    if (k > 0) {
+      const double cs = dp / sqrt(dd * pp + 1e-300);
+      if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125); else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
+    }
+    for (int q = 0; q < 6 * N; q++) Xk[q] += alpha * dprev[q];
+    for (int q = 0; q < 2 * nst; q++) Uk[q] += alpha * dprev[6 * N + q];
+  }
+  if (sqp_iters) *sqp_iters = its;
+  if (defect) {
+    double dmax = 0.0;
+    for (int i = 0; i < nst; i++) {
+      double xn[6];
+      orc_discrete_dynamics(v, out->X + 6 * i, out->U + 2 * i, in->curvatures[i], in->T_ref[i], xn);
+      for (int k = 0; k < 6; k++) dmax = fmax(dmax, fabs(xn[k] - out->X[6 * (i + 1) + k]));
+    }
+    *defect = dmax;
+  }
+  free(Xk); free(Uk); free(dprev);
+  return st;
 }

@@ -62,7 +62,9 @@ int orc_build_prob(const orc_vehicle* v, const orc_config* c, const orc_safe_set
   if (c->learning) {
     if (p->K > ORC_KMAX) return ORC_NUMERIC;
     /* query at X_ref(:, -1) after alignment (racing_mpc.cpp:249-255), pad/truncate, J - J0 */
-    p->ss_count = ss ? orc_ss_query_padded(ss, p->Xref[6 * (N - 1)], p->Xref[6 * (N - 1) + 1], p->K,
+    const double qs = in->ss_query_point ? in->ss_query_point[0] : p->Xref[6 * (N - 1)];
+    const double qe = in->ss_query_point ? in->ss_query_point[1] : p->Xref[6 * (N - 1) + 1];
+    p->ss_count = ss ? orc_ss_query_padded(ss, qs, qe, p->K,
                                            c->num_ss_pts_per_lap, p->ssx, p->ssc) : 0;
     if (p->ss_count == 0) return ORC_NO_SAFE_SET;
   }

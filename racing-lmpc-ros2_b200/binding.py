@@ -68,7 +68,7 @@ EXPORTS = [
     "lmpc_version", "lmpc_status_string", "lmpc_create", "lmpc_destroy", "lmpc_set_stream",
     "lmpc_last_error", "lmpc_launch_count", "lmpc_safe_set_add_lap", "lmpc_safe_set_load",
     "lmpc_safe_set_clear", "lmpc_safe_set_num_laps", "lmpc_safe_set_query_batch",
-    "lmpc_discrete_dynamics_batch", "lmpc_linearise_batch", "lmpc_solve_batch", "lmpc_synchronize",
+    "lmpc_discrete_dynamics_batch", "lmpc_linearise_batch", "lmpc_solve_batch", "lmpc_solve_sqp_batch", "lmpc_synchronize",
     "lmpc_set_timing", "lmpc_get_kernel_ms", "lmpc_measure_fp64_peak",
 ]
 
@@ -105,6 +105,7 @@ def load_library(path=None):
     L.lmpc_discrete_dynamics_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int]
     L.lmpc_linearise_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
     L.lmpc_solve_batch.argtypes = [vp, C.c_int, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_int]
+    L.lmpc_solve_sqp_batch.argtypes = [vp, C.c_int, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_int, C.c_double, vp, vp, C.c_int]
     L.lmpc_synchronize.argtypes = [vp]
     L.lmpc_set_timing.argtypes = [vp, C.c_int]
     L.lmpc_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]

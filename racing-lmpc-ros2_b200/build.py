@@ -11,9 +11,11 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(CSRC, "liblmpc_b200.so")
-SOURCES = ["lmpc_capi.cu"]
-DEPS = ["lmpc_capi.cu", "lmpc_kernels.cuh", "lmpc_qp_core.cuh", "lmpc_ss_core.cuh", "lmpc_model.cuh",
-        "lmpc_warp.cuh", "lmpc_host_params.h", os.path.join("..", "..", "include", "lmpc_b200.h")]
+SOURCES = ["lmpc_capi.cu", "lmpc_qp_tu0.cu", "lmpc_qp_tu1.cu", "lmpc_qp_tu2.cu", "lmpc_qp_tu3.cu"]
+DEPS = SOURCES + ["lmpc_kernels.cuh", "lmpc_qp_kernel.cuh", "lmpc_qp_launch.h", "lmpc_qp_core.cuh", "lmpc_ss_core.cuh",
+                  "lmpc_model.cuh", "lmpc_track.cuh", "lmpc_loop.cuh", "lmpc_warp.cuh", "lmpc_host_params.h",
+                  os.path.join("..", "..", "include", "lmpc_b200.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def nvcc_path():
@@ -24,17 +26,37 @@ def nvcc_path():
 
 
 def build(force=False, verbose=False):
+    """One nvcc process per translation unit (the QP kernel instantiations are spread over four), run in
+    parallel, then one link step.  Objects live in build_dbg/ at the repo root (git-ignored, not shipped to the GPU box)."""
+    deps = [os.path.join(CSRC, d) for d in DEPS if os.path.exists(os.path.join(CSRC, d))]
     if not force and os.path.exists(OUT):
         t = os.path.getmtime(OUT)
-        if all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPS):
+        if all(os.path.getmtime(d) <= t for d in deps):
             return OUT
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    nvcc = nvcc_path()
+    objdir = os.path.join(_HERE, "..", "build_dbg")   # git- and gpurun-ignored
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in deps if not d.endswith(".cu"))
+    procs, log = [], ""
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(objdir, s[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(src)):
+            continue
+        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c", "-o", obj, src]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        log += " ".join(cmd) + "\n" + out
+        failed |= p.returncode != 0
+    if not failed:
+        cmd = [nvcc, "-shared"] + ARCH + ["-o", OUT] + [os.path.join(objdir, s[:-3] + ".o") for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        failed = res.returncode != 0
     with open(os.path.join(CSRC, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
     if verbose:
@@ -43,4 +65,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True)
+    build(force="--force" in sys.argv, verbose=True)

@@ -14,6 +14,7 @@
 #include "../../include/lmpc_b200.h"
 #include "lmpc_host_params.h"
 #include "lmpc_kernels.cuh"
+#include "lmpc_qp_launch.h"
 
 namespace {
 
@@ -45,7 +46,7 @@ struct lmpc_handle {
   DevBuf slab;
   std::vector<LmpcLapView> dev_laps;   // newest first, device pointers into the slab
   // device workspace
-  DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj;
+  DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp;
   // device staging for host-memory callers
   DevBuf st_in, st_out;
   size_t qp_smem = 0;
@@ -101,24 +102,12 @@ extern "C" const char* lmpc_status_string(int s) {
 extern "C" const char* lmpc_last_error(const lmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" int64_t lmpc_launch_count(const lmpc_handle* h) { return h ? h->launches : 0; }
 
-// dispatch over the instantiated kernels: (warps per instance, columns per lane) and, for the single-warp
-// default, the compile-time layouts of the named horizons (N = 20 / 40 with 16 row slots per stage)
-#define LMPC_QP_DISPATCH(NWv, KPLv, NFv, CALL)                                        \
-  do {                                                                               \
-    if (NWv == 1) {                                                                  \
-      if (NFv == 20) { if (KPLv <= 1) { CALL(1, 1, 20, 16); } else if (KPLv == 2) { CALL(1, 2, 20, 16); } else if (KPLv == 3) { CALL(1, 3, 20, 16); } else { CALL(1, 4, 20, 16); } } \
-      else if (NFv == 40) { if (KPLv <= 1) { CALL(1, 1, 40, 16); } else if (KPLv == 2) { CALL(1, 2, 40, 16); } else if (KPLv == 3) { CALL(1, 3, 40, 16); } else { CALL(1, 4, 40, 16); } } \
-      else { if (KPLv <= 1) { CALL(1, 1, 0, 0); } else if (KPLv == 2) { CALL(1, 2, 0, 0); } else if (KPLv == 3) { CALL(1, 3, 0, 0); } else { CALL(1, 4, 0, 0); } } \
-    } else if (NWv == 2) { if (NFv == 20) { if (KPLv <= 1) { CALL(2, 1, 20, 16); } else { CALL(2, 2, 20, 16); } } \
-                           else if (KPLv <= 1) { CALL(2, 1, 0, 0); } else { CALL(2, 2, 0, 0); } } \
-    else { CALL(4, 1, 0, 0); }                                                       \
-  } while (0)
+static int qp_kpl(const lmpc_handle* h) { return std::max(1, (h->P.K + 32 * h->P.NW - 1) / (32 * h->P.NW)); }
 
 static int set_qp_attr(lmpc_handle* h) {
-  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nf = qp_fixed_n(h);
-#define SETATTR(NW_, KPL_, NF_, RS_) CK(cudaFuncSetAttribute(lmpc_qp_kernel<NW_, KPL_, NF_, RS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qp_smem))
-  LMPC_QP_DISPATCH(nw, kpl, nf, SETATTR);
-#undef SETATTR
+  cudaError_t e = cudaSuccess;
+  if (!lmpc_qp_set_smem(h->P.NW, qp_kpl(h), qp_fixed_n(h), h->qp_smem, &e)) { h->err = "no QP kernel instantiation for this configuration"; return LMPC_ERR_INVALID; }
+  if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return LMPC_ERR_CUDA; }
   return LMPC_OK;
 }
 
@@ -159,7 +148,7 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
   for (auto& e : h->tev) cudaEventDestroy(e);
-  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->st_in, &h->st_out})
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
   return LMPC_OK;
@@ -469,97 +458,187 @@ extern "C" int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, cons
 
 // ------------------------------------------------------------------------------------------ solve
 static void launch_qp(lmpc_handle* h, const LmpcQpBatch& a) {
-  const int nw = h->P.NW, kpl = std::max(1, (h->P.K + 32 * nw - 1) / (32 * nw)), nblocks = a.B, nf = qp_fixed_n(h);
-#define LAUNCH(NW_, KPL_, NF_, RS_) lmpc_qp_kernel<NW_, KPL_, NF_, RS_><<<nblocks, 32 * NW_, h->qp_smem, h->stream>>>(h->P, a)
-  LMPC_QP_DISPATCH(nw, kpl, nf, LAUNCH);
-#undef LAUNCH
+  lmpc_qp_launch(h->P.NW, qp_kpl(h), qp_fixed_n(h), a.B, h->qp_smem, h->stream, h->P, a);
 }
 
-extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int memspace) {
+// Device views of one batch: caller's buffers (LMPC_MEM_DEVICE) or the handle's staging area (LMPC_MEM_HOST).
+struct DevIO {
+  const double* din[11];
+  double* dout[7];
+  int32_t *d_status, *d_iters;
+  double *ssx, *ssj;
+  size_t nin[11], nout[7];
+};
+
+static int check_batch_args(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out) {
   if (!h || !in || !out || B < 1) return LMPC_ERR_INVALID;
   if (B > h->max_batch) return LMPC_ERR_CAPACITY;
   if (!in->x_ic || !in->u_ic || !in->X_ref || !in->U_ref || !in->T_ref || !in->bound_left || !in->bound_right ||
       !in->curvatures || !in->vel_ref || !in->total_length)
     return LMPC_ERR_INVALID;
   if (!out->X_optm || !out->U_optm || !out->dU_optm || !out->status || !out->iters) return LMPC_ERR_INVALID;
-  CK(cudaSetDevice(h->device));
+  return LMPC_OK;
+}
+
+// H2D of the 11 inputs (host callers) / pointer pass-through (device callers)
+static int stage_in(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int memspace, DevIO& io) {
   const size_t Bz = (size_t)B, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)h->P.K;
-  const bool learn = h->P.learning != 0;
-  // element counts of the 11 inputs and 9 outputs, in struct order
+  // element counts of the 11 inputs and 7 double outputs, in struct order
   const size_t nin[11] = {6 * Bz, 2 * Bz, 6 * N * Bz, 2 * NS * Bz, NS * Bz, N * Bz, N * Bz, N * Bz, N * Bz, Bz, 2 * NS * Bz};
+  const size_t nout[7] = {6 * N * Bz, 2 * NS * Bz, 2 * NS * Bz, K * Bz, 6 * K * Bz, K * Bz, Bz};
   const double* hin[11] = {in->x_ic, in->u_ic, in->X_ref, in->U_ref, in->T_ref, in->bound_left, in->bound_right,
                            in->curvatures, in->vel_ref, in->total_length, in->U_warm};
-  const double* din[11];
-  const size_t nout_d[7] = {6 * N * Bz, 2 * NS * Bz, 2 * NS * Bz, K * Bz, 6 * K * Bz, K * Bz, Bz};
-  double* hout_d[7] = {out->X_optm, out->U_optm, out->dU_optm, out->convex_combi_optm, out->ss_x, out->ss_j, out->cost};
-  double* dout_d[7];
-  int32_t *d_status = out->status, *d_iters = out->iters;
+  double* hout[7] = {out->X_optm, out->U_optm, out->dU_optm, out->convex_combi_optm, out->ss_x, out->ss_j, out->cost};
+  for (int k = 0; k < 11; k++) io.nin[k] = nin[k];
+  for (int k = 0; k < 7; k++) io.nout[k] = nout[k];
+  io.d_status = out->status; io.d_iters = out->iters;
   if (memspace == LMPC_MEM_HOST) {
     size_t tin = 0, tout = 0;
     for (int k = 0; k < 11; k++) tin += nin[k];
-    for (int k = 0; k < 7; k++) tout += nout_d[k];
+    for (int k = 0; k < 7; k++) tout += nout[k];
     int rc = dev_reserve(h, h->st_in, sizeof(double) * tin);
     if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * tout + 2 * sizeof(int32_t) * Bz);
     if (rc != LMPC_OK) return rc;
     double* p = (double*)h->st_in.p;
     for (int k = 0; k < 11; k++) {
-      if (hin[k]) { CK(cudaMemcpyAsync(p, hin[k], sizeof(double) * nin[k], cudaMemcpyHostToDevice, h->stream)); din[k] = p; }
-      else din[k] = nullptr;
+      if (hin[k]) { CK(cudaMemcpyAsync(p, hin[k], sizeof(double) * nin[k], cudaMemcpyHostToDevice, h->stream)); io.din[k] = p; }
+      else io.din[k] = nullptr;
       p += nin[k];
     }
     double* q = (double*)h->st_out.p;
-    for (int k = 0; k < 7; k++) { dout_d[k] = q; q += nout_d[k]; }
-    d_status = (int32_t*)q; d_iters = d_status + Bz;
+    for (int k = 0; k < 7; k++) { io.dout[k] = q; q += nout[k]; }
+    io.d_status = (int32_t*)q; io.d_iters = io.d_status + Bz;
+    if (!out->convex_combi_optm) io.dout[3] = nullptr;
+    if (!out->cost) io.dout[6] = nullptr;
+    io.ssx = (double*)h->st_out.p + nout[0] + nout[1] + nout[2] + nout[3]; io.ssj = io.ssx + nout[4];
   } else {
-    for (int k = 0; k < 11; k++) din[k] = hin[k];
-    for (int k = 0; k < 7; k++) dout_d[k] = hout_d[k];
+    for (int k = 0; k < 11; k++) io.din[k] = hin[k];
+    for (int k = 0; k < 7; k++) io.dout[k] = hout[k];
+    // the safe-set columns go straight to the caller's ss_x / ss_j when given, else to the workspace
+    io.ssx = out->ss_x ? out->ss_x : (double*)h->ws_ssx.p;
+    io.ssj = out->ss_j ? out->ss_j : (double*)h->ws_ssj.p;
   }
-  double* abg = (double*)h->ws_abg.p; double* cen = (double*)h->ws_cen.p;
-  // the safe-set columns go straight to the caller's ss_x / ss_j when given (device), else to the workspace
-  double* ssx = (memspace == LMPC_MEM_DEVICE && out->ss_x) ? out->ss_x : (memspace == LMPC_MEM_HOST ? dout_d[4] : (double*)h->ws_ssx.p);
-  double* ssj = (memspace == LMPC_MEM_DEVICE && out->ss_j) ? out->ss_j : (memspace == LMPC_MEM_HOST ? dout_d[5] : (double*)h->ws_ssj.p);
+  return LMPC_OK;
+}
 
+// D2H of the outputs + stream synchronise (host callers only)
+static int stage_out(lmpc_handle* h, int B, const lmpc_batch_out* out, int memspace, const DevIO& io) {
+  if (memspace != LMPC_MEM_HOST) return LMPC_OK;
+  const bool learn = h->P.learning != 0;
+  double* hout[7] = {out->X_optm, out->U_optm, out->dU_optm, out->convex_combi_optm, out->ss_x, out->ss_j, out->cost};
+  const double* dsrc[7] = {io.dout[0], io.dout[1], io.dout[2], io.dout[3], io.ssx, io.ssj, io.dout[6]};
+  for (int k = 0; k < 7; k++) {
+    if (!hout[k] || !dsrc[k]) continue;
+    if ((k == 3 || k == 4 || k == 5) && !learn) continue;
+    CK(cudaMemcpyAsync(hout[k], dsrc[k], sizeof(double) * io.nout[k], cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaMemcpyAsync(out->status, io.d_status, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out->iters, io.d_iters, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return LMPC_OK;
+}
+
+// The three kernels of one tick.  X_lin / U_lin: linearisation point; U0: initial controls of the interior point;
+// first: also write the safe-set query point and run the k-NN (later SQP iterations keep the columns of the first);
+// skip: optional per-instance mask (SQP instances that have converged).
+static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double* X_lin, const double* U_lin, const double* U0,
+                            bool first, const int* skip, int* ss_count_io) {
+  const size_t N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)h->P.K;
+  const bool learn = h->P.learning != 0;
+  double* abg = (double*)h->ws_abg.p; double* cen = (double*)h->ws_cen.p;
   cudaEvent_t* tev = (h->timing && !h->tev.empty()) ? &h->tev[4 * (size_t)(h->tcount % kTimingRing)] : nullptr;
   if (tev) CK(cudaEventRecord(tev[0], h->stream));
   // K1: linearise
   {
     const int n = B * (int)NS, threads = 64, blocks = (n + threads - 1) / threads;
-    lmpc_linearise_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, din[0], din[2], din[3], din[4], din[7], din[9], abg, cen);
+    lmpc_linearise_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, io.din[0], X_lin, U_lin, io.din[4], io.din[7], io.din[9], abg,
+                                                             first ? cen : nullptr, skip);
     h->launches++;
     CK(cudaGetLastError());
   }
   if (tev) CK(cudaEventRecord(tev[1], h->stream));
   // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272)
-  LmpcLapTable tab;
-  tab.n_used = 0; tab.count = 0;
-  if (learn) {
+  if (learn && first) {
+    LmpcLapTable tab;
     int rc = make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
     if (rc != LMPC_OK) return rc;
-    rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, ssx, ssj);
+    rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, io.ssx, io.ssj);
     if (rc != LMPC_OK) return rc;
+    *ss_count_io = tab.count;
   }
   if (tev) CK(cudaEventRecord(tev[2], h->stream));
   // K3: QP
   LmpcQpBatch a;
-  a.x_ic = din[0]; a.u_ic = din[1]; a.U0 = din[10] ? din[10] : din[3]; a.T_ref = din[4];
-  a.bl = din[5]; a.br = din[6]; a.vref = din[8]; a.ABg = abg; a.ssx = ssx; a.ssj = ssj; a.cen = cen;
-  a.X = dout_d[0]; a.U = dout_d[1]; a.dU = dout_d[2];
-  a.lam = (memspace == LMPC_MEM_HOST) ? (out->convex_combi_optm ? dout_d[3] : nullptr) : out->convex_combi_optm;
-  a.cost = (memspace == LMPC_MEM_HOST) ? (out->cost ? dout_d[6] : nullptr) : out->cost;
-  a.status = d_status; a.iters = d_iters; a.ss_count = tab.count; a.B = B;
+  a.x_ic = io.din[0]; a.u_ic = io.din[1]; a.U0 = U0; a.T_ref = io.din[4];
+  a.bl = io.din[5]; a.br = io.din[6]; a.vref = io.din[8]; a.ABg = abg; a.ssx = io.ssx; a.ssj = io.ssj; a.cen = cen;
+  a.X = io.dout[0]; a.U = io.dout[1]; a.dU = io.dout[2]; a.lam = io.dout[3]; a.cost = io.dout[6];
+  a.status = io.d_status; a.iters = io.d_iters; a.ss_count = *ss_count_io; a.B = B; a.skip = skip;
   launch_qp(h, a);
   h->launches++;
   CK(cudaGetLastError());
   if (tev) { CK(cudaEventRecord(tev[3], h->stream)); h->tcount++; }
-  if (memspace == LMPC_MEM_HOST) {
-    for (int k = 0; k < 7; k++) {
-      if (!hout_d[k]) continue;
-      if ((k == 3 || k == 4 || k == 5) && !learn) continue;
-      CK(cudaMemcpyAsync(hout_d[k], dout_d[k], sizeof(double) * nout_d[k], cudaMemcpyDeviceToHost, h->stream));
-    }
-    CK(cudaMemcpyAsync(out->status, d_status, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(out->iters, d_iters, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
   return LMPC_OK;
+}
+
+extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int memspace) {
+  int rc = check_batch_args(h, B, in, out);
+  if (rc != LMPC_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  DevIO io;
+  rc = stage_in(h, B, in, out, memspace, io);
+  if (rc != LMPC_OK) return rc;
+  int ss_count = 0;
+  rc = run_tick_kernels(h, B, io, io.din[2], io.din[3], io.din[10] ? io.din[10] : io.din[3], true, nullptr, &ss_count);
+  if (rc != LMPC_OK) return rc;
+  return stage_out(h, B, out, memspace, io);
+}
+
+// ------------------------------------------------------------------------------------------ SQP to convergence
+extern "C" int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int max_sqp_iter,
+                                    double sqp_tol, int32_t* sqp_iters, double* defect, int memspace) {
+  int rc = check_batch_args(h, B, in, out);
+  if (rc != LMPC_OK) return rc;
+  if (max_sqp_iter < 1 || !(sqp_tol > 0.0)) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  DevIO io;
+  rc = stage_in(h, B, in, out, memspace, io);
+  if (rc != LMPC_OK) return rc;
+  const size_t Bz = (size_t)B, N = (size_t)h->P.N, NS = (size_t)h->P.NS;
+  // workspace: current linearisation point, per-instance flags, defect, active counter
+  rc = dev_reserve(h, h->ws_sqp, sizeof(double) * (2 * (6 * N + 2 * NS) + 2) * Bz + sizeof(int32_t) * (2 * Bz + 2));
+  if (rc != LMPC_OK) return rc;
+  double* Xk = (double*)h->ws_sqp.p; double* Uk = Xk + 6 * N * Bz; double* Dprev = Uk + 2 * NS * Bz;
+  double* alpha = Dprev + (6 * N + 2 * NS) * Bz; double* dfc = alpha + Bz;
+  int32_t* done = (int32_t*)(dfc + Bz); int32_t* its = done + Bz; int32_t* n_active = its + Bz;
+  const int threads = 128, blocks = (B + threads - 1) / threads;
+  lmpc_sqp_init_kernel<<<blocks, threads, 0, h->stream>>>(B, (int)N, io.din[0], io.din[2], io.din[3], io.din[9], Xk, Uk, Dprev, alpha, done, its);
+  h->launches++;
+  int ss_count = 0;
+  for (int k = 0; k < max_sqp_iter; k++) {
+    // first pass: interior point started from U_warm when given; later passes from the previous solution
+    const double* U0 = (k == 0 && io.din[10]) ? io.din[10] : Uk;
+    rc = run_tick_kernels(h, B, io, Xk, Uk, U0, k == 0, done, &ss_count);
+    if (rc != LMPC_OK) return rc;
+    CK(cudaMemsetAsync(n_active, 0, sizeof(int32_t), h->stream));
+    lmpc_sqp_update_kernel<<<blocks, threads, 0, h->stream>>>(B, (int)N, sqp_tol, io.dout[0], io.dout[1], io.d_status, Xk, Uk, Dprev, alpha, done, its, n_active);
+    h->launches++;
+    CK(cudaGetLastError());
+    int32_t na = 0;
+    CK(cudaMemcpyAsync(&na, n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (na == 0) break;
+  }
+  if (defect) {
+    lmpc_sqp_defect_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, io.dout[0], io.dout[1], io.din[4], io.din[7], dfc);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  if (memspace == LMPC_MEM_HOST) {
+    if (sqp_iters) CK(cudaMemcpyAsync(sqp_iters, its, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    if (defect) CK(cudaMemcpyAsync(defect, dfc, sizeof(double) * Bz, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    if (sqp_iters) CK(cudaMemcpyAsync(sqp_iters, its, sizeof(int32_t) * Bz, cudaMemcpyDeviceToDevice, h->stream));
+    if (defect) CK(cudaMemcpyAsync(defect, dfc, sizeof(double) * Bz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return stage_out(h, B, out, memspace, io);
 }

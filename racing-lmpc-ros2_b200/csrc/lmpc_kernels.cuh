@@ -8,7 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "lmpc_model.cuh"
-#include "lmpc_qp_core.cuh"
+#include "lmpc_qp_kernel.cuh"
 #include "lmpc_ss_core.cuh"
 
 #define LMPC_MAX_LAPS_USED 64   // laps one query can draw from (the table travels as a kernel parameter, 3.6 KB)
@@ -50,16 +50,18 @@ __global__ void lmpc_step_items_kernel(LmpcModel M, int n, const double* __restr
 
 // ---- K1 (solve path): per (instance b, stage i): align X_ref abscissa to x_ic (racing_mpc.cpp:219-223),
 // linearise at (X_ref_i, U_ref_i, kappa_i, T_i) (racing_mpc.cpp:169-176), write [A|B|g] (54 doubles).
-// Stage 0's thread also writes the aligned query / centre point X_ref[:, N-1].
+// Stage 0's thread also writes the aligned query / centre point X_ref[:, N-1] (when cen is given).
+// skip: optional per-instance mask (converged SQP instances keep their linearisation).
 __global__ void lmpc_linearise_kernel(LmpcModel M, int B, int N, const double* __restrict__ x_ic,
                                       const double* __restrict__ X_ref, const double* __restrict__ U_ref,
                                       const double* __restrict__ T_ref, const double* __restrict__ kappa,
                                       const double* __restrict__ total_length, double* __restrict__ ABg,
-                                      double* __restrict__ cen) {
+                                      double* __restrict__ cen, const int* __restrict__ skip) {
   const int NS = N - 1;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * NS) return;
   const int b = t / NS, i = t - b * NS;
+  if (skip && skip[b]) return;
   const double L = total_length[b], s0 = x_ic[6 * (size_t)b];
   const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
   double xl[6], ul[2], Al[36], Bl[12], gl[6];
@@ -71,7 +73,7 @@ __global__ void lmpc_linearise_kernel(LmpcModel M, int B, int N, const double* _
   for (int k = 0; k < 36; k++) o[k] = Al[k];
   for (int k = 0; k < 12; k++) o[36 + k] = Bl[k];
   for (int k = 0; k < 6; k++) o[48 + k] = gl[k];
-  if (i == 0) {
+  if (i == 0 && cen) {
     const double* xe = X_ref + (6 * (size_t)N) * b + 6 * (N - 1);
     double* c = cen + 6 * (size_t)b;
     c[0] = lmpc_align_abscissa(xe[0], s0, L);
@@ -90,33 +92,76 @@ __global__ void lmpc_ss_query_kernel(LmpcLapTable tab, int B, const double* __re
                      j == tab.n_used - 1, tab.count, pad_to);
 }
 
-// ---- K3: one CTA of NW warps per instance
-struct LmpcQpBatch {
-  const double *x_ic, *u_ic, *U0, *T_ref, *bl, *br, *vref, *ABg, *ssx, *ssj, *cen;
-  double *X, *U, *dU, *lam, *cost;
-  int *status, *iters;
-  int ss_count;
-  int B;
-};
+// ---- SQP to convergence (the B200 counterpart of the reference's one-off full-dynamics IPOPT solve,
+// racing_mpc.cpp:67-84,162-166): the tick's QP re-linearised at its own solution.  One thread per instance.
+// init: linearisation point <- (abscissa-aligned X_ref, U_ref)
+__global__ void lmpc_sqp_init_kernel(int B, int N, const double* __restrict__ x_ic, const double* __restrict__ X_ref,
+                                     const double* __restrict__ U_ref, const double* __restrict__ total_length,
+                                     double* __restrict__ Xk, double* __restrict__ Uk, double* __restrict__ Dprev,
+                                     double* __restrict__ alpha_, int* __restrict__ done, int* __restrict__ its) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NS = N - 1;
+  const double L = total_length[b], s0 = x_ic[6 * (size_t)b];
+  const double* xr = X_ref + (6 * (size_t)N) * b; double* xk = Xk + (6 * (size_t)N) * b;
+  for (int i = 0; i < N; i++) {
+    xk[6 * i] = lmpc_align_abscissa(xr[6 * i], s0, L);
+    for (int c = 1; c < 6; c++) xk[6 * i + c] = xr[6 * i + c];
+  }
+  for (int q = 0; q < 2 * NS; q++) Uk[(2 * (size_t)NS) * b + q] = U_ref[(2 * (size_t)NS) * b + q];
+  for (int q = 0; q < 6 * N + 2 * NS; q++) Dprev[(size_t)(6 * N + 2 * NS) * b + q] = 0.0;
+  alpha_[b] = 1.0; done[b] = 0; its[b] = 0;
+}
 
-template <int NW, int KPL, int NTPL, int RSTPL>
-__global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_constant__ LmpcQpParams P, const __grid_constant__ LmpcQpBatch a) {
-  extern __shared__ __align__(16) double sm[];
-  const int b = blockIdx.x;
-  if (b >= a.B) return;
-  const int N = P.N, NS = P.NS, K = P.K;
-  LmpcQpIn in;
-  in.x_ic = a.x_ic + 6 * (size_t)b; in.u_ic = a.u_ic + 2 * (size_t)b;
-  in.U0 = a.U0 + (2 * (size_t)NS) * b; in.T = a.T_ref + (size_t)NS * b;
-  in.bl = a.bl + (size_t)N * b; in.br = a.br + (size_t)N * b; in.vref = a.vref + (size_t)N * b;
-  in.ABg = a.ABg + (54 * (size_t)NS) * b;
-  in.ssx = P.learning ? a.ssx + (6 * (size_t)K) * b : nullptr;
-  in.ssj = P.learning ? a.ssj + (size_t)K * b : nullptr;
-  in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count;
-  LmpcQpOut out;
-  out.X = a.X + (6 * (size_t)N) * b; out.U = a.U + (2 * (size_t)NS) * b; out.dU = a.dU + (2 * (size_t)NS) * b;
-  out.lam = (a.lam && P.learning) ? a.lam + (size_t)K * b : nullptr;
-  out.cost = a.cost ? a.cost + b : nullptr;
-  out.status = a.status + b; out.iters = a.iters + b;
-  lmpc_qp_solve<NW, KPL, NTPL, RSTPL>(P, in, sm, out);
+// update: d = QP solution - linearisation point; step = max |d| / max(1, |new|) over X and U; the linearisation point
+// moves by alpha d, alpha following the angle between successive displacements (cos < -0.25: oscillation of the
+// Gauss-Newton iteration -> halve, >= 1/8; cos > 0.25 -> double, <= 1).
+// done: 1 = converged (step < tol), 2 = the QP failed (its status stays in the output).
+__global__ void lmpc_sqp_update_kernel(int B, int N, double tol, const double* __restrict__ X, const double* __restrict__ U,
+                                       const int* __restrict__ status, double* __restrict__ Xk, double* __restrict__ Uk,
+                                       double* __restrict__ Dprev, double* __restrict__ alpha_, int* __restrict__ done,
+                                       int* __restrict__ its, int* __restrict__ n_active) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || done[b]) return;
+  const int k = its[b];
+  its[b] = k + 1;
+  if (status[b] != LMPC_SOLVED) { done[b] = 2; return; }
+  const int NS = N - 1, nx = 6 * N, nd = 6 * N + 2 * NS;
+  const double* xn = X + (size_t)nx * b; const double* un = U + (2 * (size_t)NS) * b;
+  double* xk = Xk + (size_t)nx * b; double* uk = Uk + (2 * (size_t)NS) * b; double* dpv = Dprev + (size_t)nd * b;
+  double step = 0.0, dd = 0.0, dp = 0.0, pp = 0.0;
+  for (int q = 0; q < nd; q++) {
+    const double nv = q < nx ? xn[q] : un[q - nx], ov = q < nx ? xk[q] : uk[q - nx];
+    const double d = nv - ov, pv = dpv[q];
+    step = fmax(step, fabs(d) / fmax(1.0, fabs(nv)));
+    dd += d * d; dp += d * pv; pp += pv * pv;
+    dpv[q] = d;
+  }
+  if (step < tol) { done[b] = 1; return; }
+  double alpha = alpha_[b];
+  if (k > 0) {
+    const double cs = dp / sqrt(dd * pp + 1e-300);
+    if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125); else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
+    alpha_[b] = alpha;
+  }
+  for (int q = 0; q < nx; q++) xk[q] += alpha * dpv[q];
+  for (int q = 0; q < 2 * NS; q++) uk[q] += alpha * dpv[nx + q];
+  atomicAdd(n_active, 1);
+}
+
+// defect of the nonlinear dynamics at the returned trajectory: max_i,c |x_{i+1} - f_d(x_i, u_i, kappa_i, T_i)|_c
+__global__ void lmpc_sqp_defect_kernel(LmpcModel M, int B, int N, const double* __restrict__ X, const double* __restrict__ U,
+                                       const double* __restrict__ T_ref, const double* __restrict__ kappa, double* __restrict__ defect) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int NS = N - 1;
+  double dmax = 0.0;
+  for (int i = 0; i < NS; i++) {
+    double xl[6], ul[2], xn[6];
+    for (int c = 0; c < 6; c++) xl[c] = X[(6 * (size_t)N) * b + 6 * i + c];
+    ul[0] = U[(2 * (size_t)NS) * b + 2 * i]; ul[1] = U[(2 * (size_t)NS) * b + 2 * i + 1];
+    lmpc_step(M, xl, ul, kappa[(size_t)N * b + i], T_ref[(size_t)NS * b + i], xn);
+    for (int c = 0; c < 6; c++) dmax = fmax(dmax, fabs(xn[c] - X[(6 * (size_t)N) * b + 6 * (i + 1) + c]));
+  }
+  defect[b] = dmax;
 }

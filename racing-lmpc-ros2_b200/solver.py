@@ -207,6 +207,33 @@ class BatchedRacingMPC:
             self._solved = True
         return out
 
+    def solve_sqp(self, batch, max_sqp_iter=20, tol=1e-9, out=None):
+        """RacingMPC(config, model, full_dynamics=True).solve (racing_mpc.cpp:67-84,162-166): the problem with the
+        nonlinear dynamics constraint, solved by SQP on the tick's kernels (host buffers).  Adds `sqp_iters` (QP solves
+        per instance) and `defect` (max nonlinear-dynamics violation of the returned trajectory) to the outputs."""
+        Bn = int(np.asarray(batch["x_ic"]).shape[0])
+        keep = {k: np.ascontiguousarray(batch[k], dtype=np.float64) for k in IN_KEYS}
+        warm = batch.get("U_optm_ref", None)
+        if warm is not None:
+            keep["U_warm"] = np.ascontiguousarray(warm, dtype=np.float64)
+        bi = B.BatchIn()
+        for k in IN_KEYS:
+            setattr(bi, k, keep[k].ctypes.data)
+        bi.U_warm = keep["U_warm"].ctypes.data if "U_warm" in keep else None
+        if out is None:
+            out = self.alloc_host_outputs(Bn)
+        out["sqp_iters"] = np.zeros(Bn, dtype=np.int32)
+        out["defect"] = np.zeros(Bn)
+        bo = B.BatchOut()
+        for k in ("X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost", "status", "iters"):
+            setattr(bo, k, out[k].ctypes.data)
+        rc = self.lib.lmpc_solve_sqp_batch(self._h, Bn, C.byref(bi), C.byref(bo), int(max_sqp_iter), float(tol),
+                                           out["sqp_iters"].ctypes.data, out["defect"].ctypes.data, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_solve_sqp_batch")
+        if (out["status"] == 0).any():
+            self._solved = True
+        return out
+
     def alloc_device_outputs(self, Bn, device=None):
         import torch
         dev = device or torch.device("cuda", self.device)

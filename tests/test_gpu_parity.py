@@ -269,3 +269,33 @@ def test_fifty_lap_safe_set_config4(pkg, laps, barc_track):
         m.add_lap(l["x"], l["u"], l["k"], l["t"], L)
     with pytest.raises(RuntimeError):
         m.ss_query(q[:2])
+
+
+@pytest.mark.parametrize("name,nb", [("barc_tracking", 16), ("barc_lmpc", 32), ("iac_tracking", 16)])
+def test_sqp_full_dynamics_matches_oracle(pkg, name, nb):
+    """Row a12: RacingMPC(config, model, full_dynamics=true)::solve (racing_mpc.cpp:67-84,162-166) -- SQP to
+    convergence on the device against the oracle's restatement, plus what defines the answer: the returned
+    trajectory satisfies the NONLINEAR dynamics."""
+    m, veh, cfg, track, mode = _mpc(pkg, name, nb)
+    o, *_ = make_oracle(pkg, name, tol=1e-10)
+    batch = pkg.workload.make_batch(veh, cfg, nb, 0x5A9, track, pkg.workload.load_laps(), mode=mode)
+    MAXIT = 60
+    n0 = m.launch_count
+    out = m.solve_sqp(batch, max_sqp_iter=MAXIT, tol=1e-9)
+    assert m.launch_count - n0 >= 4
+    conv = (out["status"] == 0) & (out["sqp_iters"] < MAXIT)
+    assert conv.sum() >= int(0.75 * nb), (conv.sum(), out["sqp_iters"], out["status"])
+    scale = max(1.0, np.abs(out["X_optm"][conv]).max())
+    assert out["defect"][conv].max() < 1e-7 * scale, out["defect"][conv].max()
+    one = m.solve(batch)
+    assert np.abs(one["X_optm"][conv] - out["X_optm"][conv]).max() > 1e-6     # not the single linearised tick
+    worst, n = 0.0, 0
+    for b in np.where(conv)[0]:
+        r = o.step_sqp(pkg.workload.instance(batch, b), max_sqp_iter=MAXIT, tol=1e-9)
+        if r["status"] != 0 or r["sqp_iters"] >= MAXIT:
+            continue
+        worst = max(worst, relerr(out["X_optm"][b], r["X"]), relerr(out["U_optm"][b], r["U"]), relerr(out["dU_optm"][b], r["dU"]))
+        n += 1
+    assert n >= int(0.7 * nb), n
+    assert worst < TOL, worst
+    print(f"[{name}] SQP: {conv.sum()}/{nb} converged, mean {out['sqp_iters'][conv].mean():.1f} QP solves, worst rel err vs oracle {worst:.2e}")
