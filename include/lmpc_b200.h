@@ -19,6 +19,11 @@
  *   lmpc_safe_set_add_lap               SafeSetManager::add_lap(x,u,k,t,total_length)   safe_set.hpp:119-121
  *   lmpc_safe_set_load                  SafeSetRecorder::load(from_files,total_length)  safe_set.cpp:260-276
  *   lmpc_safe_set_query_batch           SafeSetManager::query(const SSQuery&) -> SSResult  safe_set.cpp:153-180
+ *   lmpc_track_set / _load / _eval_batch RacingTrajectory and its interpolation functions  racing_trajectory.cpp:25-119
+ *   lmpc_frenet_to_global_batch,        RacingTrajectory::frenet_to_global / global_to_frenet
+ *   lmpc_global_to_frenet_batch           racing_trajectory.cpp:121-236
+ *   lmpc_prepare_batch                  RacingMPCNode::on_step_timer's input preparation  racing_mpc_node.cpp:236-292
+ *   lmpc_closed_loop_run                prepare + solve + RacingSimulator::step, B agents  racing_simulator.cpp:97-113
  *
  * Conventions
  *   - plain pointers and sizes only; no C++/torch types; functions return an lmpc_status code
@@ -180,6 +185,47 @@ int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_
  * returned trajectory (the nonlinear constraint violation).  out->status is the status of the last QP of the instance. */
 int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int max_sqp_iter,
                          double sqp_tol, int32_t* sqp_iters, double* defect, int memspace);
+/* ---- track (RacingTrajectory: the degree-3 "bspline" interpolants over the abscissa and what is built from them,
+ *      vehicle_dynamics_models/racing_trajectory/src/racing_trajectory.cpp:25-236) ----
+ * table: the trajectory file's rows (>= 13 columns in TrajectoryIndex order, racing_trajectory.hpp:37-56), row-major. */
+int lmpc_track_set(lmpc_handle* h, int n_rows, int n_cols, const double* table);
+int lmpc_track_load(lmpc_handle* h, const char* file);             /* RacingTrajectory(file_name), :188-191 */
+int lmpc_track_total_length(const lmpc_handle* h, double* total_length);
+/* left_boundary / right_boundary / curvature / velocity / x / y / yaw interpolation functions (:96-118) at n abscissae:
+ * out [n][7] in that order. */
+int lmpc_track_eval_batch(lmpc_handle* h, int n, const double* s, double* out, int memspace);
+/* frenet_to_global (:121-136, 193-202) and global_to_frenet (:138-186, 204-236) for n poses [n][3] = (s, t, xi) / (x, y, phi). */
+int lmpc_frenet_to_global_batch(lmpc_handle* h, int n, const double* frenet, double* global, int memspace);
+int lmpc_global_to_frenet_batch(lmpc_handle* h, int n, const double* global, double* frenet, int memspace);
+
+/* ---- closed loop on the device: tick preparation + solve + plant, many agents, no host round trip ----
+ * What RacingMPCNode::on_step_timer does around the solve (mpc/racing_mpc/src/racing_mpc_node.cpp:236-292, 322-331,
+ * 386-401) and what RacingSimulator / RacingSimulatorNode do with the published actuation
+ * (simulation/racing_simulator/src/racing_simulator.cpp:97-113, racing_simulator_node.cpp:241-286). */
+typedef struct lmpc_loop_options {
+  int32_t step_mode;        /* 0 = step: x_ic is the measured state; 1 = continuous: x_ic = f_d(measured, last_u[0])
+                             * (RacingMPCStepMode, racing_mpc_node.cpp:238-244) */
+  int32_t delay_step;       /* column of the solution that is published (racing_mpc_node.cpp:386-389) */
+  int32_t plant_substeps;   /* simulator steps per MPC tick */
+  int32_t pad_;
+  double dt;                /* MPC sample time: T_ref and the shift-and-extend step (racing_mpc_node.cpp:65,248) */
+  double plant_dt;          /* racing_simulator dt (RK4 step of the plant) */
+  double speed_limit, speed_scale, max_vel_ref_diff;   /* velocity-reference clipping, racing_mpc_node.cpp:266-287 */
+} lmpc_loop_options;
+/* Runs `ticks` MPC ticks for B agents.  Agent state, all in/out: x [B][6] plant state (Frenet), u_prev [B][2] the
+ * last published (u_a, u_steer) (= u_ic of the next tick), X_last [B][N][6] / U_last [B][N-1][2] the previous solution
+ * (last_x_ / last_u_; start them from lmpc_solve_sqp_batch as the node does).  Optional: lap_count [B] (in/out; the
+ * simulator node's counter), fail_count [B] (out: ticks whose solve failed -- the shifted reference is kept, as in the
+ * node), log_x [ticks][B][6] / log_u [ticks][B][2] (plant state after, and actuation of, every tick). */
+int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                         double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                         double* log_u, int memspace);
+/* The preparation step on its own (DEVICE buffers only): fills the input keys of lmpc_solve_batch. */
+int lmpc_prepare_batch(lmpc_handle* h, int B, const lmpc_loop_options* opt, const double* x, const double* u_prev,
+                       const double* X_last, const double* U_last, double* x_ic, double* u_ic, double* X_ref, double* U_ref,
+                       double* T_ref, double* bound_left, double* bound_right, double* curvatures, double* vel_ref,
+                       double* total_length);
+
 /* Per-kernel device timing (measurement aid): when enabled, CUDA events are recorded on the handle's
  * stream around the three kernels of every lmpc_solve_batch; lmpc_get_kernel_ms synchronises and
  * returns the summed milliseconds {linearise, safe-set query, QP} over the recorded solves. */

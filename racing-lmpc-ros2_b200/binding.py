@@ -50,6 +50,12 @@ class BatchOut(C.Structure):
         "X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost", "status", "iters")]
 
 
+class LoopOptions(C.Structure):
+    _fields_ = [("step_mode", C.c_int32), ("delay_step", C.c_int32), ("plant_substeps", C.c_int32), ("pad_", C.c_int32),
+                ("dt", C.c_double), ("plant_dt", C.c_double), ("speed_limit", C.c_double), ("speed_scale", C.c_double),
+                ("max_vel_ref_diff", C.c_double)]
+
+
 def fill_struct(st, d):
     for name, _ in st._fields_:
         if name not in d:
@@ -70,6 +76,8 @@ EXPORTS = [
     "lmpc_safe_set_clear", "lmpc_safe_set_num_laps", "lmpc_safe_set_query_batch",
     "lmpc_discrete_dynamics_batch", "lmpc_linearise_batch", "lmpc_solve_batch", "lmpc_solve_sqp_batch", "lmpc_synchronize",
     "lmpc_set_timing", "lmpc_get_kernel_ms", "lmpc_measure_fp64_peak",
+    "lmpc_track_set", "lmpc_track_load", "lmpc_track_total_length", "lmpc_track_eval_batch",
+    "lmpc_frenet_to_global_batch", "lmpc_global_to_frenet_batch", "lmpc_closed_loop_run", "lmpc_prepare_batch",
 ]
 
 _lib = None
@@ -110,6 +118,14 @@ def load_library(path=None):
     L.lmpc_set_timing.argtypes = [vp, C.c_int]
     L.lmpc_get_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.lmpc_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lmpc_track_set.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.lmpc_track_load.argtypes = [vp, C.c_char_p]
+    L.lmpc_track_total_length.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lmpc_track_eval_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.lmpc_frenet_to_global_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.lmpc_global_to_frenet_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+    L.lmpc_closed_loop_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(LoopOptions)] + [vp] * 8 + [C.c_int]
+    L.lmpc_prepare_batch.argtypes = [vp, C.c_int, C.POINTER(LoopOptions)] + [vp] * 14
     if path is None:
         _lib = L
     return L

@@ -15,6 +15,7 @@
 #include "lmpc_host_params.h"
 #include "lmpc_kernels.cuh"
 #include "lmpc_qp_launch.h"
+#include "lmpc_loop.cuh"
 
 namespace {
 
@@ -47,6 +48,10 @@ struct lmpc_handle {
   std::vector<LmpcLapView> dev_laps;   // newest first, device pointers into the slab
   // device workspace
   DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp;
+  // track interpolants (device copy of LmpcTrackHost) and closed-loop workspace
+  LmpcTrackHost track_host;
+  DevBuf track_dev, ws_loop, st_loop;
+  LmpcTrack track{};   // device view; m == 0 until lmpc_track_set
   // device staging for host-memory callers
   DevBuf st_in, st_out;
   size_t qp_smem = 0;
@@ -148,7 +153,7 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
   for (auto& e : h->tev) cudaEventDestroy(e);
-  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->st_in, &h->st_out})
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
   return LMPC_OK;
@@ -641,4 +646,197 @@ extern "C" int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* 
     if (defect) CK(cudaMemcpyAsync(defect, dfc, sizeof(double) * Bz, cudaMemcpyDeviceToDevice, h->stream));
   }
   return stage_out(h, B, out, memspace, io);
+}
+
+// ------------------------------------------------------------------------------------------ track
+extern "C" int lmpc_track_set(lmpc_handle* h, int n_rows, int n_cols, const double* table) {
+  if (!h || !table) return LMPC_ERR_INVALID;
+  LmpcTrackHost th;
+  if (!lmpc_track_build(n_rows, n_cols, table, &th)) { h->err = "track table rejected (needs >= 8 rows, >= 13 columns, increasing abscissa, total length > 0)"; return LMPC_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t nb = th.brk.size(), nc = th.coef.size(), nw = th.way.size();
+  int rc = dev_reserve(h, h->track_dev, sizeof(double) * (nb + nc + nw));
+  if (rc != LMPC_OK) return rc;
+  double* d = (double*)h->track_dev.p;
+  CK(cudaMemcpyAsync(d, th.brk.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d + nb, th.coef.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d + nb + nc, th.way.data(), sizeof(double) * nw, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->track_host = std::move(th);
+  h->track.m = h->track_host.m; h->track.n_way = h->track_host.n_way; h->track.L = h->track_host.L;
+  h->track.brk = d; h->track.coef = d + nb; h->track.way = d + nb + nc;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_track_load(lmpc_handle* h, const char* file) {
+  if (!h || !file) return LMPC_ERR_INVALID;
+  // casadi::DM::from_file(file_name).T() (racing_trajectory.cpp:188-191): whitespace-separated rows of equal length
+  FILE* f = fopen(file, "r");
+  if (!f) { h->err = std::string("cannot open ") + file; return LMPC_ERR_IO; }
+  std::vector<double> v; int rows = 0, cols = -1;
+  char* line = nullptr; size_t cap = 0;
+  bool bad = false;
+  while (getline(&line, &cap, f) > 0) {
+    int c = 0; char* p = line; char* e = nullptr;
+    for (;;) { const double x = strtod(p, &e); if (e == p) break; v.push_back(x); c++; p = e; while (*p == ',' ) p++; }
+    if (c == 0) continue;
+    if (cols < 0) cols = c; else if (c != cols) bad = true;
+    rows++;
+  }
+  free(line); fclose(f);
+  if (bad || rows == 0) { h->err = std::string("malformed track file ") + file; return LMPC_ERR_IO; }
+  return lmpc_track_set(h, rows, cols, v.data());
+}
+
+extern "C" int lmpc_track_total_length(const lmpc_handle* h, double* L) {
+  if (!h || !L || h->track.m == 0) return LMPC_ERR_INVALID;
+  *L = h->track.L;
+  return LMPC_OK;
+}
+
+// n items of `in_w` doubles in, `out_w` doubles out, through one of the three track kernels
+static int track_batch(lmpc_handle* h, int which, int n, const double* in, int in_w, double* out, int out_w, int memspace) {
+  if (!h || n < 1 || !in || !out) return LMPC_ERR_INVALID;
+  if (h->track.m == 0) { h->err = "no track set (lmpc_track_set / lmpc_track_load)"; return LMPC_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  const double* din = in; double* dout = out;
+  if (memspace == LMPC_MEM_HOST) {
+    int rc = dev_reserve(h, h->st_in, sizeof(double) * (size_t)n * in_w);
+    if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * (size_t)n * out_w);
+    if (rc != LMPC_OK) return rc;
+    CK(cudaMemcpyAsync(h->st_in.p, in, sizeof(double) * (size_t)n * in_w, cudaMemcpyHostToDevice, h->stream));
+    din = (const double*)h->st_in.p; dout = (double*)h->st_out.p;
+  }
+  const int threads = 128, blocks = (n + threads - 1) / threads;
+  if (which == 0) lmpc_track_eval_kernel<<<blocks, threads, 0, h->stream>>>(h->track, n, din, dout);
+  else if (which == 1) lmpc_frenet_to_global_kernel<<<blocks, threads, 0, h->stream>>>(h->track, n, din, dout);
+  else lmpc_global_to_frenet_kernel<<<blocks, threads, 0, h->stream>>>(h->track, n, din, dout);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (memspace == LMPC_MEM_HOST) {
+    CK(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n * out_w, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_track_eval_batch(lmpc_handle* h, int n, const double* s, double* out, int memspace) { return track_batch(h, 0, n, s, 1, out, 7, memspace); }
+extern "C" int lmpc_frenet_to_global_batch(lmpc_handle* h, int n, const double* frenet, double* global, int memspace) { return track_batch(h, 1, n, frenet, 3, global, 3, memspace); }
+extern "C" int lmpc_global_to_frenet_batch(lmpc_handle* h, int n, const double* global, double* frenet, int memspace) { return track_batch(h, 2, n, global, 3, frenet, 3, memspace); }
+
+// ------------------------------------------------------------------------------------------ closed loop
+static LmpcLoopParams loop_params(const lmpc_loop_options* o) {
+  LmpcLoopParams P;
+  P.step_mode = o->step_mode; P.delay_step = o->delay_step; P.plant_substeps = o->plant_substeps;
+  P.dt = o->dt; P.plant_dt = o->plant_dt; P.speed_limit = o->speed_limit; P.speed_scale = o->speed_scale;
+  P.max_vel_ref_diff = o->max_vel_ref_diff;
+  return P;
+}
+
+extern "C" int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                                    double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                                    double* log_u, int memspace) {
+  if (!h || !opt || B < 1 || ticks < 1 || !x || !u_prev || !X_last || !U_last) return LMPC_ERR_INVALID;
+  if (B > h->max_batch) return LMPC_ERR_CAPACITY;
+  if (h->track.m == 0) { h->err = "no track set (lmpc_track_set / lmpc_track_load)"; return LMPC_ERR_INVALID; }
+  if (opt->step_mode < 0 || opt->step_mode > 1 || opt->delay_step < 0 || opt->delay_step >= h->P.NS || opt->plant_substeps < 1 ||
+      !(opt->dt > 0.0) || !(opt->plant_dt > 0.0))
+    return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t Bz = (size_t)B, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)std::max(h->P.K, 1);
+  const LmpcLoopParams O = loop_params(opt);
+  // tick workspace: the solve's inputs and outputs, counters
+  const size_t n_in = 6 * Bz + 2 * Bz + 6 * N * Bz + 2 * NS * Bz + NS * Bz + 4 * N * Bz + Bz;
+  const size_t n_out = 6 * N * Bz + 4 * NS * Bz + K * Bz + Bz;
+  int rc = dev_reserve(h, h->ws_loop, sizeof(double) * (n_in + n_out) + sizeof(int32_t) * (4 * Bz + 4));
+  if (rc != LMPC_OK) return rc;
+  double* w = (double*)h->ws_loop.p;
+  LmpcTickIn I;
+  I.x_ic = w; w += 6 * Bz; I.u_ic = w; w += 2 * Bz; I.X_ref = w; w += 6 * N * Bz; I.U_ref = w; w += 2 * NS * Bz;
+  I.T_ref = w; w += NS * Bz; I.bl = w; w += N * Bz; I.br = w; w += N * Bz; I.kap = w; w += N * Bz; I.vref = w; w += N * Bz;
+  I.L = w; w += Bz;
+  double* oX = w; w += 6 * N * Bz; double* oU = w; w += 2 * NS * Bz; double* odU = w; w += 2 * NS * Bz;
+  double* olam = w; w += K * Bz; double* ocost = w; w += Bz;
+  int32_t* ostatus = (int32_t*)w; int32_t* oiters = ostatus + Bz; int32_t* d_lap = oiters + Bz; int32_t* d_fail = d_lap + Bz;
+  int32_t* d_tick = d_fail + Bz;
+  // agent state: caller's device buffers, or a staged copy of the caller's host buffers
+  LmpcLoopState S;
+  double *dlogx = log_x, *dlogu = log_u;
+  const size_t n_state = 6 * Bz + 2 * Bz + 6 * N * Bz + 2 * NS * Bz;
+  if (memspace == LMPC_MEM_HOST) {
+    const size_t n_log = (log_x ? 6 * Bz * (size_t)ticks : 0) + (log_u ? 2 * Bz * (size_t)ticks : 0);
+    rc = dev_reserve(h, h->st_loop, sizeof(double) * (n_state + n_log));
+    if (rc != LMPC_OK) return rc;
+    double* q = (double*)h->st_loop.p;
+    S.x = q; q += 6 * Bz; S.u_prev = q; q += 2 * Bz; S.X_last = q; q += 6 * N * Bz; S.U_last = q; q += 2 * NS * Bz;
+    if (log_x) { dlogx = q; q += 6 * Bz * (size_t)ticks; }
+    if (log_u) { dlogu = q; q += 2 * Bz * (size_t)ticks; }
+    CK(cudaMemcpyAsync(S.x, x, sizeof(double) * 6 * Bz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.u_prev, u_prev, sizeof(double) * 2 * Bz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.X_last, X_last, sizeof(double) * 6 * N * Bz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.U_last, U_last, sizeof(double) * 2 * NS * Bz, cudaMemcpyHostToDevice, h->stream));
+    if (lap_count) CK(cudaMemcpyAsync(d_lap, lap_count, sizeof(int32_t) * Bz, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(d_lap, 0, sizeof(int32_t) * Bz, h->stream));
+  } else {
+    S.x = x; S.u_prev = u_prev; S.X_last = X_last; S.U_last = U_last;
+    if (lap_count) CK(cudaMemcpyAsync(d_lap, lap_count, sizeof(int32_t) * Bz, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemsetAsync(d_lap, 0, sizeof(int32_t) * Bz, h->stream));
+  }
+  S.lap_count = d_lap; S.fail_count = d_fail; S.tick = d_tick;
+  CK(cudaMemsetAsync(d_fail, 0, sizeof(int32_t) * (Bz + 1), h->stream));   // fail counters and the tick counter
+
+  DevIO io;
+  const double* din[11] = {I.x_ic, I.u_ic, I.X_ref, I.U_ref, I.T_ref, I.bl, I.br, I.kap, I.vref, I.L, nullptr};
+  for (int k = 0; k < 11; k++) io.din[k] = din[k];
+  io.dout[0] = oX; io.dout[1] = oU; io.dout[2] = odU; io.dout[3] = olam; io.dout[4] = nullptr; io.dout[5] = nullptr; io.dout[6] = ocost;
+  io.d_status = ostatus; io.d_iters = oiters; io.ssx = (double*)h->ws_ssx.p; io.ssj = (double*)h->ws_ssj.p;
+  const int pthreads = 128, pblocks = (B * (int)N + pthreads - 1) / pthreads, ablocks = (B + pthreads - 1) / pthreads;
+  for (int t = 0; t < ticks; t++) {
+    lmpc_prepare_kernel<<<pblocks, pthreads, 0, h->stream>>>(h->M, h->track, O, B, (int)N, S, I);
+    h->launches++;
+    CK(cudaGetLastError());
+    int ss_count = 0;
+    rc = run_tick_kernels(h, B, io, I.X_ref, I.U_ref, I.U_ref, true, nullptr, &ss_count);
+    if (rc != LMPC_OK) return rc;
+    lmpc_plant_kernel<<<ablocks, pthreads, 0, h->stream>>>(h->M, h->track, O, B, (int)N, S, I, oX, oU, ostatus, dlogx, dlogu, ticks);
+    lmpc_tick_advance_kernel<<<1, 1, 0, h->stream>>>(d_tick);
+    h->launches += 2;
+    CK(cudaGetLastError());
+  }
+  if (memspace == LMPC_MEM_HOST) {
+    CK(cudaMemcpyAsync(x, S.x, sizeof(double) * 6 * Bz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(u_prev, S.u_prev, sizeof(double) * 2 * Bz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(X_last, S.X_last, sizeof(double) * 6 * N * Bz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(U_last, S.U_last, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+    if (lap_count) CK(cudaMemcpyAsync(lap_count, d_lap, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    if (fail_count) CK(cudaMemcpyAsync(fail_count, d_fail, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    if (log_x) CK(cudaMemcpyAsync(log_x, dlogx, sizeof(double) * 6 * Bz * (size_t)ticks, cudaMemcpyDeviceToHost, h->stream));
+    if (log_u) CK(cudaMemcpyAsync(log_u, dlogu, sizeof(double) * 2 * Bz * (size_t)ticks, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  } else {
+    if (lap_count) CK(cudaMemcpyAsync(lap_count, d_lap, sizeof(int32_t) * Bz, cudaMemcpyDeviceToDevice, h->stream));
+    if (fail_count) CK(cudaMemcpyAsync(fail_count, d_fail, sizeof(int32_t) * Bz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return LMPC_OK;
+}
+
+// one preparation step on its own (parity tests; device buffers only): fills the solve's input keys from the agent state
+extern "C" int lmpc_prepare_batch(lmpc_handle* h, int B, const lmpc_loop_options* opt, const double* x, const double* u_prev,
+                                  const double* X_last, const double* U_last, double* x_ic, double* u_ic, double* X_ref,
+                                  double* U_ref, double* T_ref, double* bound_left, double* bound_right, double* curvatures,
+                                  double* vel_ref, double* total_length) {
+  if (!h || !opt || B < 1 || !x || !u_prev || !X_last || !U_last || !x_ic || !u_ic || !X_ref || !U_ref || !T_ref || !bound_left ||
+      !bound_right || !curvatures || !vel_ref || !total_length)
+    return LMPC_ERR_INVALID;
+  if (h->track.m == 0) { h->err = "no track set (lmpc_track_set / lmpc_track_load)"; return LMPC_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  LmpcLoopState S{};
+  S.x = const_cast<double*>(x); S.u_prev = const_cast<double*>(u_prev); S.X_last = const_cast<double*>(X_last); S.U_last = const_cast<double*>(U_last);
+  LmpcTickIn I{x_ic, u_ic, X_ref, U_ref, T_ref, bound_left, bound_right, curvatures, vel_ref, total_length};
+  const int N = h->P.N, threads = 128, blocks = (B * N + threads - 1) / threads;
+  lmpc_prepare_kernel<<<blocks, threads, 0, h->stream>>>(h->M, h->track, loop_params(opt), B, N, S, I);
+  h->launches++;
+  CK(cudaGetLastError());
+  return LMPC_OK;
 }

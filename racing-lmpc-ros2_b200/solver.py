@@ -132,6 +132,86 @@ class BatchedRacingMPC:
         c = int(cnt[0]) if Bn else 0
         return sx[:, :c], sj[:, :c]
 
+    # ------------------------------------------------------------------ track (RacingTrajectory)
+    def set_track(self, table):
+        """table: (n, >= 13) trajectory-file rows in TrajectoryIndex column order (racing_trajectory.hpp:37-56)."""
+        tb = np.ascontiguousarray(table, dtype=np.float64)
+        _check(self.lib, self._h, self.lib.lmpc_track_set(self._h, tb.shape[0], tb.shape[1], tb.ctypes.data), "lmpc_track_set")
+
+    def load_track(self, path):
+        _check(self.lib, self._h, self.lib.lmpc_track_load(self._h, str(path).encode()), "lmpc_track_load")
+
+    def track_length(self):
+        v = C.c_double()
+        _check(self.lib, self._h, self.lib.lmpc_track_total_length(self._h, C.byref(v)), "lmpc_track_total_length")
+        return v.value
+
+    def track_eval(self, s):
+        """The interpolation functions at abscissae s -> dict of left, right, curvature, vel, x, y, yaw."""
+        s = np.ascontiguousarray(s, dtype=np.float64).ravel()
+        out = np.zeros((len(s), 7))
+        _check(self.lib, self._h, self.lib.lmpc_track_eval_batch(self._h, len(s), s.ctypes.data, out.ctypes.data, B.LMPC_MEM_HOST),
+               "lmpc_track_eval_batch")
+        return dict(left=out[:, 0], right=out[:, 1], curvature=out[:, 2], vel=out[:, 3], x=out[:, 4], y=out[:, 5], yaw=out[:, 6])
+
+    def frenet_to_global(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1, 3)
+        g = np.zeros_like(f)
+        _check(self.lib, self._h, self.lib.lmpc_frenet_to_global_batch(self._h, len(f), f.ctypes.data, g.ctypes.data, B.LMPC_MEM_HOST),
+               "lmpc_frenet_to_global_batch")
+        return g
+
+    def global_to_frenet(self, g):
+        g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1, 3)
+        f = np.zeros_like(g)
+        _check(self.lib, self._h, self.lib.lmpc_global_to_frenet_batch(self._h, len(g), g.ctypes.data, f.ctypes.data, B.LMPC_MEM_HOST),
+               "lmpc_global_to_frenet_batch")
+        return f
+
+    # ------------------------------------------------------------------ closed loop
+    @staticmethod
+    def loop_options(dt, step_mode="step", delay_step=0, plant_dt=None, plant_substeps=1, speed_limit=1e9, speed_scale=1.0,
+                     max_vel_ref_diff=1.0):
+        o = B.LoopOptions()
+        o.step_mode = {"step": 0, "continuous": 1}[step_mode]
+        o.delay_step = int(delay_step); o.plant_substeps = int(plant_substeps)
+        o.dt = float(dt); o.plant_dt = float(dt if plant_dt is None else plant_dt)
+        o.speed_limit = float(speed_limit); o.speed_scale = float(speed_scale); o.max_vel_ref_diff = float(max_vel_ref_diff)
+        return o
+
+    def prepare(self, opt, x, u_prev, X_last, U_last):
+        """RacingMPCNode's input preparation (racing_mpc_node.cpp:236-292) for B agents -> the solve's input dict
+        (torch CUDA tensors in, torch CUDA tensors out)."""
+        import torch
+        Bn, N = int(x.shape[0]), self.N
+        dev = x.device
+        shapes = dict(x_ic=(Bn, 6), u_ic=(Bn, 2), X_ref=(Bn, N, 6), U_ref=(Bn, N - 1, 2), T_ref=(Bn, N - 1), bound_left=(Bn, N),
+                      bound_right=(Bn, N), curvatures=(Bn, N), vel_ref=(Bn, N), total_length=(Bn,))
+        out = {k: torch.empty(shp, dtype=torch.float64, device=dev) for k, shp in shapes.items()}
+        rc = self.lib.lmpc_prepare_batch(self._h, Bn, C.byref(opt), x.data_ptr(), u_prev.data_ptr(), X_last.data_ptr(),
+                                         U_last.data_ptr(), *[out[k].data_ptr() for k in IN_KEYS])
+        _check(self.lib, self._h, rc, "lmpc_prepare_batch")
+        return out
+
+    def closed_loop(self, opt, ticks, x, u_prev, X_last, U_last, lap_count=None, log=True):
+        """`ticks` MPC ticks of B agents entirely on the device (prepare -> solve -> plant).  numpy in / numpy out:
+        returns dict(x, u_prev, X_last, U_last, lap_count, fail_count[, log_x (ticks, B, 6), log_u (ticks, B, 2)])."""
+        x = np.array(x, dtype=np.float64, order="C"); u_prev = np.array(u_prev, dtype=np.float64, order="C")
+        X_last = np.array(X_last, dtype=np.float64, order="C"); U_last = np.array(U_last, dtype=np.float64, order="C")
+        Bn = x.shape[0]
+        laps = np.zeros(Bn, dtype=np.int32) if lap_count is None else np.array(lap_count, dtype=np.int32)
+        fails = np.zeros(Bn, dtype=np.int32)
+        lx = np.zeros((ticks, Bn, 6)) if log else None
+        lu = np.zeros((ticks, Bn, 2)) if log else None
+        rc = self.lib.lmpc_closed_loop_run(self._h, Bn, int(ticks), C.byref(opt), x.ctypes.data, u_prev.ctypes.data,
+                                           X_last.ctypes.data, U_last.ctypes.data, laps.ctypes.data, fails.ctypes.data,
+                                           lx.ctypes.data if log else None, lu.ctypes.data if log else None, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_closed_loop_run")
+        out = dict(x=x, u_prev=u_prev, X_last=X_last, U_last=U_last, lap_count=laps, fail_count=fails)
+        if log:
+            out["log_x"] = lx; out["log_u"] = lu
+        return out
+
     # ------------------------------------------------------------------ model
     def discrete_dynamics(self, x, u, kappa, dt):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 6)

@@ -54,3 +54,21 @@ extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params*
   }
   return LMPC_OK;
 }
+
+// ---- track interpolation functions (host builder + the device evaluation code, compiled for the CPU)
+#include "../../racing-lmpc-ros2_b200/csrc/lmpc_track.cuh"
+static LmpcTrackHost g_trk;
+extern "C" int emu_track_build(int n, int ncols, const double* table) { return lmpc_track_build(n, ncols, table, &g_trk) ? 0 : -1; }
+extern "C" int emu_track_m() { return g_trk.m; }
+extern "C" double emu_track_length() { return g_trk.L; }
+extern "C" void emu_track_eval(int n, const double* s, double* out) {   // out [n][7]: left right curvature vel x y yaw
+  const LmpcTrack T = g_trk.view();
+  for (int i = 0; i < n; i++) {
+    LmpcTrackPoint p;
+    lmpc_track_eval(T, s[i], &p);
+    double* o = out + 7 * (size_t)i;
+    o[0] = p.left; o[1] = p.right; o[2] = p.curvature; o[3] = p.vel; o[4] = p.x; o[5] = p.y; o[6] = p.yaw;
+  }
+}
+extern "C" void emu_track_f2g(int n, const double* f, double* g) { const LmpcTrack T = g_trk.view(); for (int i = 0; i < n; i++) lmpc_frenet_to_global(T, f + 3 * i, g + 3 * i); }
+extern "C" void emu_track_g2f(int n, const double* g, double* f) { const LmpcTrack T = g_trk.view(); for (int i = 0; i < n; i++) lmpc_global_to_frenet(T, g + 3 * i, f + 3 * i); }

@@ -44,6 +44,8 @@ def main():
         tracks[f"{name}_left"] = np.linalg.norm(p - t[:, 9:11], axis=1)
         tracks[f"{name}_right"] = -np.linalg.norm(p - t[:, 11:13], axis=1)
         tracks[f"{name}_length"] = np.array(t[0, 7] + t[0, 6])
+        # the raw table (TrajectoryIndex columns, racing_trajectory.hpp:37-56): input of the track-spline restatement
+        tracks[f"{name}_table"] = t
     np.savez_compressed(f"{OUT}/tracks.npz", **tracks)
     for k, v in tracks.items():
         if k.endswith("_length"):

@@ -299,3 +299,162 @@ def test_sqp_full_dynamics_matches_oracle(pkg, name, nb):
     assert n >= int(0.7 * nb), n
     assert worst < TOL, worst
     print(f"[{name}] SQP: {conv.sum()}/{nb} converged, mean {out['sqp_iters'][conv].mean():.1f} QP solves, worst rel err vs oracle {worst:.2e}")
+
+
+# ------------------------------------------------------------------ rows 8f #1 / #2: track, tick preparation, plant, closed loop
+def _track_table(name):
+    return np.ascontiguousarray(np.load(os.path.join(GOLD, "tracks.npz"))[f"{name}_table"], dtype=np.float64)
+
+
+def _loop_start(pkg, veh, otrk, o, laps, nb, N, dt, seed):
+    """agents start on samples of the newest recorded lap; previous solution = rollout of the recorded controls"""
+    import oracle_loop as OL
+    rng = np.random.default_rng(seed)
+    lap = laps[-1]
+    j0 = rng.integers(0, lap["x"].shape[0] - N - 1, nb)
+    x = lap["x"][j0] + rng.standard_normal((nb, 6)) * np.array([0.02, 0.01, 0.01, 0.02, 0.01, 0.02])
+    u_prev = lap["u"][j0].copy()
+    U_last = np.stack([lap["u"][j:j + N - 1] for j in j0])
+    X_last = np.zeros((nb, N, 6))
+    X_last[:, 0] = x
+    for b in range(nb):
+        for i in range(N - 1):
+            X_last[b, i + 1] = OL.step_on_track(o, otrk, X_last[b, i], U_last[b, i], dt)
+    return x, u_prev, X_last, U_last
+
+
+@pytest.mark.parametrize("name", ["barc_center", "putnam_optm"])
+def test_track_functions_on_device_match_oracle(pkg, name):
+    from oracle_track import OracleTrack
+    tb = _track_table(name)
+    m, *_ = _mpc(pkg, "barc_tracking", 8)
+    m.set_track(tb)
+    o = OracleTrack(tb)
+    L = o.L
+    assert m.track_length() == L
+    rng = np.random.default_rng(3)
+    s = np.concatenate([rng.uniform(-1.5 * L, 2.5 * L, 2000), [0.0, L, L / 2, -L, 2 * L]])
+    a, b = m.track_eval(s), o.eval(s)
+    scale = max(1.0, np.abs(tb[:, :2]).max())
+    for key, tol in (("left", 1e-10), ("right", 1e-10), ("vel", 1e-10), ("x", 1e-10 * scale), ("y", 1e-10 * scale), ("curvature", 1e-7)):
+        assert np.abs(a[key] - b[key]).max() < tol * max(1.0, np.abs(b[key]).max()), key
+    assert np.abs(np.sin(a["yaw"] - b["yaw"])).max() < 1e-8
+    hw = 0.3 if L < 100 else 3.0
+    f = np.column_stack([rng.uniform(0.01 * L, 0.99 * L, 500), rng.uniform(-hw, hw, 500), rng.uniform(-.5, .5, 500)])
+    g = m.frenet_to_global(f)
+    go = o.frenet_to_global(f)
+    assert np.abs(g[:, :2] - go[:, :2]).max() < 1e-9 * scale
+    f2 = m.global_to_frenet(g)                 # the reference's own test: the round trip is the identity
+    assert np.abs(f2[:, 0] - f[:, 0]).max() < 1e-7 * max(1.0, L / 100) and np.abs(f2[:, 1:] - f[:, 1:]).max() < 1e-7
+    fo = o.global_to_frenet(g[:32])
+    assert np.abs(fo - f2[:32]).max() < 1e-7 * max(1.0, L / 100)
+
+
+@pytest.mark.parametrize("mode", ["step", "continuous"])
+def test_tick_preparation_matches_oracle(pkg, laps, mode):
+    import torch
+    import oracle_loop as OL
+    from oracle_track import OracleTrack
+    tb = _track_table("barc_center")
+    m, veh, cfg, track, _ = _mpc(pkg, "barc_lmpc", 32)
+    o, *_ = make_oracle(pkg, "barc_lmpc")
+    m.set_track(tb)
+    otrk = OracleTrack(tb)
+    nb, N, dt = 32, cfg["N"], 0.025
+    x, u_prev, X_last, U_last = _loop_start(pkg, veh, otrk, o, laps, nb, N, dt, 4)
+    opt = m.loop_options(dt, step_mode=mode, speed_limit=2.0, speed_scale=0.9, max_vel_ref_diff=0.3)
+    od = dict(step_mode=mode, delay_step=0, plant_substeps=1, dt=dt, plant_dt=dt, speed_limit=2.0, speed_scale=0.9, max_vel_ref_diff=0.3)
+    dev = [torch.from_numpy(a).cuda() for a in (x, u_prev, X_last, U_last)]
+    out = m.prepare(opt, *dev)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        r = OL.prepare(o, otrk, od, x[b], u_prev[b], X_last[b], U_last[b])
+        for k in ("x_ic", "u_ic", "X_ref", "U_ref", "T_ref", "bound_left", "bound_right", "vel_ref"):
+            assert np.abs(out[k][b].cpu().numpy() - r[k]).max() < 1e-10, (k, b)
+        assert np.abs(out["curvatures"][b].cpu().numpy() - r["curvatures"]).max() < 1e-8
+        assert out["total_length"][b].item() == otrk.L
+    assert np.array_equal(out["U_ref"][:, -1].cpu().numpy(), U_last[:, -1]) and np.array_equal(out["U_ref"][:, -2].cpu().numpy(), U_last[:, -1])
+
+
+def test_closed_loop_matches_oracle(pkg, laps):
+    """prepare -> solve -> actuation -> plant for 12 ticks, GPU (one call, no host round trip) against the oracle's
+    plain-Python loop around its own QP, agent by agent."""
+    import oracle_loop as OL
+    from oracle_track import OracleTrack
+    tb = _track_table("barc_center")
+    m, veh, cfg, track, _ = _mpc(pkg, "barc_lmpc", 8, tol=1e-9)
+    o, *_ = make_oracle(pkg, "barc_lmpc", tol=1e-10)
+    m.set_track(tb)
+    otrk = OracleTrack(tb)
+    nb, N, dt, ticks = 8, cfg["N"], 0.025, 12
+    x, u_prev, X_last, U_last = _loop_start(pkg, veh, otrk, o, laps, nb, N, dt, 6)
+    opt = m.loop_options(dt, plant_dt=0.0125, plant_substeps=2)
+    od = dict(step_mode="step", delay_step=0, plant_substeps=2, dt=dt, plant_dt=0.0125, speed_limit=1e9, speed_scale=1.0, max_vel_ref_diff=1.0)
+    n0 = m.launch_count
+    out = m.closed_loop(opt, ticks, x, u_prev, X_last, U_last)
+    assert m.launch_count - n0 == 6 * ticks       # prepare, linearise, safe-set query, QP, plant, tick counter
+    worst = 0.0
+    for b in range(nb):
+        r = OL.closed_loop(o, otrk, od, ticks, x[b], u_prev[b], X_last[b], U_last[b])
+        assert r["fail_count"] == 0 and out["fail_count"][b] == 0
+        worst = max(worst, relerr(out["log_x"][:, b], r["log_x"]), relerr(out["log_u"][:, b], r["log_u"]),
+                    relerr(out["X_last"][b], r["X_last"]))
+        assert out["lap_count"][b] == r["lap_count"]
+    assert worst < TOL, worst
+    assert np.abs(out["log_x"][-1] - x).max() > 0.1          # the cars moved
+    print(f"closed loop, {nb} agents x {ticks} ticks: worst rel err vs oracle {worst:.2e}")
+
+
+def test_closed_loop_full_size_properties(pkg, laps):
+    """1024 agents x 40 ticks on the device (BASELINE configs[4]'s Monte-Carlo shape, one GPU's share reduced to the
+    config-2 batch): invariants on every agent, lap counter across the start line, determinism."""
+    import oracle_loop as OL
+    from oracle_track import OracleTrack
+    tb = _track_table("barc_center")
+    m, veh, cfg, track, _ = _mpc(pkg, "barc_lmpc", 1024)
+    o, *_ = make_oracle(pkg, "barc_lmpc")
+    m.set_track(tb)
+    otrk = OracleTrack(tb)
+    L = otrk.L
+    nb, N, dt, ticks = 1024, cfg["N"], 0.025, 40
+    x, u_prev, X_last, U_last = _loop_start(pkg, veh, otrk, o, laps, 64, N, dt, 8)
+    rep = nb // 64
+    rng = np.random.default_rng(9)
+    x = np.tile(x, (rep, 1)); u_prev = np.tile(u_prev, (rep, 1)); X_last = np.tile(X_last, (rep, 1, 1)); U_last = np.tile(U_last, (rep, 1, 1))
+    x[:, 1] += rng.standard_normal(nb) * 0.005; x[:, 3] += rng.standard_normal(nb) * 0.01       # perturbed agents
+    X_last[:, 0] = x
+    opt = m.loop_options(dt)
+    out = m.closed_loop(opt, ticks, x, u_prev, X_last, U_last)
+    assert (out["fail_count"] == 0).mean() > 0.98, np.bincount(out["fail_count"])
+    lx, lu = out["log_x"], out["log_u"]
+    assert np.isfinite(lx).all() and np.isfinite(lu).all()
+    assert (lx[:, :, 0] >= 0).all() and (lx[:, :, 0] <= L).all()                               # abscissa wrapped into [0, L]
+    ds = np.diff(np.concatenate([x[None, :, 0], lx[:, :, 0]]), axis=0)
+    wraps = (ds < -0.5 * L).sum(axis=0)
+    assert np.array_equal(wraps, out["lap_count"])                                             # the lap counter counts the wraps
+    assert ((ds > 0) | (ds < -0.5 * L)).all()                                                  # cars drive forward
+    ok = out["fail_count"] == 0
+    assert np.abs(lu[:, ok, 1]).max() <= cfg["u_max"][1] + 1e-9                                # published steering within its box
+    assert np.abs(lx[:, ok, 1]).max() < 0.6                                                    # on the track
+    out2 = m.closed_loop(opt, ticks, x, u_prev, X_last, U_last)
+    assert np.array_equal(out2["log_x"], lx)
+
+
+def test_closed_loop_and_sqp_match_golden_vectors(pkg, laps):
+    """The committed golden vectors of rows 8f #1/#2 (closed loop) and a12 (SQP), generated with the dense certified QP."""
+    z = np.load(os.path.join(GOLD, "golden_closed_loop_barc.npz"))
+    m, veh, cfg, track, _ = _mpc(pkg, "barc_lmpc", 8, tol=1e-9)
+    m.set_track(_track_table("barc_center"))
+    opt = m.loop_options(float(z["dt"]), plant_dt=float(z["plant_dt"]), plant_substeps=int(z["plant_substeps"]))
+    out = m.closed_loop(opt, int(z["ticks"]), z["x0"], z["u0"], z["X0"], z["U0"])
+    assert (out["fail_count"] == 0).all() and np.array_equal(out["lap_count"], z["lap_count"])
+    e = max(relerr(out["log_x"], z["log_x"]), relerr(out["log_u"], z["log_u"]), relerr(out["X_last"], z["X_last"]))
+    assert e < TOL, e
+    for name in ("barc_tracking", "iac_tracking"):
+        g = np.load(os.path.join(GOLD, f"golden_sqp_{name}.npz"))
+        batch = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+        ms, *_ = _mpc(pkg, name, 8)
+        o = ms.solve_sqp(batch, max_sqp_iter=80, tol=1e-10)
+        assert (o["status"] == 0).all() and (o["sqp_iters"] < 80).all()
+        e = max(relerr(o["X_optm"], g["out_X"]), relerr(o["U_optm"], g["out_U"]), relerr(o["dU_optm"], g["out_dU"]))
+        assert e < TOL, (name, e)
