@@ -47,7 +47,7 @@ struct lmpc_handle {
   DevBuf slab;
   std::vector<LmpcLapView> dev_laps;   // newest first, device pointers into the slab
   // device workspace
-  DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp;
+  DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp, ws_qpscr;
   // track interpolants (device copy of LmpcTrackHost) and closed-loop workspace
   LmpcTrackHost track_host;
   DevBuf track_dev, ws_loop, st_loop;
@@ -143,6 +143,7 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
   if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_cen, sizeof(double) * 6 * B);
   if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_ssx, sizeof(double) * 6 * K * B);
   if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_ssj, sizeof(double) * K * B);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_qpscr, sizeof(double) * (size_t)LMPC_QP_SCRATCH(N, K) * B);
   (void)N;
   if (rc != LMPC_OK) { lmpc_destroy(h); return rc; }
   *out = h;
@@ -153,7 +154,7 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
   for (auto& e : h->tev) cudaEventDestroy(e);
-  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
   return LMPC_OK;
@@ -578,6 +579,7 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   a.bl = io.din[5]; a.br = io.din[6]; a.vref = io.din[8]; a.ABg = abg; a.ssx = io.ssx; a.ssj = io.ssj; a.cen = cen;
   a.X = io.dout[0]; a.U = io.dout[1]; a.dU = io.dout[2]; a.lam = io.dout[3]; a.cost = io.dout[6];
   a.status = io.d_status; a.iters = io.d_iters; a.ss_count = *ss_count_io; a.B = B; a.skip = skip;
+  a.scratch = (double*)h->ws_qpscr.p;
   launch_qp(h, a);
   h->launches++;
   CK(cudaGetLastError());

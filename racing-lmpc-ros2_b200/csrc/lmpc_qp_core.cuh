@@ -125,7 +125,10 @@ struct LmpcQpIn {
   const double* ssj;     // K   raw cost-to-go J  (J - J[0] is formed here, racing_mpc.cpp:280)
   const double* cen;     // 6   centre for the columns (the query point X_ref[:, N-1])
   int ss_count;          // 0 => no safe set
+  double* scratch;       // LMPC_QP_SCRATCH(N, K) doubles of global memory: centred safe-set columns [K][6] (re-read where needed
+                         // instead of living in registers) and the iterate saved before the polish (read back only if it fails)
 };
+#define LMPC_QP_SCRATCH(N, K) (8 * (N) + 8 * (K) + 6 * LMPC_MAX_SS_PTS + 16)
 
 struct LmpcQpOut {
   double* X;       // N x 6
@@ -138,6 +141,11 @@ struct LmpcQpOut {
 };
 
 struct ArrK { double a[LMPC_KPL_MAX]; };
+// same access syntax as LaneVar<ArrK> -- v(lane).a[p] -- for per-column values that live in global scratch instead of
+// registers (element lane + NT p of a LMPC_MAX_SS_PTS-long array): the step buffers of the lambda block
+struct ScrCol { double* b; int stride; LMPC_HDM double& operator[](int p) const { return b[stride * p]; } };
+struct ScrLane { ScrCol a; };
+template <int NT> struct ScrK { double* base; LMPC_HDM ScrLane operator()(int lane) const { return ScrLane{ScrCol{base + lane, NT}}; } };
 struct ArrKx6 { double a[LMPC_KPL_MAX][6]; };
 struct ArrKi { int a[LMPC_KPL_MAX]; };
 
@@ -239,10 +247,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 
   // ---------------------------------------------------------------- initial slacks / multipliers, channel scales
   double th = th0, yth = mu0 / th0, dth = 0.0, dyth = 0.0, dtha = 0.0, dytha = 0.0;
-  LaneVar<ArrK, NT> lam, ylam, dla, dya, dlf, dyf, glam, omg_, sscv;   // lambda block (registers)
-  LaneVar<ArrKx6, NT> St;                                            // centred columns, compacted to the nh hull components
+  LaneVar<ArrK, NT> lam, ylam, omg_;   // lambda block: iterate and weights in registers ...
+  double* const SCRK = in.scratch + 6 * P.K + 8 * P.N + 2 * P.K;
+  const ScrK<NT> dla{SCRK}, dya{SCRK + LMPC_MAX_SS_PTS}, dlf{SCRK + 2 * LMPC_MAX_SS_PTS}, dyf{SCRK + 3 * LMPC_MAX_SS_PTS},
+      glam{SCRK + 4 * LMPC_MAX_SS_PTS}, sscv{SCRK + 5 * LMPC_MAX_SS_PTS};   // ... steps, gradient, cost-to-go in global scratch
+  double* const chs_ = SCRK + 6 * LMPC_MAX_SS_PTS;   // [10] channel scales (uniform reads)
   LaneVar<ArrKi, NT> isB;
-  double R0, chs_[10];
+  double* const ST = in.scratch;   // [K][6] centred columns, compacted to the nh hull components (global memory; L2-resident)
+  double R0;
   int m_total = 0;
   {
     LaneVar<double, NT> r[12];
@@ -263,7 +275,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         dla(lane).a[p] = 0.0; dya(lane).a[p] = 0.0; dlf(lane).a[p] = 0.0; dyf(lane).a[p] = 0.0;
         glam(lane).a[p] = 0.0; omg_(lane).a[p] = 0.0; isB(lane).a[p] = 0;
         sscv(lane).a[p] = on ? in.ssj[k] - j0 : 0.0;
-        for (int a = 0; a < 6; a++) St(lane).a[p][a] = (on && a < nh) ? in.ssx[6 * k + P.hidx[a]] - in.cen[P.hidx[a]] : 0.0;
+        if (on) for (int a = 0; a < 6; a++) ST[6 * k + a] = (a < nh) ? in.ssx[6 * k + P.hidx[a]] - in.cen[P.hidx[a]] : 0.0;
         if (on) r0 = fmax(r0, fabs(sscv(lane).a[p]));
       }
       double m[10] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
@@ -296,11 +308,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   int polishing = 0, polish_tries = 0, classified = 0;
   double tol_step = P.tol, tol_mu = 0.1 * P.tol;   // complementarity level at which the polish takes over
   int numfail_polish = 0;
-  struct XuSave { double v[(LMPC_MAX_N + NT - 1) / NT][8]; };
-  LaneVar<XuSave, NT> xus_;                    // saved iterate of this lane's stages (restored if the polish fails)
+  double* const SAVE_XU = in.scratch + 6 * P.K;          // [N][8] saved iterate (restored if the polish fails); global memory, not registers
+  double* const SAVE_L = in.scratch + 6 * P.K + 8 * N;   // [K] lambda, [K] its multiplier
   double th_save = 0.0, yth_save = 0.0;
   int pact_th = 0;
-  LaneVar<ArrK, NT> lsave, ylsave;
   LaneVar<ArrKi, NT> pnb;
 
   // ================================================================ interior-point iterations
@@ -316,9 +327,9 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           RSi[q.slot * d + i] = y;
           if (y > s) RSs[q.slot * d + i] = -s; else RSy[q.slot * d + i] = 0.0;
         }
-        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) xus_(lane).v[sidx][c] = X[c * d + i]; for (int c = 0; c < 2; c++) xus_(lane).v[sidx][6 + c] = (i < NS) ? U[c * d + i] : 0.0; sidx++; } }
+        FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) SAVE_XU[8 * i + c] = X[c * d + i]; for (int c = 0; c < 2; c++) SAVE_XU[8 * i + 6 + c] = (i < NS) ? U[c * d + i] : 0.0; }
         for (int p = 0; p < KPL; p++) {
-          lsave(lane).a[p] = lam(lane).a[p]; ylsave(lane).a[p] = ylam(lane).a[p];
+          if (lane + NT * p < K) { SAVE_L[lane + NT * p] = lam(lane).a[p]; SAVE_L[K + lane + NT * p] = ylam(lane).a[p]; }
           const bool basic = lam(lane).a[p] >= ylam(lane).a[p];
           pnb(lane).a[p] = basic ? 0 : 1;
           if (basic) ylam(lane).a[p] = 0.0;
@@ -372,7 +383,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         if (!pass) for (int p = 0; p < KPL; p++) {
           const double l = lam(lane).a[p];
           msum += l * ylam(lane).a[p]; lsum += l;
-          for (int a = 0; a < 6; a++) sg6[a] += St(lane).a[p][a] * l;
+          if (lane + NT * p < K) for (int a = 0; a < 6; a++) sg6[a] += ST[6 * (lane + NT * p) + a] * l;
           if (polishing && lane + NT * p < K && !pnb(lane).a[p]) nbasic += 1.0;
         }
         rs[0](lane) = dth_acc; rs[1](lane) = cth_acc; rs[2](lane) = msum; rs[3](lane) = rpm; rs[4](lane) = lsum;
@@ -441,7 +452,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
             GLANES_BEGIN(NT)
               for (int p = 0; p < KPL; p++) if (lane + NT * p == kb) {
                 isB(lane).a[p] = 1 + q;
-                for (int a = 0; a < 6; a++) TB[TB_BCOL + 6 * q + a] = St(lane).a[p][a];
+                for (int a = 0; a < 6; a++) TB[TB_BCOL + 6 * q + a] = ST[6 * kb + a];
                 TB[TB_BD + q] = polishing ? (pnb(lane).a[p] ? LMPC_PRHO : 0.0) : ylam(lane).a[p] / lam(lane).a[p];
               }
             GLANES_END(NW)
@@ -469,12 +480,15 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               else {
                 const double om = omg_(lane).a[p];
                 og += om * gl; om1 += om;
+                double sv[6];
+#pragma unroll
+                for (int a = 0; a < 6; a++) sv[a] = ST[6 * k + a];
 #pragma unroll
                 for (int a = 0, q = 0; a < 6; a++) {
-                  const double sa = St(lane).a[p][a];
+                  const double sa = sv[a];
                   bv6[a] += sa * om * gl; av[a] += sa * om;
 #pragma unroll
-                  for (int b = 0; b <= a; b++, q++) W[q] += om * sa * St(lane).a[p][b];
+                  for (int b = 0; b <= a; b++, q++) W[q] += om * sa * sv[b];
                 }
               }
             }
@@ -916,7 +930,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               } else {
                 double se = 0.0;
 #pragma unroll
-                for (int a = 0; a < 6; a++) se += St(lane).a[p][a] * e[a];
+                for (int a = 0; a < 6; a++) se += ST[6 * k + a] * e[a];
                 dl = omg_(lane).a[p] * (se - glam(lane).a[p] - nu);
               }
               const double dy = tl - y - dl * (y / l);
@@ -1058,8 +1072,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const double s = fabs(RSs[q.slot * d + i]), y = RSi[q.slot * d + i];
           RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
         }
-        { int sidx = 0; FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = xus_(lane).v[sidx][c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = xus_(lane).v[sidx][6 + c]; sidx++; } }
-        for (int p = 0; p < KPL; p++) { lam(lane).a[p] = lsave(lane).a[p]; ylam(lane).a[p] = ylsave(lane).a[p]; }
+        FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = SAVE_XU[8 * i + c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = SAVE_XU[8 * i + 6 + c]; }
+        for (int p = 0; p < KPL; p++) if (lane + NT * p < K) { lam(lane).a[p] = SAVE_L[lane + NT * p]; ylam(lane).a[p] = SAVE_L[K + lane + NT * p]; }
       GLANES_END(NW)
       th = th_save; yth = yth_save;
       polishing = 0; classified = 0;
@@ -1156,7 +1170,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       if (k < K) {
         const double l = lam(lane).a[p];
         cst += sscv(lane).a[p] * l;
-        for (int a = 0; a < 6; a++) sg[a] += St(lane).a[p][a] * l;
+        for (int a = 0; a < 6; a++) sg[a] += ST[6 * k + a] * l;
       }
       if (out.lam && k < P.K) out.lam[k] = (k < K) ? fmax(lam(lane).a[p], 0.0) : 0.0;   // polished non-basic columns sit at -y/rho ~ 1e-20
     }

@@ -7,6 +7,7 @@
 struct LmpcQpBatch {
   const double *x_ic, *u_ic, *U0, *T_ref, *bl, *br, *vref, *ABg, *ssx, *ssj, *cen;
   double *X, *U, *dU, *lam, *cost;
+  double* scratch;   // [B][LMPC_QP_SCRATCH(N, K)] workspace
   int *status, *iters;
   int ss_count;
   int B;
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
   in.ssx = P.learning ? a.ssx + (6 * (size_t)K) * b : nullptr;
   in.ssj = P.learning ? a.ssj + (size_t)K * b : nullptr;
   in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count;
+  in.scratch = a.scratch + (size_t)LMPC_QP_SCRATCH(N, K) * b;
   LmpcQpOut out;
   out.X = a.X + (6 * (size_t)N) * b; out.U = a.U + (2 * (size_t)NS) * b; out.dU = a.dU + (2 * (size_t)NS) * b;
   out.lam = (a.lam && P.learning) ? a.lam + (size_t)K * b : nullptr;

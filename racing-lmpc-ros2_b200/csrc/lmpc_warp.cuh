@@ -20,6 +20,7 @@
 // ------------------------------------------------------------------ lane-loop emulation (tests)
 #define LMPC_DEV static inline
 #define LMPC_HD static inline
+#define LMPC_HDM inline   // member functions
 extern int g_lmpc_emu_reverse;  // run lanes NT-1..0 instead of 0..NT-1 (order-independence check)
 #define GLANES_BEGIN(NT)                                      \
   for (int lane_it_ = 0; lane_it_ < (NT); ++lane_it_) {       \
@@ -37,6 +38,7 @@ struct LaneVar {
 // ------------------------------------------------------------------ CUDA
 #define LMPC_DEV __device__ __forceinline__
 #define LMPC_HD __host__ __device__ __forceinline__
+#define LMPC_HDM __host__ __device__ __forceinline__
 #define GROUP_SYNC(NW)                       \
   do {                                       \
     if ((NW) == 1) __syncwarp(); else __syncthreads(); \

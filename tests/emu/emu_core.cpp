@@ -35,7 +35,8 @@ extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params*
   if (rc != LMPC_OK) return rc;
   if (smem_doubles) *smem_doubles = P.lay.total;
   std::vector<double> sm((size_t)P.lay.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
-  LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssj_raw, cen, ss_count};
+  std::vector<double> scr((size_t)LMPC_QP_SCRATCH(P.N, P.K > 0 ? P.K : 1), 0.0 / 0.0);
+  LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssj_raw, cen, ss_count, scr.data()};
   LmpcQpOut out = {X, U, dU, lam, cost, status, iters};
   const int kpl = (P.K + 32 * nw - 1) / (32 * nw);
   const bool fixed = (nw & 0x100) == 0 && P.RS == 16 && (P.N == 20 || P.N == 40);   // same rule as the C ABI
