@@ -19,6 +19,10 @@
  *   lmpc_safe_set_add_lap               SafeSetManager::add_lap(x,u,k,t,total_length)   safe_set.hpp:119-121
  *   lmpc_safe_set_load                  SafeSetRecorder::load(from_files,total_length)  safe_set.cpp:260-276
  *   lmpc_safe_set_query_batch           SafeSetManager::query(const SSQuery&) -> SSResult  safe_set.cpp:153-180
+ *   lmpc_safe_set_regress_batch         SafeSetManager::query(const RegQuery&) -> RegResult  safe_set.cpp:56-114,182-245
+ *   lmpc_set_error_dynamics             (the same regression applied to every stage's A, B, g inside the tick)
+ *   lmpc_recorder_step / _config        SafeSetRecorder::step / SafeSetRecorder(manager, to_file, prefix)
+ *                                       safe_set.cpp:246-258,278-322 (called from RacingMPC::solve, racing_mpc.cpp:245-246)
  *   lmpc_track_set / _load / _eval_batch RacingTrajectory and its interpolation functions  racing_trajectory.cpp:25-119
  *   lmpc_frenet_to_global_batch,        RacingTrajectory::frenet_to_global / global_to_frenet
  *   lmpc_global_to_frenet_batch           racing_trajectory.cpp:121-236
@@ -163,6 +167,44 @@ int lmpc_safe_set_num_laps(const lmpc_handle* h);
  * Columns beyond count[b] are left untouched. */
 int lmpc_safe_set_query_batch(lmpc_handle* h, int B, const double* query_s_ey /*[B][2]*/, int max_total,
                               int max_per_lap, double* ss_x, double* ss_j, int32_t* count, int memspace);
+
+/* ---- lap recorder (SafeSetRecorder, safe_set.cpp:246-258,278-322): host-side segmentation of a stream of ticks into
+ *      laps.  RacingMPC::solve feeds it (x_ic, u_ic, curvatures[0], t_ic) every tick (racing_mpc.cpp:245-246).  A lap
+ *      ends when the abscissa drops by more than half the track length (:290); the samples before the first wrap are
+ *      discarded (:293-309); a completed lap goes to lmpc_safe_set_add_lap and, with to_file, to
+ *      <prefix>lap_<k>_{x,u,t,k}.txt ("%.16e", one sample per line: what lmpc_safe_set_load reads back). ---- */
+int lmpc_recorder_config(lmpc_handle* h, int to_file, const char* file_prefix);
+/* lap_added (optional): set to 1 when this sample closed a lap that was added to the safe set */
+int lmpc_recorder_step(lmpc_handle* h, const double* x /*[6]*/, const double* u /*[2]*/, double k, double t,
+                       double total_length, int32_t* lap_added);
+int lmpc_recorder_lap_count(const lmpc_handle* h);   /* SafeSetRecorder::lap_count_ */
+
+/* ---- error-dynamics regression over the stored laps (RegQuery / RegResult, safe_set.hpp:61-88;
+ *      SSTrajectory::query(RegQuery) safe_set.cpp:56-114; SafeSetManager::query(RegQuery) :182-245).
+ *      One regression per output state: local weighted ridge regression of the one-step model error on
+ *      (x[in_x], u[in_u], 1) over the stored samples within dist_max of the query, added to the nominal A, B, C.
+ *      The reference never calls this function and it cannot run as written (csrc/lmpc_reg_core.cuh lists the
+ *      deviations); `sign` = -1 reproduces b = -M'Ky as written (:229), +1 adds the error model (LMPC paper). ---- */
+#define LMPC_REG_MAX_OUT 6
+typedef struct lmpc_reg_spec {
+  int32_t n_out;                           /* number of regressions = reg_out_state_idxs.size() */
+  int32_t out_idx[LMPC_REG_MAX_OUT];       /* reg_out_state_idxs[r][0] (exactly one per regression, :63-65) */
+  int32_t n_in_x[LMPC_REG_MAX_OUT];        /* reg_in_state_idxs[r] */
+  int32_t in_x[LMPC_REG_MAX_OUT][LMPC_NX];
+  int32_t n_in_u[LMPC_REG_MAX_OUT];        /* reg_in_control_idxs[r] */
+  int32_t in_u[LMPC_REG_MAX_OUT][LMPC_NU];
+  double dist_max;                         /* RegQuery::dist_max = the kernel bandwidth h */
+  double ridge;                            /* 1e-3 (:228) */
+  double sign;                             /* see above */
+} lmpc_reg_spec;
+/* n query items: xq [n][6], uq [n][2]; A [n][36] / B [n][12] (column-major per item) and C [n][6] hold the nominal
+ * model on entry and the corrected one on return.  npts (optional) [n][n_out]: samples within dist_max. */
+int lmpc_safe_set_regress_batch(lmpc_handle* h, int n, const lmpc_reg_spec* spec, const double* xq, const double* uq,
+                                double* A, double* Bm, double* C, int32_t* npts, int memspace);
+/* Enables (spec != NULL) or disables (NULL) the regression inside lmpc_solve_batch / lmpc_solve_sqp_batch /
+ * lmpc_closed_loop_run: after the linearisation every stage's (A, B, g) is corrected at its linearisation point
+ * (abscissa-aligned X_ref_i, U_ref_i); g takes the affine term.  One more kernel per tick. */
+int lmpc_set_error_dynamics(lmpc_handle* h, const lmpc_reg_spec* spec);
 
 /* ---- vehicle model ---- */
 int lmpc_discrete_dynamics_batch(lmpc_handle* h, int n, const double* x, const double* u,

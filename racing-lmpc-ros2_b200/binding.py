@@ -56,6 +56,28 @@ class LoopOptions(C.Structure):
                 ("max_vel_ref_diff", C.c_double)]
 
 
+class RegSpec(C.Structure):
+    _fields_ = [("n_out", C.c_int32), ("out_idx", C.c_int32 * 6), ("n_in_x", C.c_int32 * 6), ("in_x", (C.c_int32 * 6) * 6),
+                ("n_in_u", C.c_int32 * 6), ("in_u", (C.c_int32 * 2) * 6), ("dist_max", C.c_double), ("ridge", C.c_double),
+                ("sign", C.c_double)]
+
+
+def make_reg_spec(out_idx, in_x, in_u, dist_max, ridge=1e-3, sign=1.0):
+    """RegQuery's index lists (safe_set.hpp:61-76): out_idx[r] the output state of regression r, in_x[r] / in_u[r] its
+    input states / controls."""
+    sp = RegSpec()
+    sp.n_out = len(out_idx)
+    for r, o in enumerate(out_idx):
+        sp.out_idx[r] = int(o)
+        sp.n_in_x[r] = len(in_x[r]); sp.n_in_u[r] = len(in_u[r])
+        for q, c in enumerate(in_x[r]):
+            sp.in_x[r][q] = int(c)
+        for q, c in enumerate(in_u[r]):
+            sp.in_u[r][q] = int(c)
+    sp.dist_max = float(dist_max); sp.ridge = float(ridge); sp.sign = float(sign)
+    return sp
+
+
 def fill_struct(st, d):
     for name, _ in st._fields_:
         if name not in d:
@@ -78,6 +100,7 @@ EXPORTS = [
     "lmpc_set_timing", "lmpc_get_kernel_ms", "lmpc_measure_fp64_peak",
     "lmpc_track_set", "lmpc_track_load", "lmpc_track_total_length", "lmpc_track_eval_batch",
     "lmpc_frenet_to_global_batch", "lmpc_global_to_frenet_batch", "lmpc_closed_loop_run", "lmpc_prepare_batch",
+    "lmpc_recorder_config", "lmpc_recorder_step", "lmpc_recorder_lap_count", "lmpc_safe_set_regress_batch", "lmpc_set_error_dynamics",
 ]
 
 _lib = None
@@ -126,6 +149,11 @@ def load_library(path=None):
     L.lmpc_global_to_frenet_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int]
     L.lmpc_closed_loop_run.argtypes = [vp, C.c_int, C.c_int, C.POINTER(LoopOptions)] + [vp] * 8 + [C.c_int]
     L.lmpc_prepare_batch.argtypes = [vp, C.c_int, C.POINTER(LoopOptions)] + [vp] * 14
+    L.lmpc_recorder_config.argtypes = [vp, C.c_int, C.c_char_p]
+    L.lmpc_recorder_step.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double, vp]
+    L.lmpc_recorder_lap_count.argtypes = [vp]
+    L.lmpc_safe_set_regress_batch.argtypes = [vp, C.c_int, C.POINTER(RegSpec), vp, vp, vp, vp, vp, vp, C.c_int]
+    L.lmpc_set_error_dynamics.argtypes = [vp, C.POINTER(RegSpec)]
     if path is None:
         _lib = L
     return L

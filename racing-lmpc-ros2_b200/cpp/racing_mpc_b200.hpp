@@ -51,6 +51,10 @@ using StatsDict = std::map<std::string, double>;
 
 struct RacingMPCConfig {   // racing_mpc_config.hpp:37-82 (fields read by the solve path)
   lmpc_mpc_config c{};
+  bool record = false;                  // :76-77  SafeSetRecorder(to_file = record, file_prefix = path_prefix)
+  std::string path_prefix;
+  bool load = false;                    // :79-80  laps loaded on the first solve (racing_mpc.cpp:240-243)
+  std::vector<std::string> load_path;
   typedef std::shared_ptr<RacingMPCConfig> SharedPtr;
 };
 
@@ -67,10 +71,12 @@ class RacingMPC {
 
   RacingMPC(RacingMPCConfig::SharedPtr config, SingleTrackPlanarModel::SharedPtr model, const bool& full_dynamics = false,
             int device = 0, int max_batch = 1)
-      : config_(config), model_(model), max_batch_(max_batch) {
-    if (full_dynamics) throw std::invalid_argument("full_dynamics (IPOPT) mode is not provided by the B200 path");
+      : config_(config), model_(model), max_batch_(max_batch), full_dynamics_(full_dynamics) {
+    // full_dynamics: the nonlinear-equality problem the reference gives to IPOPT (racing_mpc.cpp:67-84) is solved by
+    // SQP on the tick's kernels (lmpc_solve_sqp_batch)
     const int rc = lmpc_create(&config_->c, &model_->p, device, max_batch, &h_);
     if (rc != LMPC_OK) throw std::runtime_error(std::string("lmpc_create: ") + lmpc_status_string(rc));
+    check(lmpc_recorder_config(h_, config_->record ? 1 : 0, config_->path_prefix.c_str()), "recorder_config");   // racing_mpc.cpp:59-61
   }
   ~RacingMPC() { if (h_) lmpc_destroy(h_); }
   RacingMPC(const RacingMPC&) = delete;
@@ -94,7 +100,7 @@ class RacingMPC {
     const Matrix& L = in.at("total_length");
     const Matrix& x_ic = in.at("x_ic");
     const Matrix& u_ic = in.at("u_ic");
-    (void)in.at("t_ic");                                   // read by the reference (recorder), required key
+    const Matrix& t_ic = in.at("t_ic");
     const Matrix& X_ref = in.at("X_ref");
     const Matrix& U_ref = in.at("U_ref");
     const Matrix& bl = in.at("bound_left");
@@ -111,6 +117,9 @@ class RacingMPC {
       if (!solved_) throw std::runtime_error("No warm start given and no previous solution found.");   // :312-314
       T = &in.at("T_ref");
     }
+    if (!ss_loaded_ && config_->load) { load_laps(config_->load_path, L.data[0]); ss_loaded_ = true; }   // racing_mpc.cpp:240-243
+    // add current state to safe set (racing_mpc.cpp:245-246): lap segmentation, completed laps join the device slab
+    check(lmpc_recorder_step(h_, x_ic.data.data(), u_ic.data.data(), kap.data[0], t_ic.data[0], L.data[0], nullptr), "recorder_step");
     lmpc_batch_in bi{};
     bi.x_ic = x_ic.data.data(); bi.u_ic = u_ic.data.data(); bi.X_ref = X_ref.data.data(); bi.U_ref = U_ref.data.data();
     bi.T_ref = T->data.data(); bi.bound_left = bl.data.data(); bi.bound_right = br.data.data();
@@ -123,7 +132,8 @@ class RacingMPC {
     bo.X_optm = X.data.data(); bo.U_optm = U.data.data(); bo.dU_optm = dU.data.data();
     bo.convex_combi_optm = lam.data.data(); bo.ss_x = ssx.data.data(); bo.ss_j = ssj.data.data();
     bo.cost = &cost; bo.status = &status; bo.iters = &iters;
-    check(lmpc_solve_batch(h_, 1, &bi, &bo, LMPC_MEM_HOST), "solve_batch");
+    if (full_dynamics_) check(lmpc_solve_sqp_batch(h_, 1, &bi, &bo, 30, 1e-9, nullptr, nullptr, LMPC_MEM_HOST), "solve_sqp_batch");
+    else check(lmpc_solve_batch(h_, 1, &bi, &bo, LMPC_MEM_HOST), "solve_batch");
     if (config_->c.learning) { out["ss_x"] = ssx; out["ss_j"] = ssj; }            // racing_mpc.cpp:256-257
     stats["iter_count"] = iters;
     stats["status"] = status;
@@ -165,6 +175,8 @@ class RacingMPC {
   SingleTrackPlanarModel::SharedPtr model_;
   lmpc_handle* h_ = nullptr;
   int max_batch_ = 1;
+  bool full_dynamics_ = false;
+  bool ss_loaded_ = false;
   bool solved_ = false;
   bool have_last_ = false;
   Matrix last_U_;

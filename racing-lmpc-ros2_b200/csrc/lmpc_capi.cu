@@ -23,6 +23,16 @@ struct HostLap {
   int n;
   std::vector<double> ps, pe, xr, J;
   std::vector<int> canon;
+  std::vector<double> x, u, k, t;   // the lap as given (regression points; u/k/t empty if the caller passed none)
+};
+
+// SafeSetRecorder state (safe_set.hpp:127-150)
+struct Recorder {
+  bool last_x_valid = false, initialized = false, to_file = false;
+  std::string prefix;
+  int lap_count = 0;
+  double last_px = 0.0;
+  std::vector<double> x, u, k, t;
 };
 
 struct DevBuf {
@@ -48,6 +58,13 @@ struct lmpc_handle {
   std::vector<LmpcLapView> dev_laps;   // newest first, device pointers into the slab
   // device workspace
   DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp, ws_qpscr;
+  // error-dynamics regression: points of all laps (built lazily after a safe-set change), optional in-tick plan
+  DevBuf reg_slab, ws_reg;
+  LmpcRegView reg_view{nullptr, nullptr, 0};
+  bool reg_dirty = true;
+  bool reg_in_tick = false;
+  LmpcRegPlan reg_plan{};
+  Recorder rec;
   // track interpolants (device copy of LmpcTrackHost) and closed-loop workspace
   LmpcTrackHost track_host;
   DevBuf track_dev, ws_loop, st_loop;
@@ -154,7 +171,7 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
   for (auto& e : h->tev) cudaEventDestroy(e);
-  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->reg_slab, &h->ws_reg, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
   return LMPC_OK;
@@ -281,10 +298,11 @@ static int upload_safe_set(lmpc_handle* h) {
 
 extern "C" int lmpc_safe_set_add_lap(lmpc_handle* h, int n, const double* x, const double* u, const double* k,
                                      const double* t, double L) {
-  (void)u; (void)k; (void)t;   // kept for signature parity; only the (uncalled) regression query reads them
   if (!h || n < 1 || !x) return LMPC_ERR_INVALID;
   HostLap lap;
   lap.n = n;
+  lap.x.assign(x, x + 6 * (size_t)n);   // u, k, t are read by the error-dynamics regression only
+  if (u && k && t) { lap.u.assign(u, u + 2 * (size_t)n); lap.k.assign(k, k + n); lap.t.assign(t, t + n); }
   const size_t m = 3 * (size_t)n;
   lap.ps.resize(m); lap.pe.resize(m); lap.J.resize(m); lap.xr.resize(6 * m); lap.canon.resize(m);
   // SSTrajectory::process_lap_data (safe_set.cpp:116-137): x_repeat = [x - L e0, x, x + L e0],
@@ -313,6 +331,7 @@ extern "C" int lmpc_safe_set_add_lap(lmpc_handle* h, int n, const double* x, con
   const size_t cap = (size_t)std::max(h->cfg.max_lap_stored, 1);
   if (h->laps.size() == cap) h->laps.erase(h->laps.begin());   // circular_buffer::push_back overwrites the oldest
   h->laps.push_back(std::move(lap));
+  h->reg_dirty = true;
   return upload_safe_set(h);
 }
 
@@ -345,10 +364,151 @@ extern "C" int lmpc_safe_set_clear(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   h->laps.clear();
   h->dev_laps.clear();
+  h->reg_dirty = true;
   return LMPC_OK;
 }
 
 extern "C" int lmpc_safe_set_num_laps(const lmpc_handle* h) { return h ? (int)h->laps.size() : 0; }
+
+// ------------------------------------------------------------------------------------------ lap recorder
+extern "C" int lmpc_recorder_config(lmpc_handle* h, int to_file, const char* file_prefix) {
+  if (!h || (to_file && !file_prefix)) return LMPC_ERR_INVALID;
+  h->rec.to_file = to_file != 0;
+  h->rec.prefix = file_prefix ? file_prefix : "";
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_recorder_lap_count(const lmpc_handle* h) { return h ? h->rec.lap_count : 0; }
+
+static bool write_matrix(const std::string& path, const std::vector<double>& v, int cols) {
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) return false;
+  for (size_t i = 0; i < v.size(); i++) fprintf(f, "%.16e%c", v[i], ((i + 1) % (size_t)cols) ? ' ' : '\n');
+  return fclose(f) == 0;
+}
+
+// SafeSetRecorder::step (safe_set.cpp:278-322)
+extern "C" int lmpc_recorder_step(lmpc_handle* h, const double* x, const double* u, double k, double t, double L, int32_t* lap_added) {
+  if (!h || !x || !u) return LMPC_ERR_INVALID;
+  Recorder& r = h->rec;
+  if (lap_added) *lap_added = 0;
+  if (!r.last_x_valid) {   // :282-286 -- the very first sample only arms the wrap test
+    r.last_px = x[0]; r.last_x_valid = true;
+    return LMPC_OK;
+  }
+  int rc = LMPC_OK;
+  if (r.last_px - x[0] > 0.5 * L) {   // :290 new lap
+    if (r.initialized) {
+      const int n = (int)r.k.size();
+      rc = lmpc_safe_set_add_lap(h, n, r.x.data(), r.u.data(), r.k.data(), r.t.data(), L);
+      if (rc == LMPC_OK && lap_added) *lap_added = 1;
+      if (rc == LMPC_OK && r.to_file) {
+        const std::string fn = r.prefix + "lap_" + std::to_string(r.lap_count);
+        if (!write_matrix(fn + "_x.txt", r.x, 6) || !write_matrix(fn + "_u.txt", r.u, 2) || !write_matrix(fn + "_t.txt", r.t, 1) ||
+            !write_matrix(fn + "_k.txt", r.k, 1)) { h->err = "cannot write lap " + fn; rc = LMPC_ERR_IO; }
+      }
+    } else r.initialized = true;
+    r.lap_count++;
+    r.x.clear(); r.u.clear(); r.k.clear(); r.t.clear();
+  }
+  // samples recorded before the first wrap are never used (the reference keeps appending to them and drops them at
+  // the first wrap, :306-317); they are not stored here
+  if (r.initialized) {
+    r.x.insert(r.x.end(), x, x + 6); r.u.insert(r.u.end(), u, u + 2); r.k.push_back(k); r.t.push_back(t);
+  }
+  r.last_px = x[0];
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------ error-dynamics regression
+static int make_reg_plan(lmpc_handle* h, const lmpc_reg_spec* sp, LmpcRegPlan* plan) {
+  if (lmpc_make_reg_plan(sp, plan)) return LMPC_OK;
+  h->err = "regression spec rejected (1..6 regressions, indices in range, dist_max > 0, ridge > 0, sign = +-1)";
+  return LMPC_ERR_INVALID;
+}
+
+// points of all stored laps, oldest lap first (the order SafeSetManager::query concatenates them, safe_set.cpp:196-203)
+static int ensure_reg_slab(lmpc_handle* h) {
+  if (!h->reg_dirty) return LMPC_OK;
+  size_t M = 0;
+  for (const HostLap& l : h->laps) {
+    if (l.u.empty()) { h->err = "a stored lap has no u / k / t: the regression needs them"; return LMPC_ERR_INVALID; }
+    M += (size_t)(l.n - 1);
+  }
+  h->reg_view = LmpcRegView{nullptr, nullptr, 0};
+  if (M == 0) { h->reg_dirty = false; return LMPC_OK; }
+  // slab: Z [M][8] | E [M][6] | Xn [M][6] | kappa [M] | dt [M]   (the last three only feed the prepare kernel)
+  std::vector<double> hd(22 * M);
+  double* Z = hd.data(); double* Xn = Z + 14 * M; double* kp = Xn + 6 * M; double* dt = kp + M;
+  size_t p = 0;
+  for (const HostLap& l : h->laps)
+    for (int j = 0; j + 1 < l.n; j++, p++) {
+      for (int c = 0; c < 6; c++) { Z[8 * p + c] = l.x[6 * (size_t)j + c]; Xn[6 * p + c] = l.x[6 * (size_t)(j + 1) + c]; }
+      Z[8 * p + 6] = l.u[2 * (size_t)j]; Z[8 * p + 7] = l.u[2 * (size_t)j + 1];
+      kp[p] = l.k[j]; dt[p] = l.t[j + 1] - l.t[j];
+    }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));   // kernels in flight may still read the old slab
+  int rc = dev_reserve(h, h->reg_slab, sizeof(double) * 22 * M);
+  if (rc != LMPC_OK) return rc;
+  double* d = (double*)h->reg_slab.p;
+  CK(cudaMemcpyAsync(d, hd.data(), sizeof(double) * 22 * M, cudaMemcpyHostToDevice, h->stream));
+  const int threads = 128, blocks = (int)((M + threads - 1) / threads);
+  lmpc_reg_prepare_kernel<<<blocks, threads, 0, h->stream>>>(h->M, (int)M, d, d + 14 * M, d + 20 * M, d + 21 * M, d + 8 * M);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));   // hd is stack-scoped
+  h->reg_view = LmpcRegView{d, d + 8 * M, (int)M};
+  h->reg_dirty = false;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_set_error_dynamics(lmpc_handle* h, const lmpc_reg_spec* spec) {
+  if (!h) return LMPC_ERR_INVALID;
+  if (!spec) { h->reg_in_tick = false; return LMPC_OK; }
+  int rc = make_reg_plan(h, spec, &h->reg_plan);
+  if (rc != LMPC_OK) return rc;
+  h->reg_in_tick = true;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_safe_set_regress_batch(lmpc_handle* h, int n, const lmpc_reg_spec* spec, const double* xq, const double* uq,
+                                           double* A, double* Bm, double* C, int32_t* npts, int memspace) {
+  if (!h || n < 1 || !xq || !uq || !A || !Bm || !C) return LMPC_ERR_INVALID;
+  LmpcRegPlan plan;
+  int rc = make_reg_plan(h, spec, &plan);
+  if (rc == LMPC_OK) rc = ensure_reg_slab(h);
+  if (rc != LMPC_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  const size_t nz = (size_t)n;
+  const double *dxq = xq, *duq = uq; double *dA = A, *dB = Bm, *dC = C; int32_t* dn = npts;
+  if (memspace == LMPC_MEM_HOST) {
+    rc = dev_reserve(h, h->ws_reg, sizeof(double) * 62 * nz + sizeof(int32_t) * LMPC_REG_MAX_OUT * nz);
+    if (rc != LMPC_OK) return rc;
+    double* d = (double*)h->ws_reg.p;
+    double* q6 = d; double* q2 = d + 6 * nz; dA = d + 8 * nz; dB = dA + 36 * nz; dC = dB + 12 * nz; dn = npts ? (int32_t*)(dC + 6 * nz) : nullptr;
+    CK(cudaMemcpyAsync(q6, xq, sizeof(double) * 6 * nz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(q2, uq, sizeof(double) * 2 * nz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dA, A, sizeof(double) * 36 * nz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dB, Bm, sizeof(double) * 12 * nz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dC, C, sizeof(double) * 6 * nz, cudaMemcpyHostToDevice, h->stream));
+    dxq = q6; duq = q2;
+  }
+  if (h->reg_view.M > 0) {
+    const int threads = 128, blocks = (int)((nz * 32 + threads - 1) / threads);
+    lmpc_regress_items_kernel<<<blocks, threads, 0, h->stream>>>(plan, h->reg_view, n, dxq, duq, dA, dB, dC, dn);
+    h->launches++;
+    CK(cudaGetLastError());
+  } else if (dn) CK(cudaMemsetAsync(dn, 0, sizeof(int32_t) * (size_t)plan.n_out * nz, h->stream));
+  if (memspace == LMPC_MEM_HOST) {
+    CK(cudaMemcpyAsync(A, dA, sizeof(double) * 36 * nz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(Bm, dB, sizeof(double) * 12 * nz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(C, dC, sizeof(double) * 6 * nz, cudaMemcpyDeviceToHost, h->stream));
+    if (npts) CK(cudaMemcpyAsync(npts, dn, sizeof(int32_t) * (size_t)plan.n_out * nz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
 
 // newest -> oldest while num_total < max_total (safe_set.cpp:164); the columns a lap contributes and
 // where they land do not depend on the query
@@ -561,6 +721,17 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
                                                              first ? cen : nullptr, skip);
     h->launches++;
     CK(cudaGetLastError());
+  }
+  // KR: error-dynamics regression on every stage's (A, B, g) (optional, lmpc_set_error_dynamics)
+  if (h->reg_in_tick) {
+    int rc = ensure_reg_slab(h);
+    if (rc != LMPC_OK) return rc;
+    if (h->reg_view.M > 0) {
+      const int threads = 128, blocks = (int)(((size_t)B * NS * 32 + threads - 1) / threads);
+      lmpc_regress_kernel<<<blocks, threads, 0, h->stream>>>(h->reg_plan, h->reg_view, B, (int)N, io.din[0], X_lin, U_lin, io.din[9], abg, skip);
+      h->launches++;
+      CK(cudaGetLastError());
+    }
   }
   if (tev) CK(cudaEventRecord(tev[1], h->stream));
   // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272)

@@ -2,6 +2,7 @@
 //
 //   K1 lmpc_linearise_kernel   thread per (instance, stage): abscissa alignment + RK4 Jacobians -> A,B,g
 //   K2 lmpc_ss_query_kernel    warp per (instance, lap): exact k-NN in the safe-set slab + cost-to-go gather
+//   KR lmpc_regress_kernel     warp per (instance, stage): error-dynamics regression added to [A|B|g] (optional, between K1 and K3)
 //   K3 lmpc_qp_kernel          warp group (1, 2 or 4 warps = one CTA) per instance: interior-point / Riccati solve in shared memory
 //
 // Batch arrays are instance-major, so a warp's (or thread's) reads of its own instance are contiguous.
@@ -10,6 +11,7 @@
 #include "lmpc_model.cuh"
 #include "lmpc_qp_kernel.cuh"
 #include "lmpc_ss_core.cuh"
+#include "lmpc_reg_core.cuh"
 
 #define LMPC_MAX_LAPS_USED 64   // laps one query can draw from (the table travels as a kernel parameter, 3.6 KB)
 
@@ -164,4 +166,48 @@ __global__ void lmpc_sqp_defect_kernel(LmpcModel M, int B, int N, const double* 
     for (int c = 0; c < 6; c++) dmax = fmax(dmax, fabs(xn[c] - X[(6 * (size_t)N) * b + 6 * (i + 1) + c]));
   }
   defect[b] = dmax;
+}
+
+// ---- error-dynamics regression (lmpc_reg_core.cuh)
+// prepare: thread per stored sample p with a successor: E[p] = x_{p+1} - f_d(x_p, u_p, k_p, t_{p+1} - t_p)
+__global__ void lmpc_reg_prepare_kernel(LmpcModel M, int n, const double* __restrict__ Z, const double* __restrict__ Xn,
+                                        const double* __restrict__ kappa, const double* __restrict__ dt, double* __restrict__ E) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double xl[6], ul[2], xn[6];
+  for (int c = 0; c < 6; c++) xl[c] = Z[8 * (size_t)p + c];
+  ul[0] = Z[8 * (size_t)p + 6]; ul[1] = Z[8 * (size_t)p + 7];
+  lmpc_step(M, xl, ul, kappa[p], dt[p], xn);
+  for (int c = 0; c < 6; c++) E[6 * (size_t)p + c] = Xn[6 * (size_t)p + c] - xn[c];
+}
+
+// KR, generic form (the C ABI's lmpc_safe_set_regress_batch): warp per item; xq [n][6], uq [n][2]; A [n][36], B [n][12], C [n][6]
+__global__ void lmpc_regress_items_kernel(LmpcRegPlan plan, LmpcRegView v, int n, const double* __restrict__ xq,
+                                          const double* __restrict__ uq, double* __restrict__ A, double* __restrict__ Bm,
+                                          double* __restrict__ C, int* __restrict__ npts) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n) return;
+  double zq[8];
+  for (int c = 0; c < 6; c++) zq[c] = xq[6 * (size_t)w + c];
+  zq[6] = uq[2 * (size_t)w]; zq[7] = uq[2 * (size_t)w + 1];
+  lmpc_regress_warp(plan, v, zq, A + 36 * (size_t)w, Bm + 12 * (size_t)w, C + 6 * (size_t)w, npts ? npts + (size_t)plan.n_out * w : nullptr);
+}
+
+// KR, solve path: warp per (instance b, stage i), query at the linearisation point (abscissa-aligned X_ref_i, U_ref_i),
+// [A|B|g] of the stage updated in place (g takes the affine term C)
+__global__ void lmpc_regress_kernel(LmpcRegPlan plan, LmpcRegView v, int B, int N, const double* __restrict__ x_ic,
+                                    const double* __restrict__ X_ref, const double* __restrict__ U_ref,
+                                    const double* __restrict__ total_length, double* __restrict__ ABg, const int* __restrict__ skip) {
+  const int NS = N - 1;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= B * NS) return;
+  const int b = w / NS, i = w - b * NS;
+  if (skip && skip[b]) return;
+  double zq[8];
+  const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
+  for (int c = 0; c < 6; c++) zq[c] = xr[c];
+  zq[0] = lmpc_align_abscissa(zq[0], x_ic[6 * (size_t)b], total_length[b]);
+  zq[6] = U_ref[(2 * (size_t)NS) * b + 2 * i]; zq[7] = U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
+  double* o = ABg + (54 * (size_t)NS) * b + 54 * i;
+  lmpc_regress_warp(plan, v, zq, o, o + 36, o + 48, nullptr);
 }

@@ -43,7 +43,7 @@
 // constexpr so that the kernels instantiated for the named horizons fold every address into an immediate.
 struct LmpcLayout {
   int oABG, oS, oY, oISY, oX, oU, oDXA, oDUA, oDXF, oDUF, oCZX, oCZTH, oGUD, oFAC, oKFF, oBL, oBR, oVREF, oIT,
-      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, total;
+      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, oMBAR, total;
 };
 #define LMPC_MAX_ROWS 22   // 6 x 2 state boxes + 2 boundary + 4 control boxes + 4 rate boxes
 #define LMPC_ROWS_DOUBLES (5 * LMPC_MAX_ROWS + 6)   // RowDesc[LMPC_MAX_ROWS] (40 B each) + row_begin[11] (+ pad)
@@ -65,6 +65,7 @@ LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
   L.oRED = o; o += lmpc_even(NW > 1 ? NW * LMPC_NRED : 0);
   L.oTERM = o; o += lmpc_even(LMPC_TB_SIZE_);
   L.oROWS = o; o += lmpc_even(LMPC_ROWS_DOUBLES);   // row table (copied from the parameters: constant-bank indexing is slow)
+  L.oMBAR = o; o += 2;   // mbarrier of the bulk stage-in of [A|B|g]
   L.total = o;
   return L;
 }
@@ -205,8 +206,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   const double sfloor = 1e-2, mu0 = 0.1, th0 = 0.01;
 
   // ---------------------------------------------------------------- load
+  // [A|B|g] of all stages (54 (N-1) doubles, contiguous per instance): one bulk asynchronous copy (TMA) that lands while
+  // the group stages the small inputs below
+  group_bulk_load_begin(ABG, in.ABg, 54 * NS, sm + LO(oMBAR));
   GLANES_BEGIN(NT)
-    for (int idx = lane; idx < 54 * NS; idx += NT) ABG[idx] = in.ABg[idx];
     for (int idx = lane; idx < 5 * LMPC_MAX_ROWS; idx += NT) (sm + LO(oROWS))[idx] = reinterpret_cast<const double*>(P.rows)[idx];
     for (int idx = lane; idx < 11; idx += NT) reinterpret_cast<int*>(sm + LO(oROWS) + 5 * LMPC_MAX_ROWS)[idx] = P.row_begin[idx];
     for (int i = lane; i < N; i += NT) {
@@ -233,6 +236,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   int it = 0;
 
   // ---------------------------------------------------------------- linear rollout from x_ic
+  group_bulk_load_wait(sm + LO(oMBAR));
   for (int i = 0; i < NS; i++) {
     GLANES_BEGIN(NT)
       if (lane < 6) {

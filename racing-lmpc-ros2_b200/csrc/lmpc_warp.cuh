@@ -172,6 +172,40 @@ LMPC_DEV void group_or(LaneVar<int, 32 * NW>& x, double* /*scratch*/) {
 }
 #endif
 
+// ------------------------------------------------------------------ bulk stage-in (TMA)
+// group_bulk_load_begin: one elected thread arms an mbarrier with the byte count and issues ONE bulk asynchronous
+// copy global -> shared (cp.async.bulk, the TMA engine; SASS UBLKCP) of n doubles; the group goes on with other work
+// and calls group_bulk_load_wait before the first read of dst.  Requirements: dst, src 16-byte aligned, 8 n a multiple
+// of 16, a group synchronisation (any phase end) between begin and wait so that every thread sees the initialised
+// barrier.  bar: 8 bytes of shared memory, used once per kernel (phase parity 0).  Emulation: a plain copy.
+#if defined(LMPC_EMULATE)
+LMPC_DEV void group_bulk_load_begin(double* dst, const double* src, int n, double* /*bar*/) { for (int i = 0; i < n; i++) dst[i] = src[i]; }
+LMPC_DEV void group_bulk_load_wait(double* /*bar*/) {}
+#else
+LMPC_DEV void group_bulk_load_begin(double* dst, const double* src, int n, double* bar) {
+  if (threadIdx.x == 0u) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst);
+    const uint32_t bytes = 8u * (uint32_t)n;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+  }
+}
+LMPC_DEV void group_bulk_load_wait(double* bar) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(b)
+        : "memory");
+  }
+}
+#endif
+
 // convenience single-value forms
 template <int NW>
 LMPC_DEV void group_sum(LaneVar<double, 32 * NW>& x, double* scratch) {

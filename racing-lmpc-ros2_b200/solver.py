@@ -132,6 +132,41 @@ class BatchedRacingMPC:
         c = int(cnt[0]) if Bn else 0
         return sx[:, :c], sj[:, :c]
 
+    # ------------------------------------------------------------------ lap recorder (SafeSetRecorder)
+    def recorder_config(self, to_file=False, prefix=""):
+        _check(self.lib, self._h, self.lib.lmpc_recorder_config(self._h, int(bool(to_file)), str(prefix).encode()), "lmpc_recorder_config")
+
+    def recorder_step(self, x, u, k, t, total_length):
+        """SafeSetRecorder::step: one tick's (x_ic, u_ic, curvatures[0], t_ic); True when a completed lap was added."""
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel(); u = np.ascontiguousarray(u, dtype=np.float64).ravel()
+        added = C.c_int32(0)
+        rc = self.lib.lmpc_recorder_step(self._h, x.ctypes.data, u.ctypes.data, float(k), float(t), float(total_length), C.addressof(added))
+        _check(self.lib, self._h, rc, "lmpc_recorder_step")
+        return bool(added.value)
+
+    def recorder_lap_count(self):
+        return int(self.lib.lmpc_recorder_lap_count(self._h))
+
+    # ------------------------------------------------------------------ error-dynamics regression (RegQuery)
+    def regress(self, spec, xq, uq, A, Bm, Cv):
+        """SafeSetManager::query(RegQuery) for n items: returns the corrected (A (n,6,6), B (n,6,2), C (n,6)) and the number
+        of samples within dist_max per (item, regression).  A / B are row-indexed here ([item, row, col])."""
+        xq = np.ascontiguousarray(xq, dtype=np.float64).reshape(-1, 6); uq = np.ascontiguousarray(uq, dtype=np.float64).reshape(-1, 2)
+        n = xq.shape[0]
+        Ac = np.ascontiguousarray(np.asarray(A, dtype=np.float64).reshape(n, 6, 6).transpose(0, 2, 1))   # column-major per item
+        Bc = np.ascontiguousarray(np.asarray(Bm, dtype=np.float64).reshape(n, 6, 2).transpose(0, 2, 1))
+        Cc = np.array(Cv, dtype=np.float64).reshape(n, 6).copy()
+        npts = np.zeros((n, spec.n_out), dtype=np.int32)
+        rc = self.lib.lmpc_safe_set_regress_batch(self._h, n, C.byref(spec), xq.ctypes.data, uq.ctypes.data, Ac.ctypes.data,
+                                                  Bc.ctypes.data, Cc.ctypes.data, npts.ctypes.data, B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_safe_set_regress_batch")
+        return Ac.transpose(0, 2, 1).copy(), Bc.transpose(0, 2, 1).copy(), Cc, npts
+
+    def set_error_dynamics(self, spec=None):
+        """Apply the regression to every stage's (A, B, g) inside solve / solve_sqp / closed_loop (None disables)."""
+        rc = self.lib.lmpc_set_error_dynamics(self._h, C.byref(spec) if spec is not None else None)
+        _check(self.lib, self._h, rc, "lmpc_set_error_dynamics")
+
     # ------------------------------------------------------------------ track (RacingTrajectory)
     def set_track(self, table):
         """table: (n, >= 13) trajectory-file rows in TrajectoryIndex column order (racing_trajectory.hpp:37-56)."""

@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../racing-lmpc-ros2_b200/csrc/lmpc_host_params.h"
 #include "../../racing-lmpc-ros2_b200/csrc/lmpc_ss_core.cuh"
+#include "../../racing-lmpc-ros2_b200/csrc/lmpc_reg_core.cuh"
 int g_lmpc_emu_reverse = 0;
 
 extern "C" void emu_set_reverse(int r) { g_lmpc_emu_reverse = r; }
@@ -73,3 +74,13 @@ extern "C" void emu_track_eval(int n, const double* s, double* out) {   // out [
 }
 extern "C" void emu_track_f2g(int n, const double* f, double* g) { const LmpcTrack T = g_trk.view(); for (int i = 0; i < n; i++) lmpc_frenet_to_global(T, f + 3 * i, g + 3 * i); }
 extern "C" void emu_track_g2f(int n, const double* g, double* f) { const LmpcTrack T = g_trk.view(); for (int i = 0; i < n; i++) lmpc_global_to_frenet(T, g + 3 * i, f + 3 * i); }
+
+// error-dynamics regression of one query item over M prepared points (Z [M][8], E [M][6]); A, B column-major, in place
+extern "C" int emu_regress(const lmpc_reg_spec* sp, int M, const double* Z, const double* E, const double* zq, double* A, double* B,
+                           double* C, int* npts) {
+  LmpcRegPlan plan;
+  if (!lmpc_make_reg_plan(sp, &plan)) return -1;
+  LmpcRegView v = {Z, E, M};
+  lmpc_regress_warp(plan, v, zq, A, B, C, npts);
+  return 0;
+}
