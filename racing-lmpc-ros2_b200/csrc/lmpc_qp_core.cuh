@@ -19,6 +19,9 @@
 #pragma once
 #include "lmpc_warp.cuh"
 #include "../../include/lmpc_b200.h"
+#ifdef LMPC_DEBUG_TRACE
+#include <stdio.h>
+#endif
 
 #define LMPC_MB 4               // explicit (basic-candidate) safe-set columns
 #define LMPC_NQ (1 + LMPC_MB)   // + simplex multiplier
@@ -141,6 +144,7 @@ struct LmpcQpOut {
   int* iters;      // 1
 };
 
+struct alignas(16) LmpcD2 { double x, y; };   // 16-byte shared-memory loads (LDS.128)
 struct ArrK { double a[LMPC_KPL_MAX]; };
 // same access syntax as LaneVar<ArrK> -- v(lane).a[p] -- for per-column values that live in global scratch instead of
 // registers (element lane + NT p of a LMPC_MAX_SS_PTS-long array): the step buffers of the lambda block
@@ -509,7 +513,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         double r1[6];
         static_assert(LMPC_NRED == 36, "layout of the terminal reduction");
 #ifdef LMPC_DEBUG_TRACE
-        if (it == 0 && pass == 0) { LANE0_ONLY(if (LMPC_TRACE_COND) printf("  pre-reduce lane0: W00 %.9e a0 %.9e om1 %.9e | St %.6e %.6e %.6e om %.6e %.6e isB %d %d %d K %d\n", rt[7](0), rt[28](0), rt[34](0), St(0).a[0][0], St(0).a[1][0], St(0).a[2][0], omg_(0).a[0], omg_(0).a[1], isB(0).a[0], isB(0).a[1], isB(0).a[2], K);) }
+        if (it == 0 && pass == 0) { LANE0_ONLY(if (LMPC_TRACE_COND) printf("  pre-reduce lane0: W00 %.9e a0 %.9e om1 %.9e | St %.6e %.6e %.6e om %.6e %.6e isB %d %d %d K %d\n", rt[7](0), rt[28](0), rt[34](0), ST[0], ST[6 * NT], ST[12 * NT], omg_(0).a[0], omg_(0).a[1], isB(0).a[0], isB(0).a[1], isB(0).a[2], K);) }
 #endif
         if (pass == 0) {   // values that only change with the factorisation are reduced in pass 0 only
           int ops[LMPC_NRED];
@@ -743,48 +747,44 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const double uq0 = GUD[i], uq1 = 2.0 * P.Rm[1], uq2 = GUD[d + i];
           // phases a-c produce 8x8 blocks: output (r, c) with c = lane & 7 and r = (lane >> 3) + (NT / 8) * round.
           // The rounds are unrolled with r's range visible to the compiler, so the row tests of the first round fold.
-          // phase a: [M_xx A | M_xx B + M_xu] (rows 0..5) and, in rows 6,7, A' l_x | B' l_x + l_u for the two rhs columns
+          // phase a: [M_xx A | M_xx B + M_xu] (rows 0..5) and, in rows 6,7, A' l_x | B' l_x + l_u for the two rhs columns.
+          // L1 / LTH follow PM in the layout (rows 8, 9 of the same array) and AXBW follows MAB (its rows 6, 7), so all
+          // 64 outputs are the same expression: out[r][c] = (c >= 6 ? S[rr][c] : 0) + sum_k S[rr][k] [A|B][k][c], rr = r or r + 2
           GLANES_BEGIN(NT)
 #pragma unroll
             for (int rd = 0; rd < LMPC_R8; rd++) {
               const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
               if (NT > 64 && lane >= 64) break;
-              const double* col = A + 6 * c;   // [A | B] is contiguous: column c of B follows A's six columns
-              if (r < 6) {
-                double a = (c < 6) ? 0.0 : PM[8 * r + c];
+              const LmpcD2* col = reinterpret_cast<const LmpcD2*>(A + 6 * c);   // [A | B] is contiguous: column c of B follows A's six columns
+              const double* prow = PM + 8 * (r + ((r >= 6) ? 2 : 0));
+              const LmpcD2* pr2 = reinterpret_cast<const LmpcD2*>(prow);
+              double a = (c < 6) ? 0.0 : prow[c];
 #pragma unroll
-                for (int k = 0; k < 6; k++) a += PM[8 * r + k] * col[k];
-                MAB[8 * r + c] = a;
-              } else {
-                const double* l = (r == 6) ? L1 : LTH;
-                double a = (c < 6) ? 0.0 : l[c];
-#pragma unroll
-                for (int k = 0; k < 6; k++) a += col[k] * l[k];
-                AXBW[8 * (r - 6) + c] = a;
-              }
+              for (int k = 0; k < 3; k++) { const LmpcD2 pv = pr2[k], cv = col[k]; a += pv.x * cv.x; a += pv.y * cv.y; }
+              MAB[8 * r + c] = a;
             }
           GLANES_END(NW)
-          // phase b: Yxx = A' MA, Yxu = A' MB, Yuu = B' MB + M_ux B + M_uu
+          // phase b: Yxx = A' MA, Yxu = A' MB, Yuu = B' MB + M_ux B + M_uu.  The first product is the same expression for
+          // every (r, c) -- column r of [A|B] against column c of MAB -- the M_ux B + M_uu part is a four-lane tail.
           GLANES_BEGIN(NT)
 #pragma unroll
             for (int rd = 0; rd < LMPC_R8; rd++) {
               const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
               if (NT > 64 && lane >= 64) break;
-              if (r < 6) {
-                double a = 0.0;
+              const LmpcD2* ar = reinterpret_cast<const LmpcD2*>(A + 6 * r);
+              double a = (r >= 6 && c >= 6) ? PM[8 * r + c] : 0.0;
 #pragma unroll
-                for (int k = 0; k < 6; k++) a += A[k + 6 * r] * MAB[8 * k + c];
-                YY[8 * r + c] = a;
-              } else if (c >= 6) {
-                double a = PM[8 * r + c];
-#pragma unroll
-                for (int k = 0; k < 6; k++) a += B[k + 6 * (r - 6)] * MAB[8 * k + c] + PM[8 * k + r] * B[k + 6 * (c - 6)];
-                YY[8 * r + c] = a;
-              } else if (c < 2) {
-                // rows 6,7 of Qzw = -E, parked in the unused (r >= 6, c < 2) slots so that phase c reads
-                // Qzw[r][j] = QZ(r, j) without selecting between Yxu and -E
-                YY[8 * r + c] = (r == 6) ? (c == 0 ? -e0 : -e1) : (c == 0 ? -e1 : -e2);
+              for (int k = 0; k < 3; k++) {
+                const LmpcD2 av = ar[k];
+                if (r >= 6 && c >= 6) {   // same order of additions as the single-expression form
+                  a += av.x * MAB[8 * (2 * k) + c] + PM[8 * (2 * k) + r] * B[2 * k + 6 * (c - 6)];
+                  a += av.y * MAB[8 * (2 * k + 1) + c] + PM[8 * (2 * k + 1) + r] * B[2 * k + 1 + 6 * (c - 6)];
+                } else { a += av.x * MAB[8 * (2 * k) + c]; a += av.y * MAB[8 * (2 * k + 1) + c]; }
               }
+              // rows 6,7 of Qzw = -E are parked in the unused (r >= 6, c < 2) slots so that phase c reads
+              // Qzw[r][j] = QZ(r, j) without selecting between Yxu and -E
+              if (r >= 6 && c < 2) a = (r == 6) ? (c == 0 ? -e0 : -e1) : (c == 0 ? -e1 : -e2);
+              YY[8 * r + c] = a;
             }
           GLANES_END(NW)
 #ifdef LMPC_DEBUG_TRACE
@@ -1059,7 +1059,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       changed += rc2[0](0);
       const double dymax = fmax(dymax_u, rc2[2](0));   // a second AL step removes the bias left by inexact multipliers
 #ifdef LMPC_DEBUG_TRACE
-      LANE0_ONLY(if (LMPC_TRACE_COND) printf("  polish round %d: changed %.0f viol %.0f th %.3e pact_th %d\n", polishing, changed, rc2[1](0), th, pact_th);)
+      LANE0_ONLY(if (LMPC_TRACE_COND) printf("  polish round %d: changed %.0f viol %.0f th %.3e pact_th %d dymax %.3e (u %.3e)\n", polishing, changed, rc2[1](0), th, pact_th, dymax, dymax_u);)
 #endif
       if ((changed > 0.5 || dymax > LMPC_PDY) && polishing < LMPC_PMAX) { polishing++; continue; }
       if (changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }

@@ -12,8 +12,9 @@ kern = sys.argv[3] if len(sys.argv) > 3 else "lmpc_qp_kernelILi1ELi3ELi20ELi16"
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 50
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+dis = ""   # one cubin per translation unit: the kernel's section is in one of them
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 line_of = {}
 infn = False; cur = None
 for l in dis.splitlines():
@@ -61,17 +62,27 @@ for ln, (n, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{100*n/tot[0]:5.2f}% inst {100*s/max(tot[1],1):5.2f}% samples  {ln}  {src(ln)}")
 
 # ---- section totals (line ranges of lmpc_qp_core.cuh; everything from other files = collectives / intrinsics)
-SECTIONS = [("load + initial point", 199, 305), ("iteration control / classify", 306, 333), ("row assembly (Hessian/gradient)", 334, 415),
-            ("terminal block (safe-set simplex)", 416, 696), ("stage control pieces", 697, 714), ("backward sweep, factor pass", 715, 831),
-            ("backward sweep, rhs-only pass", 832, 862), ("forward sweep", 863, 888), ("lambda directions", 889, 927),
-            ("row directions / step length", 928, 986), ("polish update", 987, 1070), ("iterate update", 1071, 1123), ("outputs", 1124, 1180)]
+# section boundaries are found from the marker comments of lmpc_qp_core.cuh (so the table follows the source as it moves)
+MARKERS = [("load + initial point", "---- load"), ("iteration control / classify", "==== interior-point iterations"),
+           ("row assembly (Hessian/gradient)", "---------- rows -> per-stage Hessian"), ("terminal block (safe-set simplex)", "---------- terminal value"),
+           ("stage control pieces", "---------- per-stage control pieces"), ("backward sweep, factor pass", "---------- backward Riccati sweep"),
+           ("backward sweep, rhs-only pass", "// pass 1: right-hand side"), ("forward sweep", "---------- sigma_b step, forward sweep"),
+           ("lambda directions", "---------- terminal directions (lambda)"), ("row directions / step length", "---------- row directions, step length"),
+           ("polish update", "if (restart) { it--; continue; }"), ("iterate update", "---------- update the iterate"), ("outputs", "---- outputs")]
+core = open(os.path.join("racing-lmpc-ros2_b200", "csrc", "lmpc_qp_core.cuh")).read().splitlines()
+starts = []
+for name, mk in MARKERS:
+    ln = next(i + 1 for i, l in enumerate(core) if mk in l)
+    starts.append((name, ln))
+SECTIONS = [(name, a, (starts[k + 1][1] - 1) if k + 1 < len(starts) else len(core)) for k, (name, a) in enumerate(starts)]
+FIRST = starts[0][1]
 sec = collections.OrderedDict((name, [0, 0]) for name, _, _ in SECTIONS)
 sec["row helpers (row_val/row_bound/FOR_ROWS)"] = [0, 0]
 sec["collectives / shuffles (other files)"] = [0, 0]
 for ln, (n, s) in agg.items():
     key = "collectives / shuffles (other files)"
     if ln is not None and ln[0] == "lmpc_qp_core.cuh":
-        if ln[1] < 199: key = "row helpers (row_val/row_bound/FOR_ROWS)"
+        if ln[1] < FIRST: key = "row helpers (row_val/row_bound/FOR_ROWS)"
         else:
             for name, a, b in SECTIONS:
                 if a <= ln[1] <= b: key = name; break
