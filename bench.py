@@ -181,19 +181,14 @@ def main():
     d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
     d_out = mpc.alloc_device_outputs(args.batch, dev)
     N, K = cfg["N"], cfg["num_ss_pts"]
-    slab_w = 6 * N + 4 * (N - 1) + 2     # X, U, dU, cost, status per instance
-    slab = torch.empty((args.batch, slab_w), dtype=torch.float64, device=dev)
-    gathered = torch.empty((max(world, 1) * args.batch, slab_w), dtype=torch.float64, device=dev) if world > 1 else None
+    # X, U, dU, cost, status of the rank live in one allocation (d_out["slab"]): the gather needs no packing kernel
+    gathered = torch.empty(max(world, 1) * d_out["slab"].numel(), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
     def step():
         mpc.solve(d_in, d_out)
         if world > 1:   # the one collective of the path: gather the converged trajectories
-            slab[:, :6 * N] = d_out["X_optm"].reshape(args.batch, -1)
-            slab[:, 6 * N:6 * N + 2 * (N - 1)] = d_out["U_optm"].reshape(args.batch, -1)
-            slab[:, 6 * N + 2 * (N - 1):6 * N + 4 * (N - 1)] = d_out["dU_optm"].reshape(args.batch, -1)
-            slab[:, -2] = d_out["cost"]; slab[:, -1] = d_out["status"].to(torch.float64)
-            dist.all_gather_into_tensor(gathered, slab)
+            dist.all_gather_into_tensor(gathered, d_out["slab"])
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
@@ -229,6 +224,12 @@ def main():
     dev_ms = float(t.item())
     status = d_out["status"].cpu().numpy()
     iters = d_out["iters"].cpu().numpy()
+    if world > 1:   # untimed check of the collective: this rank's block of the gathered buffer is its own solution
+        from racing_lmpc_ros2_b200.distributed import unpack_flat_slab
+        g = unpack_flat_slab(gathered.cpu().numpy(), world, args.batch, N)
+        lo = rank * args.batch
+        assert np.array_equal(g["X_optm"][lo:lo + args.batch], d_out["X_optm"].cpu().numpy())
+        assert np.array_equal(g["status"][lo:lo + args.batch], status)
     solved = int((status == 0).sum())
     total_instances = args.batch * max(world, 1)
     value = total_instances * args.steps / (dev_ms * 1e-3)

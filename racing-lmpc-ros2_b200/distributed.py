@@ -37,6 +37,26 @@ def unpack_slab(slab, N):
                 status=slab[:, -1].astype(np.int32))
 
 
+def unpack_flat_slab(flat, world, Bn, N):
+    """Inverse of the layout BatchedRacingMPC.alloc_device_outputs gives out["slab"], after an all-gather of it over
+    `world` ranks: flat is (world * slab_len,) float64 (numpy).  Returns the global instance-major outputs."""
+    NS = N - 1
+    n64 = Bn * (6 * N + 4 * NS + 1)
+    per = n64 + (Bn + 1) // 2
+    flat = np.ascontiguousarray(flat).reshape(world, per)
+    X, U, dU, cost, status = [], [], [], [], []
+    for r in range(world):
+        f = flat[r]
+        o = 0
+        X.append(f[o:o + Bn * 6 * N].reshape(Bn, N, 6)); o += Bn * 6 * N
+        U.append(f[o:o + Bn * 2 * NS].reshape(Bn, NS, 2)); o += Bn * 2 * NS
+        dU.append(f[o:o + Bn * 2 * NS].reshape(Bn, NS, 2)); o += Bn * 2 * NS
+        cost.append(f[o:o + Bn]); o += Bn
+        status.append(f[o:].copy().view(np.int32)[:Bn])
+    return dict(X_optm=np.concatenate(X), U_optm=np.concatenate(U), dU_optm=np.concatenate(dU), cost=np.concatenate(cost),
+                status=np.concatenate(status))
+
+
 def broadcast_laps(laps, dist, device=None):
     """Rank 0's laps to every rank (one broadcast of a packed tensor per lap)."""
     import torch

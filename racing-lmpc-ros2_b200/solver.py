@@ -350,10 +350,26 @@ class BatchedRacingMPC:
         return out
 
     def alloc_device_outputs(self, Bn, device=None):
+        """Device output buffers.  X_optm, U_optm, dU_optm, cost and status are views into ONE allocation, out["slab"]
+        (array-major: [X | U | dU | cost | status(int32)]), so that a multi-GPU caller gathers the trajectories of
+        all ranks with a single collective on that buffer and no packing kernel (distributed.unpack_flat_slab)."""
         import torch
         dev = device or torch.device("cuda", self.device)
-        out = {k: torch.empty(shp, dtype=torch.float64, device=dev) for k, shp in self._shapes(Bn).items()}
-        out["status"] = torch.empty(Bn, dtype=torch.int32, device=dev)
+        shp = self._shapes(Bn)
+        out = {}
+        gathered = ("X_optm", "U_optm", "dU_optm", "cost")
+        n64 = sum(int(np.prod(shp[k])) for k in gathered)
+        slab = torch.zeros(n64 + (Bn + 1) // 2, dtype=torch.float64, device=dev)
+        o = 0
+        for k in gathered:
+            n = int(np.prod(shp[k]))
+            out[k] = slab[o:o + n].view(shp[k])
+            o += n
+        out["status"] = slab[o:].view(torch.int32)[:Bn]
+        out["slab"] = slab
+        for k, sh in shp.items():
+            if k not in out:
+                out[k] = torch.empty(sh, dtype=torch.float64, device=dev)
         out["iters"] = torch.empty(Bn, dtype=torch.int32, device=dev)
         return out
 

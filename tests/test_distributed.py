@@ -75,3 +75,23 @@ def test_two_rank_gloo_solve_matches_single_process(pkg):
         assert X.shape == (11, 20, 6)
         assert np.array_equal(status, ref["status"])
         assert np.array_equal(X, ref["X"]) and np.array_equal(cost, ref["cost"])   # same code, same inputs: bit-exact
+
+
+def test_flat_slab_layout_round_trip(pkg):
+    """The single-allocation output layout ([X | U | dU | cost | status:int32] per rank) that the multi-GPU bench
+    all-gathers without a packing kernel: unpack_flat_slab inverts it, odd batch sizes included."""
+    from racing_lmpc_ros2_b200.distributed import unpack_flat_slab
+    rng = np.random.default_rng(4)
+    for world, Bn, N in ((2, 5, 20), (4, 8, 40), (1, 3, 7)):
+        NS = N - 1
+        parts, ref = [], dict(X_optm=[], U_optm=[], dU_optm=[], cost=[], status=[])
+        for r in range(world):
+            X = rng.normal(size=(Bn, N, 6)); U = rng.normal(size=(Bn, NS, 2)); dU = rng.normal(size=(Bn, NS, 2))
+            cost = rng.normal(size=Bn); st = rng.integers(0, 5, Bn).astype(np.int32)
+            tail = np.zeros((Bn + 1) // 2); tail.view(np.int32)[:Bn] = st
+            parts.append(np.concatenate([X.ravel(), U.ravel(), dU.ravel(), cost, tail]))
+            for k, v in zip(ref, (X, U, dU, cost, st)):
+                ref[k].append(v)
+        g = unpack_flat_slab(np.concatenate(parts), world, Bn, N)
+        for k in ref:
+            assert np.array_equal(g[k], np.concatenate(ref[k])), k
