@@ -74,32 +74,23 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
   if (NW != 1 && NW != 2 && NW != 4) return LMPC_ERR_INVALID;
   if (P.learning && (P.K + 32 * NW - 1) / (32 * NW) > LMPC_KPL_MAX) return LMPC_ERR_INVALID;
   P.NW = NW;
-  // row table: group g in [0,10): 0..5 GX(c) = state box hi/lo (+ the two boundary rows in group 1),
-  // 6..7 GU(c) control box, 8..9 GD(c) rate box; sign +1 for the upper row, -1 for the lower one
-  int nr = 0;
-  for (int g = 0; g < 10; g++) {
-    P.row_begin[g] = nr;
-    const int rows_of_g = (g == 1) ? 4 : 2;
-    for (int r = 0; r < rows_of_g; r++) {
-      RowDesc q;
-      q.sg = (r & 1) ? -1.0 : 1.0; q.i0 = 0; q.i1 = -1; q.bnd = 0.0; q.slot = 0; q.c = 0; q.rtype = 0;
-      if (g < 6) {
-        q.c = g;
-        if (r < 2) { q.rtype = 0; q.slot = P.xslot[g][r]; if (q.slot >= 0) { q.i0 = 1; q.i1 = P.N - 2; q.bnd = P.xb_h[q.slot]; } }
-        else { q.rtype = 1; q.slot = P.nxb + 8 + (r - 2); q.i0 = P.soft ? 0 : 1; q.i1 = P.N - 1; }
-      } else if (g < 8) {
-        q.c = g - 6; q.rtype = 2; q.slot = P.nxb + 2 * q.c + r;
-        if (P.ub_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; q.bnd = (r & 1) ? -P.ulo[q.c] : P.uhi[q.c]; }
-      } else {
-        q.c = g - 8; q.rtype = 3; q.slot = P.nxb + 4 + 2 * q.c + r;
-        if (P.db_act[2 * q.c + r]) { q.i0 = 0; q.i1 = P.N - 2; q.bnd = (r & 1) ? -P.dlo[q.c] : P.dhi[q.c]; }
-      }
-      if (q.i1 < q.i0) continue;   // row absent
-      if (nr >= LMPC_MAX_ROWS) return LMPC_ERR_INVALID;   // cannot happen: 22 rows at most
-      P.rows[nr++] = q;
+  // row table: state box rows (slot = their index among the finite bounds), then -- in slot order after them --
+  // u box (c0 hi, c0 lo, c1 hi, c1 lo), rate box (same order), boundary (left = upper side of e_y, right = lower side)
+  LmpcRowTab& T = P.rowtab;
+  for (int k = 0; k < 6; k++)
+    for (int r = 0; r < 2; r++) {
+      T.xslot[2 * k + r] = P.xslot[k][r];
+      T.xbnd[2 * k + r] = P.xslot[k][r] >= 0 ? P.xb_h[P.xslot[k][r]] : 0.0;
     }
-  }
-  P.row_begin[10] = nr;
+  for (int k = 0; k < 2; k++)
+    for (int r = 0; r < 2; r++) {
+      T.uslot[2 * k + r] = P.ub_act[2 * k + r] ? P.nxb + 2 * k + r : -1;
+      T.ubnd[2 * k + r] = r ? -P.ulo[k] : P.uhi[k];
+      T.dslot[2 * k + r] = P.db_act[2 * k + r] ? P.nxb + 4 + 2 * k + r : -1;
+      T.dbnd[2 * k + r] = r ? -P.dlo[k] : P.dhi[k];
+    }
+  T.bslot[0] = P.nxb + 8; T.bslot[1] = P.nxb + 9;
+  T.ib0 = P.soft ? 0 : 1; T.pad_ = 0;
   P.lay = lmpc_layout(P.N, P.RS, NW);
   *out = P;
   return LMPC_OK;

@@ -49,8 +49,17 @@ struct LmpcLayout {
       oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, oMBAR, total;
 };
 #define LMPC_MAX_ROWS 22   // 6 x 2 state boxes + 2 boundary + 4 control boxes + 4 rate boxes
-#define LMPC_ROWS_DOUBLES (5 * LMPC_MAX_ROWS + 6)   // RowDesc[LMPC_MAX_ROWS] (40 B each) + row_begin[11] (+ pad)
-#define LMPC_TB_SIZE_ (36 + 6 * LMPC_NQ + LMPC_NQ * LMPC_NQ + 6 * LMPC_NQ + LMPC_NQ + 36 + 6 + 6 * LMPC_MB + LMPC_MB + LMPC_MB + LMPC_NQ + 1)
+// Row table (depends on the configuration only; built on the host, lmpc_host_params.h).  Every row is
+//   sg * var - [theta] <= bnd,  sg = +1 (upper side) / -1 (lower side),  var = x_c(i), u_c(i) or du_c(i);
+// entry [2 c + side] of the x / u / d arrays, [side] of the boundary pair (left, right).  slot = -1: row absent.
+struct LmpcRowTab {
+  double xbnd[12], ubnd[4], dbnd[4];
+  int xslot[12], uslot[4], dslot[4], bslot[2];
+  int ib0, pad_;   // first stage of the boundary rows (0 when they are soft, 1 otherwise)
+};
+static_assert(sizeof(LmpcRowTab) % 8 == 0, "row table is copied as doubles");
+#define LMPC_ROWS_DOUBLES ((int)(sizeof(LmpcRowTab) / 8))
+#define LMPC_TB_SIZE_ (36 + 6 * LMPC_NQ + LMPC_NQ * LMPC_NQ + 6 * LMPC_NQ + LMPC_NQ + 36 + 6 + 6 * LMPC_MB + LMPC_MB + LMPC_MB + LMPC_NQ + 1 + 6 + LMPC_NQ)
 LMPC_HD constexpr int lmpc_even(int n) { return (n + 1) & ~1; }   // keep 16-byte alignment
 LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
   LmpcLayout L{};
@@ -73,12 +82,6 @@ LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
   return L;
 }
 
-// A row of group g (uniform across the lanes: every lane works on the same group, its own stage i):
-// type, slot, component, sign, constant bound (types 0, 2, 3) and the stage range [i0, i1] on which the row exists.
-// The table is built once on the host (lmpc_host_params.h) -- it depends on the configuration only.
-struct RowDesc { int rtype, slot, c, i0, i1; double sg, bnd; };
-static_assert(sizeof(RowDesc) == 40, "row table layout");
-
 struct LmpcQpParams {
   int N, NS, K, learning, soft, hull_slack;
   int nh, hidx[6];
@@ -96,8 +99,7 @@ struct LmpcQpParams {
   double tol;
   int NSd;                       // odd stage stride of the [.][stage] arrays
   int NW;                        // warps per instance the layout was sized for
-  int row_begin[11];             // rows of group g are rows[row_begin[g] .. row_begin[g+1])
-  RowDesc rows[LMPC_MAX_ROWS];   // existing rows only, group-major: 0..5 GX(c), 6..7 GU(c), 8..9 GD(c)
+  LmpcRowTab rowtab;             // the inequality rows (copied to shared memory: constant-bank indexing is slow)
   LmpcLayout lay;                // shared-memory offsets (doubles)
 };
 
@@ -113,7 +115,8 @@ struct LmpcQpParams {
 #define TB_BD (TB_BCOL + 6 * LMPC_MB)  // MB      y/lambda of basic columns
 #define TB_BG (TB_BD + LMPC_MB)        // MB      g_lambda of basic columns
 #define TB_PIV (TB_BG + LMPC_MB)       // NQ (as doubles)
-#define TB_SIZE (TB_PIV + LMPC_NQ + 1)
+#define TB_EQ (TB_PIV + LMPC_NQ + 1)   // 6 + NQ   e and q of the terminal directions (computed by 11 lanes, read by all)
+#define TB_SIZE (TB_EQ + 6 + LMPC_NQ)
 static_assert(TB_SIZE == LMPC_TB_SIZE_, "terminal scratch size");
 
 struct LmpcQpIn {
@@ -155,26 +158,64 @@ struct ArrKx6 { double a[LMPC_KPL_MAX][6]; };
 struct ArrKi { int a[LMPC_KPL_MAX]; };
 
 // ---------------------------------------------------------------------------------------- rows
-// iterate: for every group g (uniform), every stage i owned by this lane, every existing row q of g
-#define FOR_GROUPS(g) for (int g = 0; g < 10; g++)
+// Row work is organised by *variable*: group g = 0..5 is state c = g (box pair; for e_y also the two boundary rows),
+// 6..7 control c = g - 6 (box pair), 8..9 rate c = g - 8 (box pair).  LMPC_FOR_ROWS(i, NA, NF) visits the rows of stage i:
+// the variable's value in the iterate (v), in the affine step (va, when NA) and in the final step (vf, when NF) is formed
+// once per group, then the unrolled side loop runs ROW_BODY for every existing row of it.  The caller defines three
+// object-like macros before the expansion (and undefines them after):
+//   ROW_GBEGIN   once per (group, stage), before its rows        in scope: g, i, v, va, vf
+//   ROW_BODY     once per existing row                           in scope: + slot, sg, bnd, isb (constant: boundary row)
+//   ROW_GEND     once per (group, stage), after its rows
+// The value of the row on a vector is  sg * v - (isb ? theta-component : 0).
 #define FOR_MY_STAGES(i) for (int i = lane; i < N; i += NT)
-#define FOR_ROWS(q, g, i)                                                  \
-  for (int rr_ = ROWB[g]; rr_ < ROWB[(g) + 1]; rr_++)                      \
-    for (RowDesc q = ROWS[rr_]; q.i1 >= q.i0; q.i1 = -2)                   \
-      if (i >= q.i0 && i <= q.i1)
-// G v of the row for the vectors (xs, us, thv); up0 = u_{-1} component (u_ic for the iterate, 0 for a step)
-LMPC_DEV double row_val(const RowDesc& q, int i, int d, const double* xs, const double* us, const double* IT, double thv, const double* up0) {
-  switch (q.rtype) {
-    case 0: return q.sg * xs[q.c * d + i];
-    case 1: return q.sg * xs[d + i] - thv;
-    case 2: return q.sg * us[q.c * d + i];
-    default: return q.sg * (us[q.c * d + i] - (i ? us[q.c * d + i - 1] : (q.c ? up0[1] : up0[0]))) * IT[i];   // select, not an indexed load: up0 stays in registers
+#define LMPC_ROW_SIDES_(SLOTS, K2, BNDEXPR, ISB)                                                         \
+  LMPC_UNROLL                                                                                            \
+  for (int side_ = 0; side_ < 2; side_++) {                                                              \
+    const int slot = (SLOTS)[(K2) + side_];                                                              \
+    if (slot >= 0) {                                                                                     \
+      const double sg = side_ ? -1.0 : 1.0;                                                              \
+      const double bnd = (BNDEXPR);                                                                      \
+      constexpr bool isb = (ISB);                                                                        \
+      (void)sg; (void)bnd; (void)isb;                                                                    \
+      ROW_BODY                                                                                           \
+    }                                                                                                    \
   }
-}
-LMPC_DEV double row_bound(const LmpcQpParams& P, const RowDesc& q, int i, const double* BL, const double* BR) {
-  if (q.rtype == 1) return q.sg > 0.0 ? (BL[i] - P.margin) : -(BR[i] + P.margin);
-  return q.bnd;
-}
+#define LMPC_FOR_ROWS(i, NA, NF)                                                                         \
+  {                                                                                                      \
+    LMPC_NOUNROLL                                                                                        \
+    for (int c_ = 0; c_ < 6; c_++) {                                                                     \
+      const int g = c_;                                                                                  \
+      const double v = X[c_ * d + (i)], va = (NA) ? DXA[c_ * d + (i)] : 0.0, vf = (NF) ? DXF[c_ * d + (i)] : 0.0; \
+      (void)g; (void)v; (void)va; (void)vf;                                                              \
+      ROW_GBEGIN                                                                                         \
+      if ((i) >= 1 && (i) <= N - 2) { LMPC_ROW_SIDES_(RT->xslot, 2 * c_, RT->xbnd[2 * c_ + side_], false) } \
+      if (c_ == 1 && (i) >= RT->ib0) { LMPC_ROW_SIDES_(RT->bslot, 0, side_ ? -(BR[i] + P.margin) : (BL[i] - P.margin), true) } \
+      ROW_GEND                                                                                           \
+    }                                                                                                    \
+    if ((i) <= N - 2) {                                                                                  \
+      LMPC_NOUNROLL                                                                                      \
+      for (int c_ = 0; c_ < 2; c_++) {                                                                   \
+        const int g = 6 + c_;                                                                            \
+        const double v = U[c_ * d + (i)], va = (NA) ? DUA[c_ * d + (i)] : 0.0, vf = (NF) ? DUF[c_ * d + (i)] : 0.0; \
+        (void)g; (void)v; (void)va; (void)vf;                                                            \
+        ROW_GBEGIN                                                                                       \
+        LMPC_ROW_SIDES_(RT->uslot, 2 * c_, RT->ubnd[2 * c_ + side_], false)                              \
+        ROW_GEND                                                                                         \
+      }                                                                                                  \
+      const double it_ = IT[i];                                                                          \
+      LMPC_NOUNROLL                                                                                      \
+      for (int c_ = 0; c_ < 2; c_++) {                                                                   \
+        const int g = 8 + c_;                                                                            \
+        const double v = (U[c_ * d + (i)] - ((i) ? U[c_ * d + (i) - 1] : (c_ ? uic[1] : uic[0]))) * it_; \
+        const double va = (NA) ? (DUA[c_ * d + (i)] - ((i) ? DUA[c_ * d + (i) - 1] : 0.0)) * it_ : 0.0;  \
+        const double vf = (NF) ? (DUF[c_ * d + (i)] - ((i) ? DUF[c_ * d + (i) - 1] : 0.0)) * it_ : 0.0;  \
+        (void)g; (void)v; (void)va; (void)vf;                                                            \
+        ROW_GBEGIN                                                                                       \
+        LMPC_ROW_SIDES_(RT->dslot, 2 * c_, RT->dbnd[2 * c_ + side_], false)                              \
+        ROW_GEND                                                                                         \
+      }                                                                                                  \
+    }                                                                                                    \
+  }
 
 // ------------------------------------------------------------------------------------------------
 // NW warps per instance, KPL = ceil(K / (32 NW)) safe-set columns per lane (registers).
@@ -198,8 +239,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   double* DXA = sm + LO(oDXA); double* DUA = sm + LO(oDUA); double* DXF = sm + LO(oDXF); double* DUF = sm + LO(oDUF);
   double* HX = DXF;   // alias: the Hessian diagonal is dead once the pass-0 factorisation is done
   double* CZX = sm + LO(oCZX); double* CZTH = sm + LO(oCZTH); double* GUD = sm + LO(oGUD);
-  const RowDesc* ROWS = reinterpret_cast<const RowDesc*>(sm + LO(oROWS));
-  const int* ROWB = reinterpret_cast<const int*>(sm + LO(oROWS) + 5 * LMPC_MAX_ROWS);
+  const LmpcRowTab* RT = reinterpret_cast<const LmpcRowTab*>(sm + LO(oROWS));
   double* FAC = sm + LO(oFAC);   // per stage: Kz[16] (2x8 row-major), Sinv[3], pad
   double* KFF = sm + LO(oKFF);   // per stage: kff1[2], kffth[2], Cwth[2]
   double* BL = sm + LO(oBL); double* BR = sm + LO(oBR); double* VREF = sm + LO(oVREF); double* IT = sm + LO(oIT);
@@ -214,8 +254,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // the group stages the small inputs below
   group_bulk_load_begin(ABG, in.ABg, 54 * NS, sm + LO(oMBAR));
   GLANES_BEGIN(NT)
-    for (int idx = lane; idx < 5 * LMPC_MAX_ROWS; idx += NT) (sm + LO(oROWS))[idx] = reinterpret_cast<const double*>(P.rows)[idx];
-    for (int idx = lane; idx < 11; idx += NT) reinterpret_cast<int*>(sm + LO(oROWS) + 5 * LMPC_MAX_ROWS)[idx] = P.row_begin[idx];
+    for (int idx = lane; idx < LMPC_ROWS_DOUBLES; idx += NT) (sm + LO(oROWS))[idx] = reinterpret_cast<const double*>(&P.rowtab)[idx];
     for (int i = lane; i < N; i += NT) {
       BL[i] = in.bl[i]; BR[i] = in.br[i]; VREF[i] = in.vref[i];
       if (i < NS) {
@@ -268,13 +307,19 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     LaneVar<double, NT> r[12];
     GLANES_BEGIN(NT)
       double r0 = 1.0, cnt = 0.0;
-      FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-        const double slack = row_bound(P, q, i, BL, BR) - row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic);
-        const double s = slack > sfloor ? slack : sfloor;
-        const double y = mu0 / s;
-        RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
-        r0 = fmax(r0, y); cnt += 1.0;
-      }
+      const double thq = soft ? th : 0.0;
+#define ROW_GBEGIN
+#define ROW_GEND
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double slack = bnd - (sg * v - (isb ? thq : 0.0));               \
+    const double s = slack > sfloor ? slack : sfloor;                      \
+    const double y = mu0 / s;                                              \
+    RSs[slot * d + i] = s; RSy[slot * d + i] = y; RSi[slot * d + i] = 1.0 / (s * y); \
+    r0 = fmax(r0, y); cnt += 1.0;                                          \
+  }
+      FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, false, false)
+#undef ROW_BODY
       const double j0 = (learn && K > 0) ? in.ssj[0] : 0.0;
       for (int p = 0; p < KPL; p++) {
         const int k = lane + NT * p;
@@ -330,11 +375,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     if (polishing && !classified) {
       // ---------- classify from the interior-point iterate, save what a failed polish must restore
       GLANES_BEGIN(NT)
-        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i];
-          RSi[q.slot * d + i] = y;
-          if (y > s) RSs[q.slot * d + i] = -s; else RSy[q.slot * d + i] = 0.0;
-        }
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = RSs[slot * d + i], y = RSy[slot * d + i];             \
+    RSi[slot * d + i] = y;                                                 \
+    if (y > s) RSs[slot * d + i] = -s; else RSy[slot * d + i] = 0.0;       \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, false, false)
+#undef ROW_BODY
         FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) SAVE_XU[8 * i + c] = X[c * d + i]; for (int c = 0; c < 2; c++) SAVE_XU[8 * i + 6 + c] = (i < NS) ? U[c * d + i] : 0.0; }
         for (int p = 0; p < KPL; p++) {
           if (lane + NT * p < K) { SAVE_L[lane + NT * p] = lam(lane).a[p]; SAVE_L[K + lane + NT * p] = ylam(lane).a[p]; }
@@ -354,39 +402,49 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       LaneVar<double, NT> rs[12];
       GLANES_BEGIN(NT)
         double dth_acc = 0.0, cth_acc = 0.0, msum = 0.0, rpm = 0.0;
-        FOR_GROUPS(g) FOR_MY_STAGES(i) {
-          double hsum = 0.0, gsum = 0.0, cz_th = 0.0;
-          if (g < 6 && !learn) { const double w = (i == N - 1) ? P.qxN[g] : P.qx[g]; hsum = 2.0 * w; gsum = 2.0 * w * (X[g * d + i] - (g == 3 ? VREF[i] : 0.0)); }
-          FOR_ROWS(q, g, i) {
-            const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
-            const double is = y * isy;
-            double dj = y * is;
-            const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
-            double t = dj * rp;
-            if (polishing) {
-              const bool act = s < 0.0;
-              dj = act ? LMPC_PRHO : 0.0;
-              t = act ? y + LMPC_PRHO * (rp - s) : 0.0;
-            } else if (pass) {
-              // second-order term from the affine step: ds_a * dy_a with dy_a = -y - y ds_a / s
-              const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
-              const double dya_ = -y - dj * dsa;
-              t += (smu - csc * dsa * dya_) * is;
-            } else { msum += s * y; rpm = fmax(rpm, fabs(rp)); }
-            hsum += dj; gsum += q.sg * t;
-            if (q.rtype == 1 && soft) { cz_th += -q.sg * dj; dth_acc += dj; cth_acc += -t; }
-          }
-          if (g < 6) {
-            if (!pass) HX[g * d + i] = hsum;
-            CZX[g * d + i] = gsum;
-            if (g == 1) CZTH[i] = cz_th;
-          } else if (i <= N - 2) {
-            // GUD rows: 0,1 dub  2,3 tub  4,5 dd  6,7 td
-            const int c = (g - 6) & 1, base = (g < 8) ? 0 : 4;
-            if (!pass) GUD[(base + c) * d + i] = hsum;
-            GUD[(base + 2 + c) * d + i] = gsum;
-          }
-        }
+        const double thq = soft ? th : 0.0, dthaq = soft ? dtha : 0.0;
+#undef ROW_GBEGIN
+#undef ROW_GEND
+#define ROW_GBEGIN                                                         \
+  double hsum = 0.0, gsum = 0.0, cz_th = 0.0;                              \
+  if (g < 6 && !learn) { const double w = (i == N - 1) ? P.qxN[g] : P.qx[g]; hsum = 2.0 * w; gsum = 2.0 * w * (v - (g == 3 ? VREF[i] : 0.0)); }
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = RSs[slot * d + i], y = RSy[slot * d + i], isy = RSi[slot * d + i]; \
+    const double is = y * isy;                                             \
+    double dj = y * is;                                                    \
+    const double rp = (sg * v - (isb ? thq : 0.0)) + s - bnd;              \
+    double t = dj * rp;                                                    \
+    if (polishing) {                                                       \
+      const bool act = s < 0.0;                                            \
+      dj = act ? LMPC_PRHO : 0.0;                                          \
+      t = act ? y + LMPC_PRHO * (rp - s) : 0.0;                            \
+    } else if (pass) {                                                     \
+      /* second-order term from the affine step: ds_a * dy_a with dy_a = -y - y ds_a / s */ \
+      const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));            \
+      const double dya_ = -y - dj * dsa;                                   \
+      t += (smu - csc * dsa * dya_) * is;                                  \
+    } else { msum += s * y; rpm = fmax(rpm, fabs(rp)); }                   \
+    hsum += dj; gsum += sg * t;                                            \
+    if (isb && soft) { cz_th += -sg * dj; dth_acc += dj; cth_acc += -t; }  \
+  }
+#define ROW_GEND                                                           \
+  if (g < 6) {                                                             \
+    if (!pass) HX[g * d + i] = hsum;                                       \
+    CZX[g * d + i] = gsum;                                                 \
+    if (g == 1) CZTH[i] = cz_th;                                           \
+  } else {                                                                 \
+    /* GUD rows: 0,1 dub  2,3 tub  4,5 dd  6,7 td */                       \
+    const int cc_ = (g - 6) & 1, base_ = (g < 8) ? 0 : 4;                  \
+    if (!pass) GUD[(base_ + cc_) * d + i] = hsum;                          \
+    GUD[(base_ + 2 + cc_) * d + i] = gsum;                                 \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, pass != 0, false)
+#undef ROW_BODY
+#undef ROW_GBEGIN
+#undef ROW_GEND
+#define ROW_GBEGIN
+#define ROW_GEND
         double lsum = 0.0, sg6[6] = {0, 0, 0, 0, 0, 0}, nbasic = 0.0;
         if (!pass) for (int p = 0; p < KPL; p++) {
           const double l = lam(lane).a[p];
@@ -906,15 +964,32 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 
       // ---------- terminal directions (lambda), sigma_b dual
       if (learn) {
+        // e = pT + PT dx_N (6), q = q0 - Xq dx_N (NQ): one lane per entry, then every lane reads the 11 values
+        GLANES_BEGIN(NT)
+          if (lane < 6 + LMPC_NQ) {
+            double dxn[6];
+#pragma unroll
+            for (int b = 0; b < 6; b++) dxn[b] = (b < nh) ? DXo[P.hidx[b] * d + N - 1] : 0.0;
+            double s2;
+            if (lane < 6) {
+              s2 = TB[TB_PTV + lane];
+#pragma unroll
+              for (int b = 0; b < 6; b++) if (b < nh) s2 += TB[TB_PT + 6 * lane + b] * dxn[b];
+              if (lane >= nh) s2 = 0.0;
+            } else {
+              const int q = lane - 6;
+              s2 = TB[TB_Q0 + q];
+#pragma unroll
+              for (int a = 0; a < 6; a++) if (a < nh) s2 -= TB[TB_XQ + q * 6 + a] * dxn[a];
+            }
+            TB[TB_EQ + lane] = s2;
+          }
+        GLANES_END(NW)
         double e[6], qv[LMPC_NQ];
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-          double s2 = 0.0;
-          if (a < nh) { s2 = TB[TB_PTV + a]; for (int b = 0; b < nh; b++) s2 += TB[TB_PT + 6 * a + b] * DXo[P.hidx[b] * d + N - 1]; }
-          e[a] = s2;
-        }
+        for (int a = 0; a < 6; a++) e[a] = TB[TB_EQ + a];
 #pragma unroll
-        for (int q = 0; q < LMPC_NQ; q++) { double s2 = TB[TB_Q0 + q]; for (int a = 0; a < nh; a++) s2 -= TB[TB_XQ + q * 6 + a] * DXo[P.hidx[a] * d + N - 1]; qv[q] = s2; }
+        for (int q = 0; q < LMPC_NQ; q++) qv[q] = TB[TB_EQ + 6 + q];
         const double nu = qv[0];
         GLANES_BEGIN(NT)
 #pragma unroll
@@ -952,19 +1027,23 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       LaneVar<double, NT> ra[2];
       GLANES_BEGIN(NT)
         double rmax = 0.0, cross = 0.0;   // rmax = max over rows of (-ds/s, -dy/y)  ->  amax = 1 / rmax
-        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
-          const double is = y * isy, iy = s * isy;
-          const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
-          const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
-          const double dya_ = -y - y * is * dsa;
-          double ds = dsa, dy = dya_;
-          if (pass) {
-            ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
-            dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
-          } else cross += dsa * dya_;
-          rmax = fmax(rmax, fmax(-ds * is, -dy * iy));
-        }
+        const double thq = soft ? th : 0.0, dthaq = soft ? dtha : 0.0, dthq = soft ? dth : 0.0;
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = RSs[slot * d + i], y = RSy[slot * d + i], isy = RSi[slot * d + i]; \
+    const double is = y * isy, iy = s * isy;                               \
+    const double rp = (sg * v - (isb ? thq : 0.0)) + s - bnd;              \
+    const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));              \
+    const double dya_ = -y - y * is * dsa;                                 \
+    double ds = dsa, dy = dya_;                                            \
+    if (pass) {                                                            \
+      ds = -rp - (sg * vf - (isb ? dthq : 0.0));                           \
+      dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;              \
+    } else cross += dsa * dya_;                                            \
+    rmax = fmax(rmax, fmax(-ds * is, -dy * iy));                           \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, pass != 0)
+#undef ROW_BODY
 #pragma unroll
         for (int p = 0; p < KPL; p++) {
           const int k = lane + NT * p;
@@ -1028,19 +1107,23 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       LaneVar<double, NT> rc2[3];
       GLANES_BEGIN(NT)
         double ch = 0.0, viol = 0.0, dym = 0.0;
-        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-          const double s = RSs[q.slot * d + i];
-          const double r = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) - row_bound(P, q, i, BL, BR);
-          bool act = s < 0.0;
-          if (act) {
-            const double yo = RSy[q.slot * d + i];
-            const double yn = yo + LMPC_PRHO * r;
-            dym = fmax(dym, fabs(LMPC_PRHO * r) / (1.0 + fabs(yo)));
-            if (yn < -dtol * fmax(1.0, fabs(yn))) { act = false; RSs[q.slot * d + i] = -s; RSy[q.slot * d + i] = 0.0; ch += 1.0; }
-            else RSy[q.slot * d + i] = yn;
-          } else if (r > ftol) { act = true; RSs[q.slot * d + i] = -s; ch += 1.0; }
-          if (!act && r > 1e-9) viol += 1.0;
-        }
+        const double thq = soft ? th : 0.0;
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = RSs[slot * d + i];                                    \
+    const double r = (sg * v - (isb ? thq : 0.0)) - bnd;                   \
+    bool act = s < 0.0;                                                    \
+    if (act) {                                                             \
+      const double yo = RSy[slot * d + i];                                 \
+      const double yn = yo + LMPC_PRHO * r;                                \
+      dym = fmax(dym, fabs(LMPC_PRHO * r) / (1.0 + fabs(yo)));             \
+      if (yn < -dtol * fmax(1.0, fabs(yn))) { act = false; RSs[slot * d + i] = -s; RSy[slot * d + i] = 0.0; ch += 1.0; } \
+      else RSy[slot * d + i] = yn;                                         \
+    } else if (r > ftol) { act = true; RSs[slot * d + i] = -s; ch += 1.0; } \
+    if (!act && r > 1e-9) viol += 1.0;                                     \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, false, false)
+#undef ROW_BODY
         for (int p = 0; p < KPL; p++) {
           const int k = lane + NT * p;
           if (k < K) {
@@ -1072,10 +1155,13 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       // no consistent active set: restore the interior-point iterate; the first time keep iterating with a
       // 100x tighter tolerance and try once more, the second time return the interior-point solution
       GLANES_BEGIN(NT)
-        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-          const double s = fabs(RSs[q.slot * d + i]), y = RSi[q.slot * d + i];
-          RSs[q.slot * d + i] = s; RSy[q.slot * d + i] = y; RSi[q.slot * d + i] = 1.0 / (s * y);
-        }
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = fabs(RSs[slot * d + i]), y = RSi[slot * d + i];       \
+    RSs[slot * d + i] = s; RSy[slot * d + i] = y; RSi[slot * d + i] = 1.0 / (s * y); \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, false, false)
+#undef ROW_BODY
         FOR_MY_STAGES(i) { for (int c = 0; c < 6; c++) X[c * d + i] = SAVE_XU[8 * i + c]; if (i < NS) for (int c = 0; c < 2; c++) U[c * d + i] = SAVE_XU[8 * i + 6 + c]; }
         for (int p = 0; p < KPL; p++) if (lane + NT * p < K) { lam(lane).a[p] = SAVE_L[lane + NT * p]; ylam(lane).a[p] = SAVE_L[K + lane + NT * p]; }
       GLANES_END(NW)
@@ -1091,17 +1177,21 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       const double smu = sigma * mu;
       LaneVar<double, NT> rstep;
       GLANES_BEGIN(NT)
-        FOR_GROUPS(g) FOR_MY_STAGES(i) FOR_ROWS(q, g, i) {
-          const double s = RSs[q.slot * d + i], y = RSy[q.slot * d + i], isy = RSi[q.slot * d + i];
-          const double is = y * isy;
-          const double rp = row_val(q, i, d, X, U, IT, soft ? th : 0.0, uic) + s - row_bound(P, q, i, BL, BR);
-          const double dsa = -rp - row_val(q, i, d, DXA, DUA, IT, soft ? dtha : 0.0, zero2);
-          const double dya_ = -y - y * is * dsa;
-          const double ds = -rp - row_val(q, i, d, DXF, DUF, IT, soft ? dth : 0.0, zero2);
-          const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;
-          const double sn = s + alpha * ds, yn = y + alpha * dy;
-          RSs[q.slot * d + i] = sn; RSy[q.slot * d + i] = yn; RSi[q.slot * d + i] = 1.0 / (sn * yn);
-        }
+        const double thq = soft ? th : 0.0, dthaq = soft ? dtha : 0.0, dthq = soft ? dth : 0.0;
+#define ROW_BODY                                                           \
+  {                                                                        \
+    const double s = RSs[slot * d + i], y = RSy[slot * d + i], isy = RSi[slot * d + i]; \
+    const double is = y * isy;                                             \
+    const double rp = (sg * v - (isb ? thq : 0.0)) + s - bnd;              \
+    const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));              \
+    const double dya_ = -y - y * is * dsa;                                 \
+    const double ds = -rp - (sg * vf - (isb ? dthq : 0.0));                \
+    const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;   \
+    const double sn = s + alpha * ds, yn = y + alpha * dy;                 \
+    RSs[slot * d + i] = sn; RSy[slot * d + i] = yn; RSi[slot * d + i] = 1.0 / (sn * yn); \
+  }
+        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, true)
+#undef ROW_BODY
 #pragma unroll
         for (int p = 0; p < KPL; p++) {
           const int k = lane + NT * p;
@@ -1191,4 +1281,6 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     for (int a = 0; a < nh; a++) { const int c = P.hidx[a]; const double sh = X[c * d + N - 1] - in.cen[c] - ro[1 + a](0); cost += P.chs[c] * sh * sh; }
   LANE0_ONLY(if (out.cost) *out.cost = cost; *out.status = status; *out.iters = it;)
 #undef LO
+#undef ROW_GBEGIN
+#undef ROW_GEND
 }

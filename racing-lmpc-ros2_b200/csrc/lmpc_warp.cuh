@@ -16,6 +16,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#define LMPC_UNROLL _Pragma("unroll")   // usable inside macros
+#define LMPC_NOUNROLL _Pragma("unroll 1")
+
 #if defined(LMPC_EMULATE)
 // ------------------------------------------------------------------ lane-loop emulation (tests)
 #define LMPC_DEV static inline
