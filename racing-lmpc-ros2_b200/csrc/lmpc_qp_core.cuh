@@ -245,7 +245,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   double* BL = sm + LO(oBL); double* BR = sm + LO(oBR); double* VREF = sm + LO(oVREF); double* IT = sm + LO(oIT);
   double* PM = sm + LO(oPM); double* L1 = sm + LO(oL1); double* LTH = sm + LO(oLTH);
   double* MAB = sm + LO(oMAB); double* AXBW = sm + LO(oAXBW); double* YY = sm + LO(oYY);
-  double* RED = sm + LO(oRED);
+  // scratch of the group reductions: one warp uses the (then idle) YY block of the sweep, NW warps their own NW x NRED area
+  double* RED = (NW == 1) ? (sm + LO(oYY)) : (sm + LO(oRED));
   double* TB = sm + LO(oTERM);
   const double sfloor = 1e-2, mu0 = 0.1, th0 = 0.01;
 
@@ -399,7 +400,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     for (int pass = 0; pass < (polishing ? 1 : 2) && !fail; pass++) {
       const double smu = sigma * mu;
       // ---------- rows -> per-stage Hessian / gradient pieces (one lane per (group, stage))
-      LaneVar<double, NT> rs[12];
+      LaneVar<double, NT> rs[11], rmx;
       GLANES_BEGIN(NT)
         double dth_acc = 0.0, cth_acc = 0.0, msum = 0.0, rpm = 0.0;
         const double thq = soft ? th : 0.0, dthaq = soft ? dtha : 0.0;
@@ -452,19 +453,21 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           if (lane + NT * p < K) for (int a = 0; a < 6; a++) sg6[a] += ST[6 * (lane + NT * p) + a] * l;
           if (polishing && lane + NT * p < K && !pnb(lane).a[p]) nbasic += 1.0;
         }
-        rs[0](lane) = dth_acc; rs[1](lane) = cth_acc; rs[2](lane) = msum; rs[3](lane) = rpm; rs[4](lane) = lsum;
+        rs[0](lane) = dth_acc; rs[1](lane) = cth_acc; rs[2](lane) = msum; rs[3](lane) = nbasic; rs[4](lane) = lsum;
         for (int a = 0; a < 6; a++) rs[5 + a](lane) = sg6[a];
-        rs[11](lane) = nbasic;
+        rmx(lane) = rpm;
       GLANES_END(NW)
-      {
-        const int ops[12] = {LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_MAX, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM,
-                             LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM};
-        group_reduce<NW, 12>(rs, ops, RED);
+      if (pass == 0) {   // the sums of the iterate (11) + the largest primal residual; the corrector pass only needs the two theta sums
+        group_reduce_sum<NW, 11>(rs, RED);
+        group_max<NW>(rmx, RED);
+      } else {
+        LaneVar<double, NT>(&r2)[2] = reinterpret_cast<LaneVar<double, NT>(&)[2]>(rs[0]);
+        group_reduce_sum<NW, 2>(r2, RED);
       }
       double Dthth = rs[0](0), cth = rs[1](0);
       if (!pass) {
         mu = (rs[2](0) + (soft ? th * yth : 0.0)) * inv_m;
-        rpn = rs[3](0);
+        rpn = rmx(0);
         rnu = learn ? rs[4](0) - 1.0 : 0.0;
         if (learn) for (int a = 0; a < 6; a++) sig[a] = (a < nh) ? X[P.hidx[a] * d + N - 1] - in.cen[P.hidx[a]] - rs[5 + a](0) : 0.0;
         if (!polishing && mu < tol_mu && rpn < tol_mu && rho_d * R0 < tol_mu && fabs(rnu) < tol_mu) {
@@ -477,7 +480,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           polishing = 1; classified = 0; restart = true; break;
         }
         if (!polishing) { mu_m3 = mu_m2; mu_m2 = mu_m1; mu_m1 = mu; }
-        if (polishing && learn && (rs[11](0) > LMPC_MB + 0.5 || rs[11](0) < 0.5)) { fail = true; break; }   // at most MB free columns
+        if (polishing && learn && (rs[3](0) > LMPC_MB + 0.5 || rs[3](0) < 0.5)) { fail = true; break; }   // at most MB free columns
       }
       double corr_th = 0.0;
       if (soft) {
@@ -574,9 +577,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         if (it == 0 && pass == 0) { LANE0_ONLY(if (LMPC_TRACE_COND) printf("  pre-reduce lane0: W00 %.9e a0 %.9e om1 %.9e | St %.6e %.6e %.6e om %.6e %.6e isB %d %d %d K %d\n", rt[7](0), rt[28](0), rt[34](0), ST[0], ST[6 * NT], ST[12 * NT], omg_(0).a[0], omg_(0).a[1], isB(0).a[0], isB(0).a[1], isB(0).a[2], K);) }
 #endif
         if (pass == 0) {   // values that only change with the factorisation are reduced in pass 0 only
-          int ops[LMPC_NRED];
-          for (int q = 0; q < LMPC_NRED; q++) ops[q] = LMPC_RED_SUM;
-          group_reduce<NW, LMPC_NRED>(rt, ops, RED);
+          group_reduce_sum<NW, LMPC_NRED>(rt, RED);
         } else {
           LaneVar<double, NT>(&r7)[7] = reinterpret_cast<LaneVar<double, NT>(&)[7]>(rt[0]);
           const int ops[7] = {LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM, LMPC_RED_SUM};

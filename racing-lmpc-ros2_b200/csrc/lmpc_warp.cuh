@@ -102,6 +102,12 @@ LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV
     for (int l = 0; l < 32 * NW; ++l) x[q].v[l] = r;
   }
 }
+template <int NW, int NV>
+LMPC_DEV void group_reduce_sum(LaneVar<double, 32 * NW> (&x)[NV], double* scratch) {
+  int op[NV];
+  for (int q = 0; q < NV; q++) op[q] = LMPC_RED_SUM;
+  group_reduce<NW, NV>(x, op, scratch);
+}
 // arg-max / arg-min on (value, index), ties to the lowest index
 template <int NW>
 LMPC_DEV void group_argbest(LaneVar<double, 32 * NW>& val, LaneVar<int, 32 * NW>& idx, bool want_max, double* /*scratch*/) {
@@ -120,6 +126,42 @@ LMPC_DEV void group_or(LaneVar<int, 32 * NW>& x, double* /*scratch*/) {
 }
 #else
 LMPC_DEV double shfl_xor_f64(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
+// Sums only, one warp: the butterfly costs 5 NV exchange steps.  Here every exchange step HALVES the slots a lane is
+// responsible for (at offset 16 the lanes with bit 4 clear keep slots 0..15 and hand slots 16..31 to their partner, and
+// so on): 31 steps per 32 values, lane L ends with the total of slot L, which goes through `scratch` (NV doubles of
+// shared memory) to every lane.  The additions are the butterfly's own (same pairs, same order; a + b is commutative),
+// so the totals are bit-identical to it.  A remainder of fewer than 8 values takes the butterfly.
+template <int NV>
+LMPC_DEV void warp_reduce_scatter_sum(LaneVar<double, 32> (&x)[NV], double* scratch) {
+  const unsigned lane = threadIdx.x & 31u;
+  constexpr int NFULL = (NV % 32 >= 8) ? NV : (NV / 32) * 32;   // values that go through the halving scheme
+#pragma unroll
+  for (int c0 = 0; c0 < NFULL; c0 += 32) {
+    double v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = (c0 + j < NFULL) ? x[c0 + j].v : 0.0;
+#pragma unroll
+    for (int H = 16; H >= 1; H >>= 1) {
+      const bool hi = (lane & (unsigned)H) != 0u;
+#pragma unroll
+      for (int j = 0; j < H; j++) {
+        const double keep = hi ? v[j + H] : v[j];
+        const double send = hi ? v[j] : v[j + H];
+        v[j] = keep + shfl_xor_f64(send, H);
+      }
+    }
+    if (c0 + (int)lane < NFULL) scratch[c0 + lane] = v[0];
+  }
+#pragma unroll
+  for (int q = NFULL; q < NV; q++) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) x[q].v = x[q].v + shfl_xor_f64(x[q].v, off);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NFULL; q++) x[q].v = scratch[q];
+  __syncwarp();
+}
 template <int NW, int NV>
 LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV], double* scratch) {
 #pragma unroll
@@ -142,6 +184,18 @@ LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV
       x[q].v = r;
     }
     __syncthreads();
+  }
+}
+// all-SUM form: one warp with shared-memory scratch takes the halving scheme, everything else the general path
+template <int NW, int NV>
+LMPC_DEV void group_reduce_sum(LaneVar<double, 32 * NW> (&x)[NV], double* scratch) {
+  if constexpr (NW == 1 && NV >= 8) {
+    warp_reduce_scatter_sum<NV>(x, scratch);
+  } else {
+    int op[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) op[q] = LMPC_RED_SUM;
+    group_reduce<NW, NV>(x, op, scratch);
   }
 }
 template <int NW>

@@ -22,5 +22,7 @@ for Bn in [int(a) for a in sys.argv[1:]] or [1024]:
         for _ in range(10): mpc.solve(dev, out)
     (a, b, c), n = mpc.kernel_ms()
     st = out["status"].cpu().numpy(); it = out["iters"].cpu().numpy()
-    print(f"NW={os.environ.get('LMPC_WARPS_PER_INSTANCE','1')} B={Bn}: lin {a/n*1e3:.0f} us, ss {b/n*1e3:.0f} us, qp {c/n*1e3:.0f} us -> {Bn/((a+b+c)/n)*1e3:.3e} steps/s; solved {np.mean(st==0):.4f} iters mean {it.mean():.2f} max {it.max()}", flush=True)
+    import hashlib
+    chk = hashlib.sha1(out["X_optm"].cpu().numpy().tobytes() + out["U_optm"].cpu().numpy().tobytes()).hexdigest()[:12]
+    print(f"NW={os.environ.get('LMPC_WARPS_PER_INSTANCE','1')} B={Bn}: lin {a/n*1e3:.0f} us, ss {b/n*1e3:.0f} us, qp {c/n*1e3:.0f} us -> {Bn/((a+b+c)/n)*1e3:.3e} steps/s; solved {np.mean(st==0):.4f} iters mean {it.mean():.2f} max {it.max()} sha {chk}", flush=True)
     mpc.set_stream(None); mpc.close()
