@@ -50,6 +50,10 @@ struct lmpc_handle {
   int device = 0;
   int max_batch = 0;
   cudaStream_t stream = nullptr;
+  // the safe-set query of a tick does not depend on the linearisation: it runs on a side stream, forked from and joined to
+  // the caller's stream with two events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int64_t launches = 0;
   // safe set: circular buffer, oldest first (boost::circular_buffer semantics, safe_set.cpp:139-151)
@@ -162,6 +166,10 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
   if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_ssj, sizeof(double) * K * B);
   if (rc == LMPC_OK) rc = dev_reserve(h, h->ws_qpscr, sizeof(double) * (size_t)LMPC_QP_SCRATCH(N, K) * B);
   (void)N;
+  if (rc == LMPC_OK && (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
+    rc = LMPC_ERR_CUDA;
   if (rc != LMPC_OK) { lmpc_destroy(h); return rc; }
   *out = h;
   return LMPC_OK;
@@ -171,6 +179,9 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (!h) return LMPC_ERR_INVALID;
   cudaSetDevice(h->device);
   for (auto& e : h->tev) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->reg_slab, &h->ws_reg, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
@@ -714,6 +725,24 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   double* abg = (double*)h->ws_abg.p; double* cen = (double*)h->ws_cen.p;
   cudaEvent_t* tev = (h->timing && !h->tev.empty()) ? &h->tev[4 * (size_t)(h->tcount % kTimingRing)] : nullptr;
   if (tev) CK(cudaEventRecord(tev[0], h->stream));
+  // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272).  Independent of K1:
+  // forked onto the side stream here, joined before K3.
+  const bool fork_ss = learn && first;
+  if (fork_ss) {
+    LmpcLapTable tab;
+    int rc = make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
+    if (rc != LMPC_OK) return rc;
+    *ss_count_io = tab.count;
+    if (tab.n_used > 0) {
+      CK(cudaEventRecord(h->ev_fork, h->stream));
+      CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      const int warps = B * tab.n_used, threads = 128, blocks = (warps * 32 + threads - 1) / threads;
+      lmpc_ss_query_tick_kernel<<<blocks, threads, 0, h->side>>>(tab, B, (int)N, io.din[0], X_lin, io.din[9], (int)K, (int)K, io.ssx, io.ssj);
+      h->launches++;
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(h->ev_join, h->side));
+    }
+  }
   // K1: linearise
   {
     const int n = B * (int)NS, threads = 64, blocks = (n + threads - 1) / threads;
@@ -734,15 +763,7 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
     }
   }
   if (tev) CK(cudaEventRecord(tev[1], h->stream));
-  // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272)
-  if (learn && first) {
-    LmpcLapTable tab;
-    int rc = make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
-    if (rc != LMPC_OK) return rc;
-    rc = launch_ss_query(h, tab, B, cen, 6, (int)K, (int)K, io.ssx, io.ssj);
-    if (rc != LMPC_OK) return rc;
-    *ss_count_io = tab.count;
-  }
+  if (fork_ss) CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // a never-recorded event is complete: no-op when nothing was forked
   if (tev) CK(cudaEventRecord(tev[2], h->stream));
   // K3: QP
   LmpcQpBatch a;

@@ -94,6 +94,20 @@ __global__ void lmpc_ss_query_kernel(LmpcLapTable tab, int B, const double* __re
                      j == tab.n_used - 1, tab.count, pad_to);
 }
 
+// ---- K2 inside the tick: the query point is the abscissa-aligned X_ref[:, N-1] (racing_mpc.cpp:219-223,249-255), formed
+// here from the tick's inputs so that the kernel does not depend on K1 and can run beside it on a second stream
+__global__ void lmpc_ss_query_tick_kernel(LmpcLapTable tab, int B, int N, const double* __restrict__ x_ic,
+                                          const double* __restrict__ X_ref, const double* __restrict__ total_length,
+                                          int max_total, int pad_to, double* __restrict__ ss_x, double* __restrict__ ss_j) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= B * tab.n_used) return;
+  const int b = w / tab.n_used, j = w - b * tab.n_used;
+  const double* xe = X_ref + (6 * (size_t)N) * b + 6 * (N - 1);
+  const double qs = lmpc_align_abscissa(xe[0], x_ic[6 * (size_t)b], total_length[b]), qe = xe[1];
+  lmpc_ss_query_warp(tab.lap[j], qs, qe, max_total, ss_x + (6 * (size_t)pad_to) * b, ss_j + (size_t)pad_to * b,
+                     j == tab.n_used - 1, tab.count, pad_to);
+}
+
 // ---- SQP to convergence (the B200 counterpart of the reference's one-off full-dynamics IPOPT solve,
 // racing_mpc.cpp:67-84,162-166): the tick's QP re-linearised at its own solution.  One thread per instance.
 // init: linearisation point <- (abscissa-aligned X_ref, U_ref)
