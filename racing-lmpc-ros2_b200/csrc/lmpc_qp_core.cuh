@@ -817,7 +817,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               const LmpcD2* col = reinterpret_cast<const LmpcD2*>(A + 6 * c);   // [A | B] is contiguous: column c of B follows A's six columns
               const double* prow = PM + 8 * (r + ((r >= 6) ? 2 : 0));
               const LmpcD2* pr2 = reinterpret_cast<const LmpcD2*>(prow);
-              double a = (c < 6) ? 0.0 : prow[c];
+              const double pc = prow[c];   // unconditional load + select: no branch around it
+              double a = (c < 6) ? 0.0 : pc;
 #pragma unroll
               for (int k = 0; k < 3; k++) { const LmpcD2 pv = pr2[k], cv = col[k]; a += pv.x * cv.x; a += pv.y * cv.y; }
               MAB[8 * r + c] = a;
@@ -831,14 +832,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
               if (NT > 64 && lane >= 64) break;
               const LmpcD2* ar = reinterpret_cast<const LmpcD2*>(A + 6 * r);
-              double a = (r >= 6 && c >= 6) ? PM[8 * r + c] : 0.0;
+              double a = 0.0;
 #pragma unroll
-              for (int k = 0; k < 3; k++) {
-                const LmpcD2 av = ar[k];
-                if (r >= 6 && c >= 6) {   // same order of additions as the single-expression form
-                  a += av.x * MAB[8 * (2 * k) + c] + PM[8 * (2 * k) + r] * B[2 * k + 6 * (c - 6)];
-                  a += av.y * MAB[8 * (2 * k + 1) + c] + PM[8 * (2 * k + 1) + r] * B[2 * k + 1 + 6 * (c - 6)];
-                } else { a += av.x * MAB[8 * (2 * k) + c]; a += av.y * MAB[8 * (2 * k + 1) + c]; }
+              for (int k = 0; k < 3; k++) { const LmpcD2 av = ar[k]; a += av.x * MAB[8 * (2 * k) + c]; a += av.y * MAB[8 * (2 * k + 1) + c]; }
+              if (r >= 6 && c >= 6) {   // the four Yuu entries: + M_uu + M_ux B (one divergent tail instead of one per term)
+                double e = PM[8 * r + c];
+#pragma unroll
+                for (int k = 0; k < 6; k++) e += PM[8 * k + r] * B[k + 6 * (c - 6)];
+                a += e;
               }
               // rows 6,7 of Qzw = -E are parked in the unused (r >= 6, c < 2) slots so that phase c reads
               // Qzw[r][j] = QZ(r, j) without selecting between Yxu and -E
@@ -878,31 +879,27 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
             for (int rd = 0; rd < LMPC_R8; rd++) {
               const int c = lane & 7, r = ((lane >> 3) & (LMPC_L8 - 1)) + LMPC_L8 * rd;
               if (NT > 64 && lane >= 64) break;
-              double pv;
-              if (r >= 6 && c >= 6) {
-                pv = (r == 6 && c == 6) ? p00 : ((r == 7 && c == 7) ? p11 : p01s);
-              } else {
-                const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1], qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
-                double qzz = 0.0;
-                if (r < 6 && c < 6) qzz = YY[8 * r + c] + (r == c ? HX[r * d + i] : 0.0);
-                pv = qzz - (qr0 * (i0 * qc0 + i1 * qc1) + qr1 * (i1 * qc0 + i2_ * qc1));
-              }
+              // every load is unconditional (all addresses are valid), the cases are selects: no branches in this phase
+              const double qr0 = YY[QZ0(r)], qr1 = YY[QZ0(r) + 1], qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
+              const double yv = YY[8 * r + c], hx = HX[(r < 6 ? r : 0) * d + i];
+              const double qzz = (r < 6 && c < 6) ? yv + (r == c ? hx : 0.0) : 0.0;
+              double pv = qzz - (qr0 * (i0 * qc0 + i1 * qc1) + qr1 * (i1 * qc0 + i2_ * qc1));
+              if (r >= 6 && c >= 6) pv = (r == 6 && c == 6) ? p00 : ((r == 7 && c == 7) ? p11 : p01s);
               PM[8 * r + c] = pv;
             }
             if (lane < 32) {
               const int c = lane & 7, j = (lane >> 3) & 3;
               const double qc0 = YY[QZ0(c)], qc1 = YY[QZ0(c) + 1];
-              if (j < 2) {            // Kz (2x8): Kz[j][c] = Sinv[j][:] . Qzw[c][:]
-                fac[8 * j + c] = (j == 0) ? (i0 * qc0 + i1 * qc1) : (i1 * qc0 + i2_ * qc1);
-              } else {                // l1 and lth:  l = Cz' - Qzw kff
-                const bool isth = (j == 3);
-                const double kk0 = isth ? kt_0 : k1_0, kk1 = isth ? kt_1 : k1_1;
-                double cz;
-                if (isth) cz = (c == 1) ? CZTH[i] : 0.0;
-                else cz = (c < 6) ? CZX[c * d + i] : ((c == 6) ? -ev0 : -ev1);
-                const double ax = (c < 6) ? AXBW[(isth ? 8 : 0) + c] : 0.0;
-                (isth ? LTH : L1)[c] = cz + ax - (qc0 * kk0 + qc1 * kk1);
-              }
+              const bool isth = (j == 3);
+              // rows 0,1: Kz (2x8): Kz[j][c] = Sinv[j][:] . Qzw[c][:];  rows 2,3: l1 and lth:  l = Cz' - Qzw kff
+              const double kz = (j == 0) ? (i0 * qc0 + i1 * qc1) : (i1 * qc0 + i2_ * qc1);
+              const double kk0 = isth ? kt_0 : k1_0, kk1 = isth ? kt_1 : k1_1;
+              const double czth = CZTH[i], czx = CZX[(c < 6 ? c : 0) * d + i], axv = AXBW[(isth ? 8 : 0) + c];
+              const double cz = isth ? (c == 1 ? czth : 0.0) : (c < 6 ? czx : (c == 6 ? -ev0 : -ev1));
+              const double ax = (c < 6) ? axv : 0.0;
+              const double lv = cz + ax - (qc0 * kk0 + qc1 * kk1);
+              double* dst = (j < 2) ? (fac + 8 * j + c) : ((isth ? LTH : L1) + c);
+              *dst = (j < 2) ? kz : lv;
             }
             if (lane == 0) { fac[16] = i0; fac[17] = i1; fac[18] = i2_; kf[0] = k1_0; kf[1] = k1_1; kf[2] = kt_0; kf[3] = kt_1; kf[4] = cwt_0; kf[5] = cwt_1; }
           GLANES_END(NW)
