@@ -404,6 +404,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       GLANES_BEGIN(NT)
         double dth_acc = 0.0, cth_acc = 0.0, msum = 0.0, rpm = 0.0;
         const double thq = soft ? th : 0.0, dthaq = soft ? dtha : 0.0;
+        const bool ip0 = !pass && !polishing;   // interior-point predictor pass: complementarity and residual are measured here
 #undef ROW_GBEGIN
 #undef ROW_GEND
 #define ROW_GBEGIN                                                         \
@@ -411,21 +412,20 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   if (g < 6 && !learn) { const double w = (i == N - 1) ? P.qxN[g] : P.qx[g]; hsum = 2.0 * w; gsum = 2.0 * w * (v - (g == 3 ? VREF[i] : 0.0)); }
 #define ROW_BODY                                                           \
   {                                                                        \
+    /* straight-line: the three variants (predictor, corrector with the second-order term of the affine step   \
+       ds_a * dy_a, dy_a = -y - y ds_a / s, and the polish) are selects on group-uniform flags, not branches */ \
     const double s = RSs[slot * d + i], y = RSy[slot * d + i], isy = RSi[slot * d + i]; \
     const double is = y * isy;                                             \
-    double dj = y * is;                                                    \
+    const double dj0 = y * is;                                             \
     const double rp = (sg * v - (isb ? thq : 0.0)) + s - bnd;              \
-    double t = dj * rp;                                                    \
-    if (polishing) {                                                       \
-      const bool act = s < 0.0;                                            \
-      dj = act ? LMPC_PRHO : 0.0;                                          \
-      t = act ? y + LMPC_PRHO * (rp - s) : 0.0;                            \
-    } else if (pass) {                                                     \
-      /* second-order term from the affine step: ds_a * dy_a with dy_a = -y - y ds_a / s */ \
-      const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));            \
-      const double dya_ = -y - dj * dsa;                                   \
-      t += (smu - csc * dsa * dya_) * is;                                  \
-    } else { msum += s * y; rpm = fmax(rpm, fabs(rp)); }                   \
+    const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));              \
+    const double dya_ = -y - dj0 * dsa;                                    \
+    const double tip = dj0 * rp + (pass ? (smu - csc * dsa * dya_) * is : 0.0); \
+    const bool act = s < 0.0;                                              \
+    const double dj = polishing ? (act ? LMPC_PRHO : 0.0) : dj0;           \
+    const double t = polishing ? (act ? y + LMPC_PRHO * (rp - s) : 0.0) : tip; \
+    msum += ip0 ? s * y : 0.0;                                             \
+    rpm = ip0 ? fmax(rpm, fabs(rp)) : rpm;                                 \
     hsum += dj; gsum += sg * t;                                            \
     if (isb && soft) { cz_th += -sg * dj; dth_acc += dj; cth_acc += -t; }  \
   }
@@ -914,13 +914,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           Pi1th -= kf[4] * k0 + kf[5] * k1;
           LaneVar<double, NT> newl;
           GLANES_BEGIN(NT)
-            if (lane < 8) {
-              const int r = lane;
-              double a = (r < 6) ? CZX[r * d + i] : ((r == 6) ? -ev0 : -ev1);
-              if (r < 6) {
+            {   // every lane computes row (lane & 7) without branches; lanes 0..7 store in the next phase
+              const int r = lane & 7, r6 = (r < 6) ? r : 0;
+              const double czx = CZX[r6 * d + i];
+              const double a0 = (r < 6) ? czx : ((r == 6) ? -ev0 : -ev1);
+              double a2 = a0;
 #pragma unroll
-                for (int k = 0; k < 6; k++) a += A[k + 6 * r] * L1[k];
-              }
+              for (int k = 0; k < 6; k++) a2 += A[k + 6 * r6] * L1[k];
+              double a = (r < 6) ? a2 : a0;
               a -= fac[r] * cw0 + fac[8 + r] * cw1;
               newl(lane) = a;
             }
@@ -946,17 +947,26 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         double dz[8];
 #pragma unroll
         for (int k = 0; k < 6; k++) dz[k] = DXo[k * d + i];
-        dz[6] = i ? DUo[i - 1] : 0.0; dz[7] = i ? DUo[d + i - 1] : 0.0;
+        const int im = i ? i - 1 : 0;
+        const double pu0 = DUo[im], pu1 = DUo[d + im];   // unconditional loads, then selects
+        dz[6] = i ? pu0 : 0.0; dz[7] = i ? pu1 : 0.0;
         double du0 = -kf[0] - kf[2] * dthp, du1 = -kf[1] - kf[3] * dthp;
+        const LmpcD2* f2 = reinterpret_cast<const LmpcD2*>(fac);
 #pragma unroll
-        for (int k = 0; k < 8; k++) { du0 -= fac[k] * dz[k]; du1 -= fac[8 + k] * dz[k]; }
+        for (int k = 0; k < 4; k++) {
+          const LmpcD2 fa = f2[k], fb = f2[4 + k];
+          du0 -= fa.x * dz[2 * k]; du1 -= fb.x * dz[2 * k];
+          du0 -= fa.y * dz[2 * k + 1]; du1 -= fb.y * dz[2 * k + 1];
+        }
         GLANES_BEGIN(NT)
-          if (lane < 6) {
-            double a = B[lane] * du0 + B[6 + lane] * du1;
+          {
+            const int l6 = (lane < 6) ? lane : 0;   // lanes >= 6 repeat row 0 and store nothing
+            double a = B[l6] * du0 + B[6 + l6] * du1;
 #pragma unroll
-            for (int k = 0; k < 6; k++) a += A[lane + 6 * k] * dz[k];
-            DXo[lane * d + i + 1] = a;
-          } else if (lane == 6) { DUo[i] = du0; DUo[d + i] = du1; }
+            for (int k = 0; k < 6; k++) a += A[l6 + 6 * k] * dz[k];
+            if (lane < 6) DXo[lane * d + i + 1] = a;
+            if (lane == 6) { DUo[i] = du0; DUo[d + i] = du1; }
+          }
         GLANES_END(NW)
       }
 
@@ -1033,11 +1043,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double rp = (sg * v - (isb ? thq : 0.0)) + s - bnd;              \
     const double dsa = -rp - (sg * va - (isb ? dthaq : 0.0));              \
     const double dya_ = -y - y * is * dsa;                                 \
-    double ds = dsa, dy = dya_;                                            \
-    if (pass) {                                                            \
-      ds = -rp - (sg * vf - (isb ? dthq : 0.0));                           \
-      dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;              \
-    } else cross += dsa * dya_;                                            \
+    const double dsf = -rp - (sg * vf - (isb ? dthq : 0.0));               \
+    const double dyf_ = (-(s * y - smu + csc * dsa * dya_) - y * dsf) * is; \
+    const double ds = pass ? dsf : dsa, dy = pass ? dyf_ : dya_;           \
+    cross += pass ? 0.0 : dsa * dya_;                                      \
     rmax = fmax(rmax, fmax(-ds * is, -dy * iy));                           \
   }
         FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, pass != 0)
