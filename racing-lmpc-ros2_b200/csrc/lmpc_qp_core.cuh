@@ -489,7 +489,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           if (pact_th) { Dthth += LMPC_PRHO; cth += -yth + LMPC_PRHO * th; }
         } else {
           if (pass) corr_th = csc * dtha * dytha;
-          Dthth += 2.0 * P.qb + yth / th; cth += 2.0 * P.qb * th - (smu - corr_th) / th;
+          { const double ith = lmpc_rcp(th); Dthth += 2.0 * P.qb + yth * ith; cth += 2.0 * P.qb * th - (smu - corr_th) * ith; }
         }
       }
 
@@ -504,7 +504,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           GLANES_BEGIN(NT)
             for (int p = 0; p < KPL; p++) {
               const int k = lane + NT * p;
-              double om = (k < K) ? lam(lane).a[p] / ylam(lane).a[p] : -1.0;
+              double om = (k < K) ? lam(lane).a[p] * lmpc_rcp(ylam(lane).a[p]) : -1.0;
               if (polishing && k < K) om = pnb(lane).a[p] ? 1.0 / LMPC_PRHO : 1e300;   // free (basic) columns must be explicit
               omg_(lane).a[p] = om; isB(lane).a[p] = 0;
             }
@@ -542,7 +542,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               const double l = lam(lane).a[p];
               double tl = smu;
               if (pass) tl -= csc * dla(lane).a[p] * dya(lane).a[p];
-              double gl = sscv(lane).a[p] - tl / l;
+              double gl = sscv(lane).a[p] - tl * lmpc_rcp(l);
               if (polishing) gl = pnb(lane).a[p] ? sscv(lane).a[p] - ylam(lane).a[p] + LMPC_PRHO * l : sscv(lane).a[p];
               glam(lane).a[p] = gl;
               if (isB(lane).a[p]) TB[TB_BG + isB(lane).a[p] - 1] = gl;
@@ -860,7 +860,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #endif
             fail = true; break;
           }
-          const double idet = 1.0 / det;
+          const double idet = lmpc_rcp(det);
           const double i0 = s2_ * idet, i1 = -s1 * idet, i2_ = s0 * idet;
           const double cw1_0 = cwc0 + AXBW[6], cw1_1 = cwc1 + AXBW[7];
           const double cwt_0 = AXBW[8 + 6], cwt_1 = AXBW[8 + 7];
@@ -1007,7 +1007,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               const double l = lam(lane).a[p], y = ylam(lane).a[p];
               double tl = smu;
               if (pass) tl -= csc * dla(lane).a[p] * dya(lane).a[p];
-              tl /= l;
+              const double il_ = lmpc_rcp(l);
+              tl *= il_;
               double dl;
               const int ib = isB(lane).a[p];
               if (ib) {
@@ -1020,7 +1021,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
                 for (int a = 0; a < 6; a++) se += ST[6 * k + a] * e[a];
                 dl = omg_(lane).a[p] * (se - glam(lane).a[p] - nu);
               }
-              const double dy = tl - y - dl * (y / l);
+              const double dy = tl - y - dl * (y * il_);
               if (pass) { dlf(lane).a[p] = dl; dyf(lane).a[p] = dy; } else { dla(lane).a[p] = dl; dya(lane).a[p] = dy; }
             }
           }
@@ -1028,7 +1029,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       }
       double dthc = dthp, dythc = 0.0;
       if (polishing) { dtha = dthc; break; }   // the polish takes the full step below, no ratio test
-      if (soft) { const double tt = (smu - corr_th) / th; dythc = tt - yth - (yth / th) * dthc; }
+      if (soft) { const double ith = lmpc_rcp(th); const double tt = (smu - corr_th) * ith; dythc = tt - yth - (yth * ith) * dthc; }
       if (pass) { dth = dthc; dyth = dythc; } else { dtha = dthc; dytha = dythc; }
 
       // ---------- row directions, step length
@@ -1056,7 +1057,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const int k = lane + NT * p;
           if (k < K) {
             const double dl = pass ? dlf(lane).a[p] : dla(lane).a[p], dy = pass ? dyf(lane).a[p] : dya(lane).a[p];
-            rmax = fmax(rmax, fmax(-dl / lam(lane).a[p], -dy / ylam(lane).a[p]));
+            rmax = fmax(rmax, fmax(-dl * lmpc_rcp(lam(lane).a[p]), -dy * lmpc_rcp(ylam(lane).a[p])));
             if (!pass) cross += dl * dy;
           }
         }
@@ -1195,7 +1196,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double ds = -rp - (sg * vf - (isb ? dthq : 0.0));                \
     const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;   \
     const double sn = s + alpha * ds, yn = y + alpha * dy;                 \
-    RSs[slot * d + i] = sn; RSy[slot * d + i] = yn; RSi[slot * d + i] = 1.0 / (sn * yn); \
+    RSs[slot * d + i] = sn; RSy[slot * d + i] = yn; RSi[slot * d + i] = lmpc_rcp(sn * yn); \
   }
         FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, true)
 #undef ROW_BODY
