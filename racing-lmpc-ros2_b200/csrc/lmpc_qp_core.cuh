@@ -522,7 +522,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               for (int p = 0; p < KPL; p++) if (lane + NT * p == kb) {
                 isB(lane).a[p] = 1 + q;
                 for (int a = 0; a < 6; a++) TB[TB_BCOL + 6 * q + a] = ST[6 * kb + a];
-                TB[TB_BD + q] = polishing ? (pnb(lane).a[p] ? LMPC_PRHO : 0.0) : ylam(lane).a[p] / lam(lane).a[p];
+                TB[TB_BD + q] = polishing ? (pnb(lane).a[p] ? LMPC_PRHO : 0.0) : ylam(lane).a[p] * lmpc_rcp(lam(lane).a[p]);
               }
             GLANES_END(NW)
           }
@@ -545,20 +545,20 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               double gl = sscv(lane).a[p] - tl * lmpc_rcp(l);
               if (polishing) gl = pnb(lane).a[p] ? sscv(lane).a[p] - ylam(lane).a[p] + LMPC_PRHO * l : sscv(lane).a[p];
               glam(lane).a[p] = gl;
-              if (isB(lane).a[p]) TB[TB_BG + isB(lane).a[p] - 1] = gl;
-              else {
-                const double om = omg_(lane).a[p];
-                og += om * gl; om1 += om;
-                double sv[6];
+              // explicit (basic) columns hand their gradient to the LU system and enter the sums with weight zero
+              const int ib = isB(lane).a[p];
+              if (ib) TB[TB_BG + ib - 1] = gl;
+              const double om = ib ? 0.0 : omg_(lane).a[p];
+              og += om * gl; om1 += om;
+              double sv[6];
 #pragma unroll
-                for (int a = 0; a < 6; a++) sv[a] = ST[6 * k + a];
+              for (int a = 0; a < 6; a++) sv[a] = ST[6 * k + a];
 #pragma unroll
-                for (int a = 0, q = 0; a < 6; a++) {
-                  const double sa = sv[a];
-                  bv6[a] += sa * om * gl; av[a] += sa * om;
+              for (int a = 0, q = 0; a < 6; a++) {
+                const double sa = sv[a];
+                bv6[a] += sa * om * gl; av[a] += sa * om;
 #pragma unroll
-                  for (int b = 0; b <= a; b++, q++) W[q] += om * sa * sv[b];
-                }
+                for (int b = 0; b <= a; b++, q++) W[q] += om * sa * sv[b];
               }
             }
           }
@@ -603,7 +603,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #pragma unroll
             for (int k = 0; k < j; k++) dg -= Lc[j * (j + 1) / 2 + k] * Lc[j * (j + 1) / 2 + k];
             if (!(dg > 0.0)) { ok = false; dg = 1.0; }
-            const double il = 1.0 / sqrt(dg);
+            const double il = lmpc_rsqrt(dg);
             Lc[j * (j + 1) / 2 + j] = il;
 #pragma unroll
             for (int i2 = j + 1; i2 < 6; i2++) {
@@ -683,7 +683,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #pragma unroll
                 for (int c2 = 0; c2 < LMPC_NQ; c2++) { const double t0 = M[k][c2], t1 = M[i2][c2]; M[k][c2] = sw ? t1 : t0; M[i2][c2] = sw ? t0 : t1; }
               }
-              const double ip = 1.0 / (fail ? 1.0 : M[k][k]);
+              const double ip = lmpc_rcp(fail ? 1.0 : M[k][k]);
 #pragma unroll
               for (int i2 = k + 1; i2 < LMPC_NQ; i2++) {
                 const double f = M[i2][k] * ip; M[i2][k] = f;
@@ -730,7 +730,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               double a2 = v[i2];
 #pragma unroll
               for (int k = i2 + 1; k < LMPC_NQ; k++) a2 -= TB[TB_S2 + i2 * LMPC_NQ + k] * v[k];
-              v[i2] = a2 / TB[TB_S2 + i2 * LMPC_NQ + i2];
+              v[i2] = a2 * lmpc_rcp(TB[TB_S2 + i2 * LMPC_NQ + i2]);
             }
             if (doX) {
 #pragma unroll
@@ -1009,18 +1009,16 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               if (pass) tl -= csc * dla(lane).a[p] * dya(lane).a[p];
               const double il_ = lmpc_rcp(l);
               tl *= il_;
-              double dl;
+              // both forms are evaluated (the loads of the three columns go out together), the column's kind selects
               const int ib = isB(lane).a[p];
-              if (ib) {
-                dl = qv[1];
+              double dlb = qv[1];
 #pragma unroll
-                for (int q = 2; q < LMPC_NQ; q++) if (ib == q) dl = qv[q];
-              } else {
-                double se = 0.0;
+              for (int q = 2; q < LMPC_NQ; q++) dlb = (ib == q) ? qv[q] : dlb;
+              double se = 0.0;
 #pragma unroll
-                for (int a = 0; a < 6; a++) se += ST[6 * k + a] * e[a];
-                dl = omg_(lane).a[p] * (se - glam(lane).a[p] - nu);
-              }
+              for (int a = 0; a < 6; a++) se += ST[6 * k + a] * e[a];
+              const double dln = omg_(lane).a[p] * (se - glam(lane).a[p] - nu);
+              const double dl = ib ? dlb : dln;
               const double dy = tl - y - dl * (y * il_);
               if (pass) { dlf(lane).a[p] = dl; dyf(lane).a[p] = dy; } else { dla(lane).a[p] = dl; dya(lane).a[p] = dy; }
             }

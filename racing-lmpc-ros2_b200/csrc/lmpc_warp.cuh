@@ -67,7 +67,17 @@ struct LaneVar {
 // slow-path branch, within 1 ulp of the IEEE quotient; the IEEE division costs about fifteen and a call.  Emulation: 1 / x.
 #if defined(LMPC_EMULATE)
 LMPC_HD double lmpc_rcp(double x) { return 1.0 / x; }
+LMPC_HD double lmpc_rsqrt(double x) { return 1.0 / sqrt(x); }
 #else
+// 1 / sqrt(x), x > 0 normal: rsqrt.approx.ftz.f64 and two Newton steps r <- r + r (1/2 - x r^2 / 2)
+LMPC_DEV double lmpc_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  r = fma(r, fma(-hx * r, r, 0.5), r);
+  return r;
+}
 LMPC_DEV double lmpc_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
