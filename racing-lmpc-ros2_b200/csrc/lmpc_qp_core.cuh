@@ -46,7 +46,7 @@
 // constexpr so that the kernels instantiated for the named horizons fold every address into an immediate.
 struct LmpcLayout {
   int oABG, oS, oY, oISY, oX, oU, oDXA, oDUA, oDXF, oDUF, oCZX, oCZTH, oGUD, oFAC, oKFF, oBL, oBR, oVREF, oIT,
-      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, oMBAR, total;
+      oPM, oL1, oLTH, oMAB, oAXBW, oYY, oRED, oTERM, oROWS, oMBAR, oCHS, total;
 };
 #define LMPC_MAX_ROWS 22   // 6 x 2 state boxes + 2 boundary + 4 control boxes + 4 rate boxes
 // Row table (depends on the configuration only; built on the host, lmpc_host_params.h).  Every row is
@@ -78,6 +78,7 @@ LMPC_HD constexpr LmpcLayout lmpc_layout(int N, int RS, int NW) {
   L.oTERM = o; o += lmpc_even(LMPC_TB_SIZE_);
   L.oROWS = o; o += lmpc_even(LMPC_ROWS_DOUBLES);   // row table (copied from the parameters: constant-bank indexing is slow)
   L.oMBAR = o; o += 2;   // mbarrier of the bulk stage-in of [A|B|g]
+  L.oCHS = o; o += 10;   // channel scales of the step-based acceptance test
   L.total = o;
   return L;
 }
@@ -299,7 +300,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   double* const SCRK = in.scratch + 6 * P.K + 8 * P.N + 2 * P.K;
   const ScrK<NT> dla{SCRK}, dya{SCRK + LMPC_MAX_SS_PTS}, dlf{SCRK + 2 * LMPC_MAX_SS_PTS}, dyf{SCRK + 3 * LMPC_MAX_SS_PTS},
       glam{SCRK + 4 * LMPC_MAX_SS_PTS}, sscv{SCRK + 5 * LMPC_MAX_SS_PTS};   // ... steps, gradient, cost-to-go in global scratch
-  double* const chs_ = SCRK + 6 * LMPC_MAX_SS_PTS;   // [10] channel scales (uniform reads)
+  double* const chs_ = sm + LO(oCHS);   // [10] channel scales
   LaneVar<ArrKi, NT> isB;
   double* const ST = in.scratch;   // [K][6] centred columns, compacted to the nh hull components (global memory; L2-resident)
   double R0;
@@ -425,7 +426,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double dj = polishing ? (act ? LMPC_PRHO : 0.0) : dj0;           \
     const double t = polishing ? (act ? y + LMPC_PRHO * (rp - s) : 0.0) : tip; \
     msum += ip0 ? s * y : 0.0;                                             \
-    rpm = ip0 ? fmax(rpm, fabs(rp)) : rpm;                                 \
+    rpm = ip0 ? lmpc_max(rpm, fabs(rp)) : rpm;                             \
     hsum += dj; gsum += sg * t;                                            \
     if (isb && soft) { cz_th += -sg * dj; dth_acc += dj; cth_acc += -t; }  \
   }
@@ -1046,7 +1047,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double dyf_ = (-(s * y - smu + csc * dsa * dya_) - y * dsf) * is; \
     const double ds = pass ? dsf : dsa, dy = pass ? dyf_ : dya_;           \
     cross += pass ? 0.0 : dsa * dya_;                                      \
-    rmax = fmax(rmax, fmax(-ds * is, -dy * iy));                           \
+    rmax = lmpc_max(lmpc_max(rmax, -ds * is), -dy * iy);                   \
   }
         FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, pass != 0)
 #undef ROW_BODY
@@ -1055,7 +1056,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           const int k = lane + NT * p;
           if (k < K) {
             const double dl = pass ? dlf(lane).a[p] : dla(lane).a[p], dy = pass ? dyf(lane).a[p] : dya(lane).a[p];
-            rmax = fmax(rmax, fmax(-dl * lmpc_rcp(lam(lane).a[p]), -dy * lmpc_rcp(ylam(lane).a[p])));
+            rmax = lmpc_max(lmpc_max(rmax, -dl * lmpc_rcp(lam(lane).a[p])), -dy * lmpc_rcp(ylam(lane).a[p]));
             if (!pass) cross += dl * dy;
           }
         }
@@ -1206,11 +1207,11 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         // step-based acceptance: the primal step per channel, relative to max(1, |channel|)
         double m = 0.0;
         for (int i = lane; i < N; i += NT) {
-          for (int c = 0; c < 6; c++) m = fmax(m, fabs(DXF[c * d + i]) * chs_[c]);
+          for (int c = 0; c < 6; c++) m = lmpc_max(m, fabs(DXF[c * d + i]) * chs_[c]);
           if (i < NS) for (int c = 0; c < 2; c++) {
             const double dup = i ? DUF[c * d + i - 1] : 0.0;
-            m = fmax(m, fabs(DUF[c * d + i]) * chs_[6 + c]);
-            m = fmax(m, fabs(DUF[c * d + i] - dup) * IT[i] * chs_[8 + c]);
+            m = lmpc_max(m, fabs(DUF[c * d + i]) * chs_[6 + c]);
+            m = lmpc_max(m, fabs(DUF[c * d + i] - dup) * IT[i] * chs_[8 + c]);
           }
         }
         rstep(lane) = m;
