@@ -91,6 +91,18 @@ static inline int lmpc_make_qp_params(const lmpc_mpc_config& c, const lmpc_vehic
     }
   T.bslot[0] = P.nxb + 8; T.bslot[1] = P.nxb + 9;
   T.ib0 = P.soft ? 0 : 1; T.pad_ = 0;
+  // by slot: x rows exist on stages 1..N-2, boundary rows on ib0..N-1, control and rate rows on 0..N-2
+  for (int q = 0; q < LMPC_MAX_ROWS; q++) { T.sbnd[q] = 0.0; T.sdesc[q] = 0; }
+  auto desc = [](int c8, int lower, int isb, int rate, int i0, int last) { return c8 | (lower << 4) | (isb << 5) | (rate << 6) | (i0 << 8) | (last << 9) | (1 << 10); };   // bit 10: the slot holds a row
+  for (int k = 0; k < 6; k++)
+    for (int r = 0; r < 2; r++)
+      if (T.xslot[2 * k + r] >= 0) { T.sdesc[T.xslot[2 * k + r]] = desc(k, r, 0, 0, 1, 0); T.sbnd[T.xslot[2 * k + r]] = T.xbnd[2 * k + r]; }
+  for (int k = 0; k < 2; k++)
+    for (int r = 0; r < 2; r++) {
+      if (T.uslot[2 * k + r] >= 0) { T.sdesc[T.uslot[2 * k + r]] = desc(6 + k, r, 0, 0, 0, 0); T.sbnd[T.uslot[2 * k + r]] = T.ubnd[2 * k + r]; }
+      if (T.dslot[2 * k + r] >= 0) { T.sdesc[T.dslot[2 * k + r]] = desc(6 + k, r, 0, 1, 0, 0); T.sbnd[T.dslot[2 * k + r]] = T.dbnd[2 * k + r]; }
+    }
+  for (int r = 0; r < 2; r++) T.sdesc[T.bslot[r]] = desc(1, r, 1, 0, T.ib0, 1);
   P.lay = lmpc_layout(P.N, P.RS, NW);
   *out = P;
   return LMPC_OK;

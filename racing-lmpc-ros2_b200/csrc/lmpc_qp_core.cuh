@@ -56,6 +56,11 @@ struct LmpcRowTab {
   double xbnd[12], ubnd[4], dbnd[4];
   int xslot[12], uslot[4], dslot[4], bslot[2];
   int ib0, pad_;   // first stage of the boundary rows (0 when they are soft, 1 otherwise)
+  // the same rows by slot, for the passes that give one lane to one row (LMPC_FOR_ROWS_BY_LANE):
+  // sdesc = component of (x, u) [bits 0-3] | lower side [4] | boundary row [5] | rate row [6] | first stage [8] |
+  //         last stage is N-1 instead of N-2 [9] | slot in use [10];  sbnd = the constant bound (boundary rows take theirs from the track)
+  double sbnd[LMPC_MAX_ROWS];
+  int sdesc[LMPC_MAX_ROWS];
 };
 static_assert(sizeof(LmpcRowTab) % 8 == 0, "row table is copied as doubles");
 #define LMPC_ROWS_DOUBLES ((int)(sizeof(LmpcRowTab) / 8))
@@ -177,7 +182,8 @@ struct ArrKi { int a[LMPC_KPL_MAX]; };
       const double sg = side_ ? -1.0 : 1.0;                                                              \
       const double bnd = (BNDEXPR);                                                                      \
       constexpr bool isb = (ISB);                                                                        \
-      (void)sg; (void)bnd; (void)isb;                                                                    \
+      constexpr bool on = true;                                                                          \
+      (void)sg; (void)bnd; (void)isb; (void)on;                                                          \
       ROW_BODY                                                                                           \
     }                                                                                                    \
   }
@@ -218,6 +224,42 @@ struct ArrKi { int a[LMPC_KPL_MAX]; };
     }                                                                                                    \
   }
 
+// One lane per row: lane = slot + SL * half; the lane walks the stages of its half of the horizon (SL = 16 and two halves
+// when the configuration has at most 16 rows per stage, else 32 and one).  All lanes run the same straight-line code --
+// the variable is fetched through the row's descriptor, rows that do not exist at a stage are masked by `on` -- so a
+// pass costs (stages per half) bodies instead of (groups x sides) bodies.  One warp per instance only.
+// In scope for ROW_BODY: slot, i (a valid stage even when masked), on, sg, bnd, isb, v, va, vf.
+#define LMPC_FOR_ROWS_BY_LANE(NA, NF)                                                                    \
+  {                                                                                                      \
+    const int SL_ = (RSN <= 16) ? 16 : 32;                                                               \
+    const int slot_ = lane & (SL_ - 1), half_ = lane / SL_, HS_ = (RSN <= 16) ? (N + 1) / 2 : N;         \
+    const int sd_ = RT->sdesc[slot_ < RSN ? slot_ : 0];                                                  \
+    const bool rowon_ = slot_ < RSN && (sd_ & 1024) != 0;                                                \
+    const int slot = slot_ < RSN ? slot_ : 0;                                                            \
+    const double bndc_ = RT->sbnd[slot];                                                                 \
+    const int c8_ = sd_ & 15, i0_ = (sd_ >> 8) & 1, i1_ = N - 2 + ((sd_ >> 9) & 1);                      \
+    const bool neg_ = (sd_ & 16) != 0, isb = (sd_ & 32) != 0, rate_ = (sd_ & 64) != 0;                   \
+    const double sg = neg_ ? -1.0 : 1.0;                                                                 \
+    const double uicl_ = (c8_ == 7) ? uic[1] : uic[0];                                                   \
+    LMPC_UNROLL2                                                                                         \
+    for (int it_ = 0; it_ < HS_; it_++) {                                                                \
+      const int iraw_ = half_ * HS_ + it_;                                                               \
+      const bool on = rowon_ && iraw_ >= i0_ && iraw_ <= i1_;                                            \
+      const int i = on ? iraw_ : i0_;                                                                    \
+      const int ip_ = i ? i - 1 : 0;                                                                     \
+      const double sc_ = rate_ ? IT[i] : 1.0;                                                            \
+      const double cur_ = X[c8_ * d + i], prv_ = X[c8_ * d + ip_];                                       \
+      const double v = rate_ ? (cur_ - (i ? prv_ : uicl_)) * sc_ : cur_;                                 \
+      double va = 0.0, vf = 0.0;                                                                         \
+      if (NA) { const double ca_ = DXA[c8_ * d + i], pa_ = DXA[c8_ * d + ip_]; va = rate_ ? (ca_ - (i ? pa_ : 0.0)) * sc_ : ca_; } \
+      if (NF) { const double cf_ = DXF[c8_ * d + i], pf_ = DXF[c8_ * d + ip_]; vf = rate_ ? (cf_ - (i ? pf_ : 0.0)) * sc_ : cf_; } \
+      const double bl_ = BL[i], br_ = BR[i];                                                             \
+      const double bnd = isb ? (neg_ ? -(br_ + P.margin) : (bl_ - P.margin)) : bndc_;                    \
+      (void)v; (void)va; (void)vf; (void)bnd; (void)sg; (void)on;                                        \
+      ROW_BODY                                                                                           \
+    }                                                                                                    \
+  }
+
 // ------------------------------------------------------------------------------------------------
 // NW warps per instance, KPL = ceil(K / (32 NW)) safe-set columns per lane (registers).
 // NTPL / RSTPL > 0: horizon and rows-per-stage are compile-time (addresses fold to immediates); 0 = runtime.
@@ -241,6 +283,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   double* HX = DXF;   // alias: the Hessian diagonal is dead once the pass-0 factorisation is done
   double* CZX = sm + LO(oCZX); double* CZTH = sm + LO(oCZTH); double* GUD = sm + LO(oGUD);
   const LmpcRowTab* RT = reinterpret_cast<const LmpcRowTab*>(sm + LO(oROWS));
+  const int RSN = FIXED ? RSTPL : P.RS;   // row slots per stage
   double* FAC = sm + LO(oFAC);   // per stage: Kz[16] (2x8 row-major), Sinv[3], pad
   double* KFF = sm + LO(oKFF);   // per stage: kff1[2], kffth[2], Cwth[2]
   double* BL = sm + LO(oBL); double* BR = sm + LO(oBR); double* VREF = sm + LO(oVREF); double* IT = sm + LO(oIT);
@@ -1046,10 +1089,11 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double dsf = -rp - (sg * vf - (isb ? dthq : 0.0));               \
     const double dyf_ = (-(s * y - smu + csc * dsa * dya_) - y * dsf) * is; \
     const double ds = pass ? dsf : dsa, dy = pass ? dyf_ : dya_;           \
-    cross += pass ? 0.0 : dsa * dya_;                                      \
-    rmax = lmpc_max(lmpc_max(rmax, -ds * is), -dy * iy);                   \
+    cross += (pass || !on) ? 0.0 : dsa * dya_;                             \
+    rmax = on ? lmpc_max(lmpc_max(rmax, -ds * is), -dy * iy) : rmax;       \
   }
-        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, pass != 0)
+        if constexpr (NW == 1) LMPC_FOR_ROWS_BY_LANE(true, pass != 0)
+        else { FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, pass != 0) }
 #undef ROW_BODY
 #pragma unroll
         for (int p = 0; p < KPL; p++) {
@@ -1195,9 +1239,10 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     const double ds = -rp - (sg * vf - (isb ? dthq : 0.0));                \
     const double dy = (-(s * y - smu + csc * dsa * dya_) - y * ds) * is;   \
     const double sn = s + alpha * ds, yn = y + alpha * dy;                 \
-    RSs[slot * d + i] = sn; RSy[slot * d + i] = yn; RSi[slot * d + i] = lmpc_rcp(sn * yn); \
+    if (on) { RSs[slot * d + i] = sn; RSy[slot * d + i] = yn; RSi[slot * d + i] = lmpc_rcp(sn * yn); } \
   }
-        FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, true)
+        if constexpr (NW == 1) LMPC_FOR_ROWS_BY_LANE(true, true)
+        else { FOR_MY_STAGES(i) LMPC_FOR_ROWS(i, true, true) }
 #undef ROW_BODY
 #pragma unroll
         for (int p = 0; p < KPL; p++) {

@@ -18,6 +18,7 @@
 
 #define LMPC_UNROLL _Pragma("unroll")   // usable inside macros
 #define LMPC_NOUNROLL _Pragma("unroll 1")
+#define LMPC_UNROLL2 _Pragma("unroll 2")
 
 #if defined(LMPC_EMULATE)
 // ------------------------------------------------------------------ lane-loop emulation (tests)

@@ -180,3 +180,27 @@ def test_emulated_qp_kernel_fifty_lap_variant(emu, pkg, laps, barc_track):
         if d["status"] == 0 and d["kkt"] < 1e-10 and k["status"] == 0:
             worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"])); n += 1
     assert n >= 4 and worst < 1e-6, (n, worst)
+
+
+@pytest.mark.parametrize("name", ["barc_lmpc", "barc_tracking"])
+def test_emulated_qp_kernel_all_state_boxes(emu, pkg, name):
+    """Every state boxed (12 + 10 = 22 rows per stage): the lane-per-row passes take their one-half, 32-slot mapping and
+    the run-time shared-memory layout; loose e_y / e_psi / s boxes so that the optimum has both active and idle boxes."""
+    from oracle import Oracle
+    od, veh, cfg, track, mode = make_oracle(pkg, name, tol=1e-11)
+    cfg = dict(cfg, x_max=[1e3, 0.5, 0.6, cfg["x_max"][3], 1.0, 3.0], x_min=[-1e3, -0.5, -0.6, 0.1, -1.0, -3.0], tol=1e-11)
+    od = Oracle(veh, cfg)
+    for l in pkg.workload.load_laps():
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 6, 0xA11, track, pkg.workload.load_laps(), mode=mode)
+    worst, n = 0.0, 0
+    for b in range(6):
+        inp = pkg.workload.instance(batch, b)
+        dref = od.step(inp, impl="dense")
+        if not (dref["status"] == 0 and dref["polished"] == 1 and dref["kkt"] < 1e-9):
+            continue
+        k = _emu_solve(emu, pkg, od, veh, dict(cfg, tol=1e-13), inp)
+        assert k["status"] == 0
+        worst = max(worst, relerr(k["X"], dref["X"]), relerr(k["U"], dref["U"]), relerr(k["dU"], dref["dU"]))
+        n += 1
+    assert n >= 3 and worst < 1e-6, (n, worst)
