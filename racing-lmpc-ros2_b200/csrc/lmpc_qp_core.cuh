@@ -553,23 +553,41 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               omg_(lane).a[p] = om; isB(lane).a[p] = 0;
             }
           GLANES_END(NW)
+          int kbs[LMPC_MB];
+#pragma unroll
           for (int q = 0; q < LMPC_MB; q++) {
             LaneVar<double, NT> bv; LaneVar<int, NT> bi;
             GLANES_BEGIN(NT)
               double v = -2.0; int ix = 1 << 30;
-              for (int p = 0; p < KPL; p++) { const int k = lane + NT * p; if (k < K && !isB(lane).a[p] && omg_(lane).a[p] > v) { v = omg_(lane).a[p]; ix = k; } }
+#pragma unroll
+              for (int p = 0; p < KPL; p++) {
+                const int k = lane + NT * p;
+                const bool take = k < K && !isB(lane).a[p] && omg_(lane).a[p] > v;
+                v = take ? omg_(lane).a[p] : v; ix = take ? k : ix;
+              }
               bv(lane) = v; bi(lane) = ix;
             GLANES_END(NW)
             group_argbest<NW>(bv, bi, true, RED);
             const int kb = bi(0);
+            kbs[q] = kb;
             GLANES_BEGIN(NT)
+#pragma unroll
               for (int p = 0; p < KPL; p++) if (lane + NT * p == kb) {
                 isB(lane).a[p] = 1 + q;
-                for (int a = 0; a < 6; a++) TB[TB_BCOL + 6 * q + a] = ST[6 * kb + a];
                 TB[TB_BD + q] = polishing ? (pnb(lane).a[p] ? LMPC_PRHO : 0.0) : ylam(lane).a[p] * lmpc_rcp(lam(lane).a[p]);
               }
             GLANES_END(NW)
           }
+          // the MB explicit columns, one element per lane: a single round trip to the scratch instead of one per column
+          GLANES_BEGIN(NT)
+            if (lane < 6 * LMPC_MB) {
+              const int q = lane / 6, a = lane - 6 * q;
+              int kb = kbs[0];
+#pragma unroll
+              for (int r = 1; r < LMPC_MB; r++) kb = (q == r) ? kbs[r] : kb;
+              TB[TB_BCOL + lane] = ST[6 * kb + a];
+            }
+          GLANES_END(NW)
         }
         // ---- sums over the non-basic columns: b (6), og | W (21), a (6), om1
         LaneVar<double, NT> rt[LMPC_NRED];

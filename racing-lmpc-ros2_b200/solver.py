@@ -279,20 +279,41 @@ class BatchedRacingMPC:
         return dict(X_optm=(Bn, N, 6), U_optm=(Bn, N - 1, 2), dU_optm=(Bn, N - 1, 2), convex_combi_optm=(Bn, K),
                     ss_x=(Bn, K, 6), ss_j=(Bn, K), cost=(Bn,))
 
-    def alloc_host_outputs(self, Bn, pinned=False):
-        """Output buffers for the host path (optionally CUDA-pinned through torch)."""
-        out = {}
+    def _arena(self, nbytes, pinned):
         if pinned:
             import torch
-            for k, shp in self._shapes(Bn).items():
-                out[k] = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
-            out["status"] = torch.empty(Bn, dtype=torch.int32).pin_memory().numpy()
-            out["iters"] = torch.empty(Bn, dtype=torch.int32).pin_memory().numpy()
-        else:
-            for k, shp in self._shapes(Bn).items():
-                out[k] = np.zeros(shp)
-            out["status"] = np.zeros(Bn, dtype=np.int32)
-            out["iters"] = np.zeros(Bn, dtype=np.int32)
+            return torch.empty(nbytes, dtype=torch.uint8).pin_memory().numpy()
+        return np.zeros(nbytes, dtype=np.uint8)
+
+    def alloc_host_outputs(self, Bn, pinned=False):
+        """Output buffers for the host path (optionally CUDA-pinned through torch), carved from ONE arena in the order of
+        lmpc_batch_out so that the library returns them with two copies (trajectories + multipliers, cost + status +
+        iterations) plus the safe-set columns on the side stream."""
+        shp = self._shapes(Bn)
+        order = ("X_optm", "U_optm", "dU_optm", "convex_combi_optm", "ss_x", "ss_j", "cost")
+        nb = sum(int(np.prod(shp[k])) * 8 for k in order) + 8 * Bn
+        arena = self._arena(nb, pinned)
+        out, o = {}, 0
+        for k in order:
+            n = int(np.prod(shp[k])) * 8
+            out[k] = arena[o:o + n].view(np.float64).reshape(shp[k])
+            o += n
+        out["status"] = arena[o:o + 4 * Bn].view(np.int32); o += 4 * Bn
+        out["iters"] = arena[o:o + 4 * Bn].view(np.int32)
+        return out
+
+    def alloc_host_inputs(self, batch, pinned=False):
+        """Copy a batch (dict of numpy arrays, the reference's input keys) into ONE arena in the order of lmpc_batch_in:
+        the host path then uploads it with a single copy."""
+        keys = list(IN_KEYS) + (["U_optm_ref"] if "U_optm_ref" in batch else [])
+        arrs = {k: np.ascontiguousarray(batch[k], dtype=np.float64) for k in keys}
+        arena = self._arena(sum(a.nbytes for a in arrs.values()), pinned)
+        out, o = {}, 0
+        for k in keys:
+            a = arrs[k]
+            out[k] = arena[o:o + a.nbytes].view(np.float64).reshape(a.shape)
+            out[k][...] = a
+            o += a.nbytes
         return out
 
     def solve(self, batch, out=None):

@@ -218,6 +218,27 @@ def test_device_path_matches_host_path(pkg):
         assert np.array_equal(out[k].cpu().numpy(), host[k]), k
 
 
+def test_host_arena_buffers_match_plain_host_buffers(pkg):
+    """Host path with inputs / outputs carved from one (pinned) arena -- merged H2D / D2H copies, safe-set columns
+    returned on the side stream -- against the same call with separate pageable buffers; repeated, and for the tracking
+    configuration (no safe-set outputs)."""
+    for name in ("barc_lmpc", "barc_tracking"):
+        m, veh, cfg, track, mode = _mpc(pkg, name, 48)
+        batch = pkg.workload.make_batch(veh, cfg, 48, 77, track, pkg.workload.load_laps(), mode=mode)
+        plain = m.solve({k: v.copy() for k, v in batch.items()})
+        h_in = m.alloc_host_inputs(batch, pinned=True)
+        keys = list(h_in)
+        for a, b in zip(keys[:-1], keys[1:]):   # adjacent in struct order
+            assert h_in[a].ctypes.data + h_in[a].nbytes == h_in[b].ctypes.data
+        h_out = m.alloc_host_outputs(48, pinned=True)
+        for rep in range(3):
+            for v in h_out.values():
+                v[...] = 0
+            out = m.solve(h_in, h_out)
+            for k in ("X_optm", "U_optm", "dU_optm", "cost", "status", "iters") + (("convex_combi_optm", "ss_x", "ss_j") if cfg["learning"] else ()):
+                assert np.array_equal(out[k], plain[k]), (name, k, rep)
+
+
 def test_horizon_is_a_runtime_parameter(pkg):
     """N is a parameter of RacingMPCConfig (racing_mpc_config.hpp:47): the shipped YAMLs use 40 / 60."""
     for name, N in (("barc_lmpc", 40), ("barc_tracking", 60), ("barc_lmpc", 5)):
