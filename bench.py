@@ -165,6 +165,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     veh, cfg, track, laps, data = workload(pkg, 0xB200 + 2 + 7919 * rank, args.batch)
