@@ -1009,7 +1009,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         double dz[8];
 #pragma unroll
         for (int k = 0; k < 6; k++) dz[k] = DXo[k * d + i];
-        const int im = i ? i - 1 : 0;
+        const int im = i ? i - 1 : 1;                    // stage 0 has no predecessor: read an entry this phase does not write
         const double pu0 = DUo[im], pu1 = DUo[d + im];   // unconditional loads, then selects
         dz[6] = i ? pu0 : 0.0; dz[7] = i ? pu1 : 0.0;
         double du0 = -kf[0] - kf[2] * dthp, du1 = -kf[1] - kf[3] * dthp;
