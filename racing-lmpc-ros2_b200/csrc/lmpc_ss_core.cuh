@@ -38,18 +38,30 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
   LANES_BEGIN
     double a0 = 1e300, a1 = 1e300, a2 = 1e300, a3 = 1e300;
     int b0 = 1 << 30, b1 = 1 << 30, b2 = 1 << 30, b3 = 1 << 30;
-    for (int idx = lane; idx < m; idx += 32) {
-      const double ds = qs - lap.ps[idx], de = qe - lap.pe[idx];
-      const double v = ds * ds + de * de;
-      // strided indices increase, so on equal distance the earlier (lower) index stays ahead
-      if (v < a3) {
-        if (v < a2) {
-          a3 = a2; b3 = b2;
-          if (v < a1) {
-            a2 = a1; b2 = b1;
-            if (v < a0) { a1 = a0; b1 = b0; a0 = v; b0 = idx; } else { a1 = v; b1 = idx; }
-          } else { a2 = v; b2 = idx; }
-        } else { a3 = v; b3 = idx; }
+    // four points per trip: their eight loads go out together, then the (branchy, usually one-test) insertions
+    for (int base = lane; base < m; base += 128) {
+      double vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = base + 32 * u;
+        const int ic = idx < m ? idx : base;   // clamp: always a valid address
+        const double ds = qs - lap.ps[ic], de = qe - lap.pe[ic];
+        vv[u] = idx < m ? ds * ds + de * de : 1e300;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = base + 32 * u;
+        const double v = vv[u];
+        // strided indices increase, so on equal distance the earlier (lower) index stays ahead
+        if (v < a3) {
+          if (v < a2) {
+            a3 = a2; b3 = b2;
+            if (v < a1) {
+              a2 = a1; b2 = b1;
+              if (v < a0) { a1 = a0; b1 = b0; a0 = v; b0 = idx; } else { a1 = v; b1 = idx; }
+            } else { a2 = v; b2 = idx; }
+          } else { a3 = v; b3 = idx; }
+        }
       }
     }
     c0(lane) = a0; c1(lane) = a1; c2(lane) = a2; c3(lane) = a3;
@@ -82,13 +94,21 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
     LANES_END
     warp_or(anyex);
     last_d = wv; last_i = wi;
-    const int col = lap.out_off + r;
-    if (col < max_total) {
+    // ranks 0..31: lane r keeps the winner of rank r, the payload is gathered for all ranks at once after the merge
+    // (a gather per round would put two dependent global loads on the critical path of every round)
+    if (r < 32) {
       LANES_BEGIN
-        const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
-        if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
-        else if (lane == 6) ss_j[col] = lap.J[src];
+        if (lane == r) sel(lane) = wi;
       LANES_END
+    } else {
+      const int col = lap.out_off + r;
+      if (col < max_total) {
+        LANES_BEGIN
+          const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
+          if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
+          else if (lane == 6) ss_j[col] = lap.J[src];
+        LANES_END
+      }
     }
     // the winner above is exact (every head was valid); a lane that just ran out of kept candidates
     // may hold unseen closer points, so the remaining ranks take the exact path
@@ -110,17 +130,33 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
       LANES_END
       warp_argmin(hv, hi);
       last_d = hv(0); last_i = hi(0);
-      const int col = lap.out_off + r;
-      if (col < max_total) {
-        const int wi = last_i;
+      const int wi = last_i;
+      if (r < 32) {
         LANES_BEGIN
-          const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
-          if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
-          else if (lane == 6) ss_j[col] = lap.J[src];
+          if (lane == r) sel(lane) = wi;
         LANES_END
+      } else {
+        const int col = lap.out_off + r;
+        if (col < max_total) {
+          LANES_BEGIN
+            const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
+            if (lane < 6) ss_x[6 * col + lane] = lap.xr[6 * src + lane];
+            else if (lane == 6) ss_j[col] = lap.J[src];
+          LANES_END
+        }
       }
     }
   }
+  // ---- payload of ranks 0..31, one lane per rank
+  LANES_BEGIN
+    const int col = lap.out_off + lane;
+    if (lane < lap.take && col < max_total) {
+      const int wi = sel(lane);
+      const int src = (wi >= 0 && wi < m) ? lap.canon[wi] : 0;   // NaN query: no valid winner
+      for (int c = 0; c < 6; c++) ss_x[6 * col + c] = lap.xr[6 * src + c];
+      ss_j[col] = lap.J[src];
+    }
+  LANES_END
   // ---- pad with the last column (racing_mpc.cpp:263-272)
   if (last && count > 0 && count < pad_to) {
     LANES_BEGIN
