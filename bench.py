@@ -26,6 +26,11 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line there.  Must be set before
+# torch (and with it NCCL) is loaded.  An explicit INFO / TRACE request is left alone.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -152,7 +157,7 @@ def main():
     config_desc = {"workload": f"BASELINE configs[1]: BARC LMPC, N={N_HORIZON}, 6-state Frenet bicycle, K=96 safe-set columns "
                                f"(3 recorded laps), {args.batch} random initial states per GPU",
                    "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "N": N_HORIZON, "K": 96,
-                   "parallelism": f"instances sharded over {max(world, 1)} GPU(s), safe set replicated, one all-gather of trajectories",
+                   "parallelism": f"instances sharded over {max(world, 1)} GPU(s), safe set replicated, one all-gather of trajectories per step (overlapped with the next step's solve, waited inside its timed window)",
                    "l2": "256 MiB scratch written between timed steps (untimed) to flush the 126 MB L2", "tol": 1e-7, "polish": "active-set (augmented-Lagrangian) polish after the interior point"}
 
     # ------------------------------------------------------------------ CPU ("reference") arm
@@ -182,8 +187,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     veh, cfg, track, laps, data = workload(pkg, 0xB200 + 2 + 7919 * rank, args.batch)
@@ -198,20 +201,35 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     mpc.set_stream(stream)
     d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
-    d_out = mpc.alloc_device_outputs(args.batch, dev)
+    # two output sets: while the trajectories of step k are gathered (NCCL, its own stream), step k + 1 solves into the other
+    d_outs = [mpc.alloc_device_outputs(args.batch, dev) for _ in range(2 if world > 1 else 1)]
+    d_out = d_outs[0]
     N, K = cfg["N"], cfg["num_ss_pts"]
     # X, U, dU, cost, status of the rank live in one allocation (d_out["slab"]): the gather needs no packing kernel
-    gathered = torch.empty(max(world, 1) * d_out["slab"].numel(), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = [torch.empty(world * d_out["slab"].numel(), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    pending = [None]
 
-    def step():
-        mpc.solve(d_in, d_out)
-        if world > 1:   # the one collective of the path: gather the converged trajectories
-            dist.all_gather_into_tensor(gathered, d_out["slab"])
+    def step(k):
+        """Solve, then the one collective of the path (all-gather of the converged trajectories).  The gather of step k
+        overlaps the solve of step k + 1 and is waited for INSIDE that step's timed window (the last one in a window of
+        its own, drain()), so every gather is inside the timed region."""
+        o = d_outs[k % len(d_outs)]
+        mpc.solve(d_in, o)
+        if world > 1:
+            if pending[0] is not None:
+                pending[0].wait()
+            pending[0] = dist.all_gather_into_tensor(gathered[k % 2], o["slab"], async_op=True)
+
+    def drain():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
 
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
+        for k in range(args.warmup):
+            step(k)
+        drain()
     stream.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -222,12 +240,16 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    ev_tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     with torch.cuda.stream(stream):
         for k in range(args.steps):
             flush.fill_(float(k))            # untimed L2 flush
             ev[k][0].record(stream)
-            step()
+            step(k)
             ev[k][1].record(stream)
+        ev_tail[0].record(stream)            # the gather of the last step, timed on its own
+        drain()
+        ev_tail[1].record(stream)
     stream.synchronize()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -236,16 +258,18 @@ def main():
     (ms_lin, ms_ss, ms_qp), nrec = mpc.kernel_ms()
     mpc.set_timing(False)
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + ev_tail[0].elapsed_time(ev_tail[1])
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+    last = (args.steps - 1) % len(d_outs)
+    d_out = d_outs[last]
     status = d_out["status"].cpu().numpy()
     iters = d_out["iters"].cpu().numpy()
     if world > 1:   # untimed check of the collective: this rank's block of the gathered buffer is its own solution
         from racing_lmpc_ros2_b200.distributed import unpack_flat_slab
-        g = unpack_flat_slab(gathered.cpu().numpy(), world, args.batch, N)
+        g = unpack_flat_slab(gathered[(args.steps - 1) % 2].cpu().numpy(), world, args.batch, N)
         lo = rank * args.batch
         assert np.array_equal(g["X_optm"][lo:lo + args.batch], d_out["X_optm"].cpu().numpy())
         assert np.array_equal(g["status"][lo:lo + args.batch], status)
