@@ -42,7 +42,8 @@ def build(force=False, verbose=False):
         src, obj = os.path.join(CSRC, s), os.path.join(objdir, s[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(src)):
             continue
-        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-c", "-o", obj, src]
+        extra = os.environ.get("LMPC_NVCC_FLAGS", "").split()   # experiments only, e.g. -DLMPC_K1_MINBLOCKS=3
+        cmd = [nvcc, "-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + extra + ["-c", "-o", obj, src]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, p in procs:

@@ -23,14 +23,36 @@ struct LmpcModel {
 
 // f(x,u,kappa) and, when JAC, the non-zero partials.  Column order of the Jacobian rows:
 // 0:e_y 1:e_psi 2:v_x 3:v_y 4:omega 5:u_lon 6:delta   (d/ds is identically zero)
+// The transcendental part of f: independent chains (front tyre, rear tyre, controls, heading), kept apart from the algebra.
+// (Measured in round 1: giving each chain of an item to its own thread -- four threads per item, two tangent columns each,
+// bit-identical results -- made the linearisation kernel slower, 66-77 us against 51 us: the redundant algebra with its
+// fifteen IEEE divisions and a second wave of blocks cost more than the shorter chains saved.)
+struct LmpcTrig { double th, sd, cdl, sph, cph, a_rf, a_rr, sqf, cqf, sqr, cqr; };
+LMPC_HD void lmpc_trig_front(const LmpcModel& P, const double* x, const double* u, LmpcTrig& T) {
+  const double ivxe = 1.0 / (x[3] + 1e-3);
+  const double rf = (P.lf * x[5] + x[4]) * ivxe;
+  T.a_rf = atan(rf);
+  const double qf = P.Cf * atan(P.Bf * (u[1] - T.a_rf));
+  sincos(qf, &T.sqf, &T.cqf);
+}
+LMPC_HD void lmpc_trig_rear(const LmpcModel& P, const double* x, LmpcTrig& T) {
+  const double ivxe = 1.0 / (x[3] + 1e-3);
+  const double rr = (P.lr * x[5] - x[4]) * ivxe;
+  T.a_rr = atan(rr);
+  const double qr = P.Cr * atan(P.Br * T.a_rr);
+  sincos(qr, &T.sqr, &T.cqr);
+}
+LMPC_HD void lmpc_trig_controls(const double* u, LmpcTrig& T) { T.th = tanh(u[0]); sincos(u[1], &T.sd, &T.cdl); }
+LMPC_HD void lmpc_trig_heading(const double* x, LmpcTrig& T) { sincos(x[2], &T.sph, &T.cph); }
+
 template <bool JAC>
-LMPC_HD void lmpc_f(const LmpcModel& P, const double* x, const double* u, double kappa, double* xd,
-                    double (*J)[7]) {
-  const double ey = x[1], phi = x[2], vx = x[3], vy = x[4], om = x[5];
+LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u, double kappa, const LmpcTrig& T, double* xd,
+                            double (*J)[7]) {
+  const double ey = x[1], vx = x[3], vy = x[4], om = x[5];
   const double ul = u[0], de = u[1];
   const double m = P.m, l = P.l, lr = P.lr, lf = P.lf;
   // longitudinal command -> drive / brake force (single_track_planar_model.cpp:214-217)
-  const double th = tanh(ul);
+  const double th = T.th;
   const double fd = ul * (0.5 * th + 0.5) * 1000.0;
   const double fb = ul * (-0.5 * th + 0.5) * 1000.0;  // tanh(-u) = -tanh(u)
   const double vsq = vx * vx;
@@ -47,16 +69,11 @@ LMPC_HD void lmpc_f(const LmpcModel& P, const double* x, const double* u, double
   const double ivxe = 1.0 / (vx + 1e-3);
   const double nf = lf * om + vy, nr = lr * om - vy;
   const double rf = nf * ivxe, rr = nr * ivxe;
-  const double af = de - atan(rf);
-  const double ar = atan(rr);
+  const double af = de - T.a_rf;
+  const double ar = T.a_rr;
   // :299-300
   const double pf = P.Bf * af, pr = P.Br * ar;
-  const double qf = P.Cf * atan(pf), qr = P.Cr * atan(pr);
-  double sqf, cqf, sqr, cqr, sd, cdl, sph, cph;
-  sincos(qf, &sqf, &cqf);
-  sincos(qr, &sqr, &cqr);
-  sincos(de, &sd, &cdl);
-  sincos(phi, &sph, &cph);
+  const double sqf = T.sqf, cqf = T.cqf, sqr = T.sqr, cqr = T.cqr, sd = T.sd, cdl = T.cdl, sph = T.sph, cph = T.cph;
   const double Fyf = P.mu * Fzf * sqf;
   const double Fyr = P.mu * Fzr * sqr;
   // :309-319
@@ -124,6 +141,16 @@ LMPC_HD void lmpc_f(const LmpcModel& P, const double* x, const double* u, double
     J[4][2] += -om;
     J[4][4] += -vx;
   }
+}
+
+template <bool JAC>
+LMPC_HD void lmpc_f(const LmpcModel& P, const double* x, const double* u, double kappa, double* xd, double (*J)[7]) {
+  LmpcTrig T;
+  lmpc_trig_front(P, x, u, T);
+  lmpc_trig_rear(P, x, T);
+  lmpc_trig_controls(u, T);
+  lmpc_trig_heading(x, T);
+  lmpc_f_algebra<JAC>(P, x, u, kappa, T, xd, J);
 }
 
 // one integrator step (u, kappa held over the step)
