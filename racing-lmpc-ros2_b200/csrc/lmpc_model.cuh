@@ -143,30 +143,38 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
   }
 }
 
+// Tu: lmpc_trig_controls(u) -- u is held over an integrator step, so its tanh / sincos are evaluated once per step
+template <bool JAC>
+LMPC_HD void lmpc_f_u(const LmpcModel& P, const double* x, const double* u, double kappa, const LmpcTrig& Tu, double* xd, double (*J)[7]) {
+  LmpcTrig T = Tu;
+  lmpc_trig_front(P, x, u, T);
+  lmpc_trig_rear(P, x, T);
+  lmpc_trig_heading(x, T);
+  lmpc_f_algebra<JAC>(P, x, u, kappa, T, xd, J);
+}
 template <bool JAC>
 LMPC_HD void lmpc_f(const LmpcModel& P, const double* x, const double* u, double kappa, double* xd, double (*J)[7]) {
   LmpcTrig T;
-  lmpc_trig_front(P, x, u, T);
-  lmpc_trig_rear(P, x, T);
   lmpc_trig_controls(u, T);
-  lmpc_trig_heading(x, T);
-  lmpc_f_algebra<JAC>(P, x, u, kappa, T, xd, J);
+  lmpc_f_u<JAC>(P, x, u, kappa, T, xd, J);
 }
 
 // one integrator step (u, kappa held over the step)
 LMPC_HD void lmpc_step(const LmpcModel& P, const double* x, const double* u, double kappa, double dt, double* xn) {
   double k1[6], k2[6], k3[6], k4[6], xt[6];
-  lmpc_f<false>(P, x, u, kappa, k1, nullptr);
+  LmpcTrig Tu;
+  lmpc_trig_controls(u, Tu);
+  lmpc_f_u<false>(P, x, u, kappa, Tu, k1, nullptr);
   if (P.integrator == 1) {
     for (int i = 0; i < 6; i++) xn[i] = x[i] + dt * k1[i];
     return;
   }
   for (int i = 0; i < 6; i++) xt[i] = x[i] + dt / 2.0 * k1[i];
-  lmpc_f<false>(P, xt, u, kappa, k2, nullptr);
+  lmpc_f_u<false>(P, xt, u, kappa, Tu, k2, nullptr);
   for (int i = 0; i < 6; i++) xt[i] = x[i] + dt / 2.0 * k2[i];
-  lmpc_f<false>(P, xt, u, kappa, k3, nullptr);
+  lmpc_f_u<false>(P, xt, u, kappa, Tu, k3, nullptr);
   for (int i = 0; i < 6; i++) xt[i] = x[i] + dt * k3[i];
-  lmpc_f<false>(P, xt, u, kappa, k4, nullptr);
+  lmpc_f_u<false>(P, xt, u, kappa, Tu, k4, nullptr);
   for (int i = 0; i < 6; i++) xn[i] = x[i] + dt / 6.0 * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
 }
 
@@ -191,7 +199,9 @@ LMPC_HD void lmpc_linearise(const LmpcModel& P, const double* x, const double* u
                             double* A, double* B, double* g, double* xnext) {
   double J[6][7];
   double k[6], xt[6], acc[6], D[48], Dn[48], Dacc[48];
-  lmpc_f<true>(P, x, u, kappa, k, J);
+  LmpcTrig Tu;
+  lmpc_trig_controls(u, Tu);
+  lmpc_f_u<true>(P, x, u, kappa, Tu, k, J);
   lmpc_tangent_stage(J, 0.0, nullptr, D);
   if (P.integrator == 1) {
     for (int i = 0; i < 6; i++) acc[i] = x[i] + dt * k[i];
@@ -200,15 +210,15 @@ LMPC_HD void lmpc_linearise(const LmpcModel& P, const double* x, const double* u
     const double w6 = dt / 6.0;
     for (int i = 0; i < 6; i++) { acc[i] = k[i]; xt[i] = x[i] + dt / 2.0 * k[i]; }
     for (int i = 0; i < 48; i++) Dacc[i] = D[i];
-    lmpc_f<true>(P, xt, u, kappa, k, J);
+    lmpc_f_u<true>(P, xt, u, kappa, Tu, k, J);
     lmpc_tangent_stage(J, dt / 2.0, D, Dn);
     for (int i = 0; i < 6; i++) { acc[i] += 2.0 * k[i]; xt[i] = x[i] + dt / 2.0 * k[i]; }
     for (int i = 0; i < 48; i++) { Dacc[i] += 2.0 * Dn[i]; D[i] = Dn[i]; }
-    lmpc_f<true>(P, xt, u, kappa, k, J);
+    lmpc_f_u<true>(P, xt, u, kappa, Tu, k, J);
     lmpc_tangent_stage(J, dt / 2.0, D, Dn);
     for (int i = 0; i < 6; i++) { acc[i] += 2.0 * k[i]; xt[i] = x[i] + dt * k[i]; }
     for (int i = 0; i < 48; i++) { Dacc[i] += 2.0 * Dn[i]; D[i] = Dn[i]; }
-    lmpc_f<true>(P, xt, u, kappa, k, J);
+    lmpc_f_u<true>(P, xt, u, kappa, Tu, k, J);
     lmpc_tangent_stage(J, dt, D, Dn);
     for (int i = 0; i < 6; i++) acc[i] = x[i] + w6 * (acc[i] + k[i]);
     for (int i = 0; i < 48; i++) Dacc[i] = w6 * (Dacc[i] + Dn[i]);
