@@ -64,7 +64,7 @@ struct lmpc_handle {
   DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp, ws_qpscr;
   // error-dynamics regression: points of all laps (built lazily after a safe-set change), optional in-tick plan
   DevBuf reg_slab, ws_reg;
-  LmpcRegView reg_view{nullptr, nullptr, 0};
+  LmpcRegView reg_view{nullptr, nullptr, 0, 0};
   bool reg_dirty = true;
   bool reg_in_tick = false;
   LmpcRegPlan reg_plan{};
@@ -446,30 +446,32 @@ static int ensure_reg_slab(lmpc_handle* h) {
     if (l.u.empty()) { h->err = "a stored lap has no u / k / t: the regression needs them"; return LMPC_ERR_INVALID; }
     M += (size_t)(l.n - 1);
   }
-  h->reg_view = LmpcRegView{nullptr, nullptr, 0};
+  h->reg_view = LmpcRegView{nullptr, nullptr, 0, 0};
   if (M == 0) { h->reg_dirty = false; return LMPC_OK; }
-  // slab: Z [M][8] | E [M][6] | Xn [M][6] | kappa [M] | dt [M]   (the last three only feed the prepare kernel)
-  std::vector<double> hd(22 * M);
-  double* Z = hd.data(); double* Xn = Z + 14 * M; double* kp = Xn + 6 * M; double* dt = kp + M;
+  // slab, by column with stride ld (M rounded up to 32): Z [8][ld] | E [6][ld] | Xn [6][ld] | kappa [ld] | dt [ld]
+  // (the last three only feed the prepare kernel)
+  const size_t ld = (M + 31) & ~(size_t)31;
+  std::vector<double> hd(22 * ld, 0.0);
+  double* Z = hd.data(); double* Xn = Z + 14 * ld; double* kp = Xn + 6 * ld; double* dt = kp + ld;
   size_t p = 0;
   for (const HostLap& l : h->laps)
     for (int j = 0; j + 1 < l.n; j++, p++) {
-      for (int c = 0; c < 6; c++) { Z[8 * p + c] = l.x[6 * (size_t)j + c]; Xn[6 * p + c] = l.x[6 * (size_t)(j + 1) + c]; }
-      Z[8 * p + 6] = l.u[2 * (size_t)j]; Z[8 * p + 7] = l.u[2 * (size_t)j + 1];
+      for (int c = 0; c < 6; c++) { Z[c * ld + p] = l.x[6 * (size_t)j + c]; Xn[c * ld + p] = l.x[6 * (size_t)(j + 1) + c]; }
+      Z[6 * ld + p] = l.u[2 * (size_t)j]; Z[7 * ld + p] = l.u[2 * (size_t)j + 1];
       kp[p] = l.k[j]; dt[p] = l.t[j + 1] - l.t[j];
     }
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));   // kernels in flight may still read the old slab
-  int rc = dev_reserve(h, h->reg_slab, sizeof(double) * 22 * M);
+  int rc = dev_reserve(h, h->reg_slab, sizeof(double) * 22 * ld);
   if (rc != LMPC_OK) return rc;
   double* d = (double*)h->reg_slab.p;
-  CK(cudaMemcpyAsync(d, hd.data(), sizeof(double) * 22 * M, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d, hd.data(), sizeof(double) * 22 * ld, cudaMemcpyHostToDevice, h->stream));
   const int threads = 128, blocks = (int)((M + threads - 1) / threads);
-  lmpc_reg_prepare_kernel<<<blocks, threads, 0, h->stream>>>(h->M, (int)M, d, d + 14 * M, d + 20 * M, d + 21 * M, d + 8 * M);
+  lmpc_reg_prepare_kernel<<<blocks, threads, 0, h->stream>>>(h->M, (int)M, (int)ld, d, d + 14 * ld, d + 20 * ld, d + 21 * ld, d + 8 * ld);
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));   // hd is stack-scoped
-  h->reg_view = LmpcRegView{d, d + 8 * M, (int)M};
+  h->reg_view = LmpcRegView{d, d + 8 * ld, (int)M, (int)ld};
   h->reg_dirty = false;
   return LMPC_OK;
 }
@@ -506,8 +508,11 @@ extern "C" int lmpc_safe_set_regress_batch(lmpc_handle* h, int n, const lmpc_reg
     dxq = q6; duq = q2;
   }
   if (h->reg_view.M > 0) {
-    const int threads = 128, blocks = (int)((nz * 32 + threads - 1) / threads);
-    lmpc_regress_items_kernel<<<blocks, threads, 0, h->stream>>>(plan, h->reg_view, n, dxq, duq, dA, dB, dC, dn);
+    LmpcRegItems ri{};
+    ri.n = n; ri.tick = 0; ri.xq = dxq; ri.uq = duq; ri.A = dA; ri.Bm = dB; ri.C = dC; ri.npts = dn;
+    const int blocks = (n + LMPC_REG_WARPS - 1) / LMPC_REG_WARPS;
+    if (lmpc_reg_size_class(plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+    else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
     h->launches++;
     CK(cudaGetLastError());
   } else if (dn) CK(cudaMemsetAsync(dn, 0, sizeof(int32_t) * (size_t)plan.n_out * nz, h->stream));
@@ -782,8 +787,12 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
     int rc = ensure_reg_slab(h);
     if (rc != LMPC_OK) return rc;
     if (h->reg_view.M > 0) {
-      const int threads = 128, blocks = (int)(((size_t)B * NS * 32 + threads - 1) / threads);
-      lmpc_regress_kernel<<<blocks, threads, 0, h->stream>>>(h->reg_plan, h->reg_view, B, (int)N, io.din[0], X_lin, U_lin, io.din[9], abg, skip);
+      LmpcRegItems ri{};
+      ri.n = B * (int)NS; ri.tick = 1; ri.B = B; ri.N = (int)N; ri.x_ic = io.din[0]; ri.X_ref = X_lin; ri.U_ref = U_lin;
+      ri.total_length = io.din[9]; ri.ABg = abg; ri.skip = skip;
+      const int blocks = (ri.n + LMPC_REG_WARPS - 1) / LMPC_REG_WARPS;
+      if (lmpc_reg_size_class(h->reg_plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(h->reg_plan, h->reg_view, ri);
+      else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(h->reg_plan, h->reg_view, ri);
       h->launches++;
       CK(cudaGetLastError());
     }

@@ -183,45 +183,82 @@ __global__ void lmpc_sqp_defect_kernel(LmpcModel M, int B, int N, const double* 
 }
 
 // ---- error-dynamics regression (lmpc_reg_core.cuh)
-// prepare: thread per stored sample p with a successor: E[p] = x_{p+1} - f_d(x_p, u_p, k_p, t_{p+1} - t_p)
-__global__ void lmpc_reg_prepare_kernel(LmpcModel M, int n, const double* __restrict__ Z, const double* __restrict__ Xn,
+// prepare: thread per stored sample p with a successor: E[:, p] = x_{p+1} - f_d(x_p, u_p, k_p, t_{p+1} - t_p).
+// Z [8][ld], Xn [6][ld], E [6][ld] by column.
+__global__ void lmpc_reg_prepare_kernel(LmpcModel M, int n, int ld, const double* __restrict__ Z, const double* __restrict__ Xn,
                                         const double* __restrict__ kappa, const double* __restrict__ dt, double* __restrict__ E) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   double xl[6], ul[2], xn[6];
-  for (int c = 0; c < 6; c++) xl[c] = Z[8 * (size_t)p + c];
-  ul[0] = Z[8 * (size_t)p + 6]; ul[1] = Z[8 * (size_t)p + 7];
+  for (int c = 0; c < 6; c++) xl[c] = Z[(size_t)c * ld + p];
+  ul[0] = Z[(size_t)6 * ld + p]; ul[1] = Z[(size_t)7 * ld + p];
   lmpc_step(M, xl, ul, kappa[p], dt[p], xn);
-  for (int c = 0; c < 6; c++) E[6 * (size_t)p + c] = Xn[6 * (size_t)p + c] - xn[c];
+  for (int c = 0; c < 6; c++) E[(size_t)c * ld + p] = Xn[(size_t)c * ld + p] - xn[c];
 }
 
-// KR, generic form (the C ABI's lmpc_safe_set_regress_batch): warp per item; xq [n][6], uq [n][2]; A [n][36], B [n][12], C [n][6]
-__global__ void lmpc_regress_items_kernel(LmpcRegPlan plan, LmpcRegView v, int n, const double* __restrict__ xq,
-                                          const double* __restrict__ uq, double* __restrict__ A, double* __restrict__ Bm,
-                                          double* __restrict__ C, int* __restrict__ npts) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n) return;
-  double zq[8];
-  for (int c = 0; c < 6; c++) zq[c] = xq[6 * (size_t)w + c];
-  zq[6] = uq[2 * (size_t)w]; zq[7] = uq[2 * (size_t)w + 1];
-  lmpc_regress_warp(plan, v, zq, A + 36 * (size_t)w, Bm + 12 * (size_t)w, C + 6 * (size_t)w, npts ? npts + (size_t)plan.n_out * w : nullptr);
-}
-
-// KR, solve path: warp per (instance b, stage i), query at the linearisation point (abscissa-aligned X_ref_i, U_ref_i),
-// [A|B|g] of the stage updated in place (g takes the affine term C)
-__global__ void lmpc_regress_kernel(LmpcRegPlan plan, LmpcRegView v, int B, int N, const double* __restrict__ x_ic,
-                                    const double* __restrict__ X_ref, const double* __restrict__ U_ref,
-                                    const double* __restrict__ total_length, double* __restrict__ ABg, const int* __restrict__ skip) {
-  const int NS = N - 1;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= B * NS) return;
-  const int b = w / NS, i = w - b * NS;
-  if (skip && skip[b]) return;
-  double zq[8];
-  const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
-  for (int c = 0; c < 6; c++) zq[c] = xr[c];
-  zq[0] = lmpc_align_abscissa(zq[0], x_ic[6 * (size_t)b], total_length[b]);
-  zq[6] = U_ref[(2 * (size_t)NS) * b + 2 * i]; zq[7] = U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
-  double* o = ABg + (54 * (size_t)NS) * b + 54 * i;
-  lmpc_regress_warp(plan, v, zq, o, o + 36, o + 48, nullptr);
+// KR: every query scans every stored sample.  A block of LMPC_REG_WARPS warps (one query each) streams the samples through a
+// shared-memory tile that holds, by column, only the regression's own inputs and its output's error: loaded once per
+// block, read conflict-free by the scan (lane = sample), 8x less L2 traffic than every warp pulling the samples itself.
+// DD = size class of the plan (5: at most four regressors + 1 -- 20 accumulators per lane; 9: the general case, 54).
+#define LMPC_REG_TILE 256
+#define LMPC_REG_WARPS 8
+struct LmpcRegItems {          // where the items of a launch live
+  int n;                       // items
+  int tick;                    // 1: item = (instance b, stage i) of a tick, query at the aligned linearisation point, [A|B|g] in ABg
+  const double *xq, *uq; double *A, *Bm, *C; int* npts;                                                  // generic items
+  int B, N; const double *x_ic, *X_ref, *U_ref, *total_length; double* ABg; const int* skip;              // tick items
+};
+template <int DD>
+__global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel(LmpcRegPlan plan, LmpcRegView v, LmpcRegItems it) {
+  __shared__ __align__(16) double tZ[(DD - 1) * LMPC_REG_TILE];
+  __shared__ __align__(16) double tE[LMPC_REG_TILE];
+  constexpr int D = DD, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int item = blockIdx.x * LMPC_REG_WARPS + w;
+  bool live = item < it.n;
+  double zq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double *A = nullptr, *Bm = nullptr, *C = nullptr; int* npts = nullptr;
+  if (live) {
+    if (it.tick) {
+      const int NS = it.N - 1, b = item / NS, i = item - b * NS;
+      if (it.skip && it.skip[b]) live = false;
+      const double* xr = it.X_ref + (6 * (size_t)it.N) * b + 6 * i;
+      for (int c = 0; c < 6; c++) zq[c] = xr[c];
+      zq[0] = lmpc_align_abscissa(zq[0], it.x_ic[6 * (size_t)b], it.total_length[b]);
+      zq[6] = it.U_ref[(2 * (size_t)NS) * b + 2 * i]; zq[7] = it.U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
+      A = it.ABg + (54 * (size_t)NS) * b + 54 * i; Bm = A + 36; C = A + 48;
+    } else {
+      for (int c = 0; c < 6; c++) zq[c] = it.xq[6 * (size_t)item + c];
+      zq[6] = it.uq[2 * (size_t)item]; zq[7] = it.uq[2 * (size_t)item + 1];
+      A = it.A + 36 * (size_t)item; Bm = it.Bm + 12 * (size_t)item; C = it.C + 6 * (size_t)item;
+      npts = it.npts ? it.npts + (size_t)plan.n_out * item : nullptr;
+    }
+  }
+  const double h = plan.h, ih = 1.0 / h, kc = 0.75 / h;
+  for (int r = 0; r < plan.n_out; r++) {
+    const LmpcRegRow& row = plan.row[r];
+    double q[D], Q[NQ], bv[D], cnt = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NQ; k++) Q[k] = 0.0;
+    for (int t0 = 0; t0 < v.M; t0 += LMPC_REG_TILE) {
+      const int count = min(LMPC_REG_TILE, v.M - t0);
+      __syncthreads();   // the previous tile has been scanned by every warp
+      for (int a = 0; a < row.D - 1; a++)
+        for (int e = threadIdx.x; e < count; e += blockDim.x) tZ[a * LMPC_REG_TILE + e] = v.Z[(size_t)row.sel[a] * v.ld + t0 + e];
+      for (int e = threadIdx.x; e < count; e += blockDim.x) tE[e] = v.E[(size_t)row.out * v.ld + t0 + e];
+      __syncthreads();
+      if (live) lmpc_reg_scan_lane<DD, true>(row, h, ih, kc, q, tZ, tE, LMPC_REG_TILE, count, lane, Q, bv, cnt);
+    }
+    if (live) {   // warp-uniform: a warp is one item
+      LaneVar<double> acc[NV];
+#pragma unroll
+      for (int k = 0; k < NQ; k++) acc[k].v = Q[k];
+#pragma unroll
+      for (int a = 0; a < D; a++) acc[NQ + a].v = bv[a];
+      acc[NQ + D].v = cnt;
+      lmpc_reg_finish<DD>(plan, row, acc, A, Bm, C, npts ? npts + r : nullptr);
+    }
+  }
 }

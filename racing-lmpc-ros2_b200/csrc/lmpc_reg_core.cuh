@@ -59,117 +59,155 @@ static inline bool lmpc_make_reg_plan(const lmpc_reg_spec* sp, LmpcRegPlan* plan
   return true;
 }
 
-// Device view of the regression points: Z [M][8] = (x, u) of every sample with a successor, E [M][6] its model error
+// Device view of the regression points, by column (a lane per sample reads consecutive doubles): Z [8][ld] = (x, u) of
+// every sample with a successor, E [6][ld] its model error; M samples, ld >= M the column stride
 struct LmpcRegView {
   const double* Z;
   const double* E;
   int M;
+  int ld;
 };
 
-// One query item.  zq [8] = (x_q, u_q).  A (6x6 column-major), B (6x2 column-major), C (6) are updated in place.
+// One lane's share of the scan of `count` points (global memory or a shared-memory tile):
+// points lane, lane + 32, ...  Accumulates the upper triangle of M'KM into Q, M'Ky into bv and the number of points
+// within dist_max into cnt.  Visiting the points tile by tile (tiles a multiple of 32 long) keeps every lane's order.
+// DD: compile-time size of the regression (5 covers the LMPC paper's choice of three states and one control; 9 everything).
+// GATHERED = false: Z, E are the by-column arrays of the view (column sel[a] at Z + sel[a] ld).  GATHERED = true: Z is a tile that
+// already holds the regression's own columns in order (column a at Z + a ld) and E its output column.
+template <int DD, bool GATHERED>
+LMPC_DEV void lmpc_reg_scan_lane(const LmpcRegRow& row, double h, double ih, double kc, const double* q, const double* Z,
+                                 const double* E, int ld, int count, int lane, double* Q, double* bv, double& cnt) {
+  constexpr int D = DD;
+  const double h2 = h * h * (1.0 + 1e-12);   // cheap rejection on the squared distance; the exact test d < h follows
+  for (int p = lane; p < count; p += 32) {
+    double m[D], d2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+      const int s = row.sel[a];
+      m[a] = (s < 8) ? Z[(size_t)(GATHERED ? a : s) * ld + p] : (s == 8 ? 1.0 : 0.0);
+      if (s < 8) { const double t = m[a] - q[a]; d2 += t * t; }
+    }
+    if (!(d2 < h2)) continue;
+    const double d = sqrt(d2);
+    if (d < h) {
+      const double t = d * ih, u1 = 1.0 - t * t;
+      const double w = kc * u1 * u1;
+      const double y = E[(size_t)(GATHERED ? 0 : row.out) * ld + p];
+#pragma unroll
+      for (int a = 0, k = 0; a < D; a++) {
+        const double wa = w * m[a];
+        bv[a] += wa * y;
+#pragma unroll
+        for (int b = a; b < D; b++, k++) Q[k] += wa * m[b];
+      }
+      cnt += 1.0;
+    }
+  }
+}
+
+// After the scan: all-reduce of the partial normal equations (acc: Q upper triangle row-major, then M'Ky, then the count),
+// Cholesky of Q + ridge I (every lane the same), solve, update of A (6x6 column-major), B (6x2 column-major), C (6).
+template <int DD>
+LMPC_DEV void lmpc_reg_finish(const LmpcRegPlan& plan, const LmpcRegRow& row, LaneVar<double> (&acc)[DD * (DD + 1) / 2 + DD + 1],
+                              double* A, double* B, double* C, int* npts_r) {
+  constexpr int D = DD, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
+  {
+    int ops[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) ops[k] = LMPC_RED_SUM;
+    group_reduce<1, NV>(acc, ops, nullptr);
+  }
+  const int used = (int)(acc[NQ + D](0) + 0.5);
+  LANES_BEGIN
+    if (lane == 0 && npts_r) *npts_r = used;
+  LANES_END
+  if (used == 0) return;   // safe_set.cpp:203-205
+  // ---- Cholesky of Q + ridge I (uniform: every lane holds the reduced sums), unused rows are ridge-only
+  double Lc[NQ], R[D];       // lower factor stored in the same packed upper-triangle slots: L[b][a] at (a, b), a <= b
+#pragma unroll
+  for (int a = 0, k = 0; a < D; a++)
+#pragma unroll
+    for (int b = a; b < D; b++, k++) Lc[k] = acc[k](0) + (a == b ? plan.ridge : 0.0);
+#define LMPC_RQ(a, b) Lc[(a) * D - (a) * ((a) - 1) / 2 + ((b) - (a))]
+#pragma unroll
+  for (int j = 0; j < D; j++) {
+    double dg = LMPC_RQ(j, j);
+#pragma unroll
+    for (int k = 0; k < j; k++) dg -= LMPC_RQ(k, j) * LMPC_RQ(k, j);
+    const double il = 1.0 / sqrt(dg);   // dg >= ridge > 0
+    LMPC_RQ(j, j) = il;
+#pragma unroll
+    for (int i = j + 1; i < D; i++) {
+      double a2 = LMPC_RQ(j, i);
+#pragma unroll
+      for (int k = 0; k < j; k++) a2 -= LMPC_RQ(k, i) * LMPC_RQ(k, j);
+      LMPC_RQ(j, i) = a2 * il;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double a2 = plan.sign * acc[NQ + i](0);
+#pragma unroll
+    for (int k = 0; k < i; k++) a2 -= LMPC_RQ(k, i) * R[k];
+    R[i] = a2 * LMPC_RQ(i, i);
+  }
+#pragma unroll
+  for (int i = D - 1; i >= 0; i--) {
+    double a2 = R[i];
+#pragma unroll
+    for (int k = i + 1; k < D; k++) a2 -= LMPC_RQ(i, k) * R[k];
+    R[i] = a2 * LMPC_RQ(i, i);
+  }
+#undef LMPC_RQ
+  // ---- lane a adds R[a] where sel[a] points
+  LANES_BEGIN
+    if (lane < row.D) {
+      double ra = R[0];
+#pragma unroll
+      for (int a = 1; a < D; a++) if (lane == a) ra = R[a];
+      const int s = row.sel[lane];
+      if (s < 6) A[row.out + 6 * s] += ra;
+      else if (s < 8) B[row.out + 6 * (s - 6)] += ra;
+      else if (s == 8) C[row.out] += ra;
+    }
+  LANES_END
+}
+
+// One query item over points in global memory (the emulator's and the reference form; the CUDA kernels stream the points
+// the same way, lmpc_kernels.cuh).  zq [8] = (x_q, u_q).  A, B, C are updated in place.
 // npts (optional): points used per regression [n_out].
-LMPC_DEV void lmpc_regress_warp(const LmpcRegPlan& plan, const LmpcRegView& v, const double* zq, double* A, double* B,
-                                double* C, int* npts) {
-  constexpr int D = LMPC_REG_D, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
+template <int DD>
+LMPC_DEV void lmpc_regress_warp_d(const LmpcRegPlan& plan, const LmpcRegView& v, const double* zq, double* A, double* B,
+                                  double* C, int* npts) {
+  constexpr int D = DD, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
   const double h = plan.h, ih = 1.0 / h, kc = 0.75 / h;
   for (int r = 0; r < plan.n_out; r++) {
     const LmpcRegRow& row = plan.row[r];
-    LaneVar<double> acc[NV];   // Q upper triangle (a <= b) row-major, then M'Ky, then the point count
+    LaneVar<double> acc[NV];
     LANES_BEGIN
       double q[D], Q[NQ], bv[D], cnt = 0.0;
 #pragma unroll
       for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; }
 #pragma unroll
       for (int k = 0; k < NQ; k++) Q[k] = 0.0;
-      for (int p = lane; p < v.M; p += 32) {
-        const double* zp = v.Z + 8 * (size_t)p;
-        double m[D], d2 = 0.0;
-#pragma unroll
-        for (int a = 0; a < D; a++) {
-          const int s = row.sel[a];
-          m[a] = (s < 8) ? zp[s] : (s == 8 ? 1.0 : 0.0);
-          if (s < 8) { const double t = m[a] - q[a]; d2 += t * t; }
-        }
-        const double d = sqrt(d2);
-        if (d < h) {
-          const double t = d * ih, u1 = 1.0 - t * t;
-          const double w = kc * u1 * u1;
-          const double y = v.E[6 * (size_t)p + row.out];
-#pragma unroll
-          for (int a = 0, k = 0; a < D; a++) {
-            const double wa = w * m[a];
-            bv[a] += wa * y;
-#pragma unroll
-            for (int b = a; b < D; b++, k++) Q[k] += wa * m[b];
-          }
-          cnt += 1.0;
-        }
-      }
+      lmpc_reg_scan_lane<DD, false>(row, h, ih, kc, q, v.Z, v.E, v.ld, v.M, lane, Q, bv, cnt);
 #pragma unroll
       for (int k = 0; k < NQ; k++) acc[k](lane) = Q[k];
 #pragma unroll
       for (int a = 0; a < D; a++) acc[NQ + a](lane) = bv[a];
       acc[NQ + D](lane) = cnt;
     LANES_END
-    {
-      int ops[NV];
-#pragma unroll
-      for (int k = 0; k < NV; k++) ops[k] = LMPC_RED_SUM;
-      group_reduce<1, NV>(acc, ops, nullptr);
-    }
-    const int used = (int)(acc[NQ + D](0) + 0.5);
-    LANES_BEGIN
-      if (lane == 0 && npts) npts[r] = used;
-    LANES_END
-    if (used == 0) continue;   // safe_set.cpp:203-205
-    // ---- Cholesky of Q + ridge I (uniform: every lane holds the reduced sums), unused rows are ridge-only
-    double Lc[NQ], R[D];       // lower factor stored in the same packed upper-triangle slots: L[b][a] at (a, b), a <= b
-#pragma unroll
-    for (int a = 0, k = 0; a < D; a++)
-#pragma unroll
-      for (int b = a; b < D; b++, k++) Lc[k] = acc[k](0) + (a == b ? plan.ridge : 0.0);
-#define LMPC_RQ(a, b) Lc[(a) * D - (a) * ((a) - 1) / 2 + ((b) - (a))]
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-      double dg = LMPC_RQ(j, j);
-#pragma unroll
-      for (int k = 0; k < j; k++) dg -= LMPC_RQ(k, j) * LMPC_RQ(k, j);
-      const double il = 1.0 / sqrt(dg);   // dg >= ridge > 0
-      LMPC_RQ(j, j) = il;
-#pragma unroll
-      for (int i = j + 1; i < D; i++) {
-        double a2 = LMPC_RQ(j, i);
-#pragma unroll
-        for (int k = 0; k < j; k++) a2 -= LMPC_RQ(k, i) * LMPC_RQ(k, j);
-        LMPC_RQ(j, i) = a2 * il;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < D; i++) {
-      double a2 = plan.sign * acc[NQ + i](0);
-#pragma unroll
-      for (int k = 0; k < i; k++) a2 -= LMPC_RQ(k, i) * R[k];
-      R[i] = a2 * LMPC_RQ(i, i);
-    }
-#pragma unroll
-    for (int i = D - 1; i >= 0; i--) {
-      double a2 = R[i];
-#pragma unroll
-      for (int k = i + 1; k < D; k++) a2 -= LMPC_RQ(i, k) * R[k];
-      R[i] = a2 * LMPC_RQ(i, i);
-    }
-#undef LMPC_RQ
-    // ---- lane a adds R[a] where sel[a] points
-    LANES_BEGIN
-      if (lane < row.D) {
-        double ra = R[0];
-#pragma unroll
-        for (int a = 1; a < D; a++) if (lane == a) ra = R[a];
-        const int s = row.sel[lane];
-        if (s < 6) A[row.out + 6 * s] += ra;
-        else if (s < 8) B[row.out + 6 * (s - 6)] += ra;
-        else if (s == 8) C[row.out] += ra;
-      }
-    LANES_END
+    lmpc_reg_finish<DD>(plan, row, acc, A, B, C, npts ? npts + r : nullptr);
   }
+}
+// the size class of a plan: 5 when every regression has at most four inputs, else 9
+LMPC_HD int lmpc_reg_size_class(const LmpcRegPlan& plan) {
+  int dmax = 0;
+  for (int r = 0; r < plan.n_out; r++) dmax = plan.row[r].D > dmax ? plan.row[r].D : dmax;
+  return dmax <= 5 ? 5 : LMPC_REG_D;
+}
+LMPC_DEV void lmpc_regress_warp(const LmpcRegPlan& plan, const LmpcRegView& v, const double* zq, double* A, double* B,
+                                double* C, int* npts) {
+  if (lmpc_reg_size_class(plan) == 5) lmpc_regress_warp_d<5>(plan, v, zq, A, B, C, npts);
+  else lmpc_regress_warp_d<LMPC_REG_D>(plan, v, zq, A, B, C, npts);
 }

@@ -71,6 +71,25 @@ def test_emulated_regression_matches_oracle(emu, pkg):
     assert worst < 1e-9, worst
 
 
+def test_emulated_regression_general_size_class(emu, pkg):
+    """Regressions with more than four inputs take the general (9-wide) instantiation: five states + both controls."""
+    import oracle_regress as R
+    from racing_lmpc_ros2_b200.binding import make_reg_spec
+    o, laps, pts = _points(pkg)
+    Z = np.ascontiguousarray(np.vstack([p[0] for p in pts])); E = np.ascontiguousarray(np.vstack([p[1] for p in pts]))
+    out, in_x, in_u, h = [3, 5], [[1, 2, 3, 4, 5], [3, 4, 5]], [[0, 1], [1]], 0.8
+    spec = make_reg_spec(out, in_x, in_u, h)
+    xq, uq, kq = _queries(laps, 8, 21)
+    worst = 0.0
+    for i in range(len(xq)):
+        A0, B0, g0, _ = o.linearise(xq[i], uq[i], kq[i], 0.025)
+        A2, B2, C2, n2 = R.regress(pts, out, in_x, in_u, h, xq[i], uq[i], A0, B0, g0)
+        A1, B1, C1, n1 = _emu_regress(emu, spec, Z, E, xq[i], uq[i], A0, B0, g0)
+        assert (n1 == n2).all() and n1.sum() > 0
+        worst = max(worst, np.abs(A1 - A2).max(), np.abs(B1 - B2).max(), np.abs(C1 - C2).max())
+    assert worst < 1e-8, worst
+
+
 def test_emulated_regression_sign_and_empty(emu, pkg):
     from racing_lmpc_ros2_b200.binding import make_reg_spec
     o, laps, pts = _points(pkg)
