@@ -772,8 +772,13 @@ int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* 
     }
     if (step < tol) break;
     if (k > 0) {
+      /* successive displacements (anti)parallel: one mode d_k = (1 - alpha (1 + rho)) d_{k-1} dominates; the secant step
+       * alpha / (1 - d_k.d_{k-1} / |d_{k-1}|^2) = 1 / (1 + rho) cancels it.  Otherwise halve on oscillation, double on progress. */
       const double cs = dp / sqrt(dd * pp + 1e-300);
-      if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125); else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
+      const double sr = dp / (pp + 1e-300);
+      if (fabs(cs) > 0.9) alpha = (1.0 - sr > 0.1) ? fmin(fmax(alpha / (1.0 - sr), 0.125), 1.0) : 1.0;
+      else if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125);
+      else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
     }
     for (int q = 0; q < 6 * N; q++) Xk[q] += alpha * dprev[q];
     for (int q = 0; q < 2 * nst; q++) Uk[q] += alpha * dprev[6 * N + q];

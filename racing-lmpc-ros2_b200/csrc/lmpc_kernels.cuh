@@ -130,8 +130,9 @@ __global__ void lmpc_sqp_init_kernel(int B, int N, const double* __restrict__ x_
 }
 
 // update: d = QP solution - linearisation point; step = max |d| / max(1, |new|) over X and U; the linearisation point
-// moves by alpha d, alpha following the angle between successive displacements (cos < -0.25: oscillation of the
-// Gauss-Newton iteration -> halve, >= 1/8; cos > 0.25 -> double, <= 1).
+// moves by alpha d, alpha following successive displacements: (anti)parallel (|cos| > 0.9) -> the secant step length that
+// cancels the dominant mode; else cos < -0.25 (oscillation of the Gauss-Newton iteration) -> halve, >= 1/8; cos > 0.25 ->
+// double, <= 1.
 // done: 1 = converged (step < tol), 2 = the QP failed (its status stays in the output).
 __global__ void lmpc_sqp_update_kernel(int B, int N, double tol, const double* __restrict__ X, const double* __restrict__ U,
                                        const int* __restrict__ status, double* __restrict__ Xk, double* __restrict__ Uk,
@@ -156,8 +157,13 @@ __global__ void lmpc_sqp_update_kernel(int B, int N, double tol, const double* _
   if (step < tol) { done[b] = 1; return; }
   double alpha = alpha_[b];
   if (k > 0) {
+    // successive displacements (anti)parallel: one mode d_k = (1 - alpha (1 + rho)) d_{k-1} dominates; the secant step
+    // alpha / (1 - d_k.d_{k-1} / |d_{k-1}|^2) = 1 / (1 + rho) cancels it.  Otherwise halve on oscillation, double on progress.
     const double cs = dp / sqrt(dd * pp + 1e-300);
-    if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125); else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
+    const double sr = dp / (pp + 1e-300);
+    if (fabs(cs) > 0.9) alpha = (1.0 - sr > 0.1) ? fmin(fmax(alpha / (1.0 - sr), 0.125), 1.0) : 1.0;
+    else if (cs < -0.25) alpha = fmax(0.5 * alpha, 0.125);
+    else if (cs > 0.25) alpha = fmin(2.0 * alpha, 1.0);
     alpha_[b] = alpha;
   }
   for (int q = 0; q < nx; q++) xk[q] += alpha * dpv[q];
