@@ -204,3 +204,37 @@ def test_emulated_qp_kernel_all_state_boxes(emu, pkg, name):
         worst = max(worst, relerr(k["X"], dref["X"]), relerr(k["U"], dref["U"]), relerr(k["dU"], dref["dU"]))
         n += 1
     assert n >= 3 and worst < 1e-6, (n, worst)
+
+
+@pytest.mark.parametrize("hs", [[0.0] * 6, [20.0, 20.0, 0.0, 20.0, 0.0, 2.0]], ids=["hard_hull", "partly_free_slack"])
+def test_emulated_qp_kernel_hull_slack_variants(emu, pkg, hs):
+    """`convex_hull_slack` all zero -> the hull is a hard equality x_N = SS lambda (racing_mpc.cpp:493,502-503); a zero
+    weight on some components only -> those slack components are free and their hull rows vacuous.  Infeasible hard-hull
+    instances must be reported by kernel and oracle alike."""
+    from oracle import Oracle
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc", tol=1e-11)
+    cfg = dict(cfg, convex_hull_slack=hs, tol=1e-11)
+    od = Oracle(veh, cfg)
+    for l in pkg.workload.load_laps():
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 8, 0xC0, track, pkg.workload.load_laps(), mode=mode)
+    worst, n, nfail = 0.0, 0, 0
+    for b in range(8):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        k = _emu_solve(emu, pkg, od, veh, dict(cfg, tol=1e-13), inp)
+        if d["status"] != 0:
+            assert k["status"] != 0
+            nfail += 1
+            continue
+        if not (d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        assert k["status"] == 0
+        worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"]))
+        assert abs(k["cost"] - d["cost"]) < 1e-8 * max(1, abs(d["cost"]))
+        if not any(hs):
+            assert np.abs(k["X"][-1] - k["ss_x"].T @ k["lam"]).max() < 1e-9      # terminal state inside the hull
+        n += 1
+    assert n >= 6 and worst < 1e-6, (n, worst)
+    if not any(hs):
+        assert nfail >= 1        # seed 0xC0 holds one initial state that cannot reach the hull in N steps

@@ -141,6 +141,40 @@ def test_solve_matches_dense_oracle(pkg, name):
     print(f"[{name}] worst relative error vs dense oracle over {n} instances: {worst:.2e}")
 
 
+@pytest.mark.parametrize("hs", [[0.0] * 6, [20.0, 20.0, 0.0, 20.0, 0.0, 2.0]], ids=["hard_hull", "partly_free_slack"])
+def test_hull_slack_variants_match_dense_oracle(pkg, laps, barc_track, hs):
+    """`convex_hull_slack` = 0: hard hull equality (racing_mpc.cpp:493,502-503); zero weight on some components: free
+    slack, vacuous rows.  Instances the dense oracle finds infeasible must come back with a non-zero status."""
+    from oracle import Oracle
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    veh, cfg, track, mode = make_case(pkg, "barc_lmpc", None, None)
+    cfg = dict(cfg, convex_hull_slack=hs)
+    m = BatchedRacingMPC(veh, cfg, max_batch=32)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    for l in laps:
+        m.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 32, 0xC0, track, laps, mode=mode)
+    out = m.solve(batch)
+    worst, n, nfail = 0.0, 0, 0
+    for b in range(32):
+        d = od.step(pkg.workload.instance(batch, b), impl="dense")
+        if d["status"] != 0:
+            assert out["status"][b] != 0
+            nfail += 1
+            continue
+        if not (d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        assert out["status"][b] == 0
+        worst = max(worst, relerr(out["X_optm"][b], d["X"]), relerr(out["U_optm"][b], d["U"]), relerr(out["dU_optm"][b], d["dU"]))
+        assert abs(out["cost"][b] - d["cost"]) < 1e-7 * max(1, abs(d["cost"]))
+        if not any(hs):
+            assert np.abs(out["X_optm"][b][-1] - out["ss_x"][b].T @ out["convex_combi_optm"][b]).max() < 1e-8
+        n += 1
+    assert n >= 20 and worst < TOL, (n, worst)
+    print(f"[hull slack {hs}] worst relative error vs dense oracle over {n} instances ({nfail} infeasible, reported): {worst:.2e}")
+
+
 def test_full_size_batch_properties_config2(pkg):
     """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): port parity on a sample plus
     size-independent invariants on every instance."""
