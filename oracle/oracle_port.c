@@ -155,6 +155,46 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       w->x[6 * (i + 1) + r] = a;
     }
   }
+  /* A linear rollout that leaves the neighbourhood of the linearisation is useless as a start and would set the channel
+   * scales of the stopping test (an explicit-Euler discretisation of the stiff lateral dynamics is unstable at
+   * dt = 0.025: |x| grows to 1e5 over 19 stages).  Any channel beyond 100 x max(1, |x_ic|, |X_ref[N-1]|) => roll out
+   * again with controls chosen stage by stage (2x2 least squares, clipped into the box) so that the velocity states
+   * (v_x, v_y, omega) follow the chord x_ic -> X_ref[N-1]; the iterate stays dynamically feasible. */
+  {
+    int diverged = 0;
+    for (int k = 0; k < 6; k++) {
+      const double lim = 100.0 * fmax(1.0, fmax(fabs(p->x_ic[k]), fabs(p->Xref[6 * (N - 1) + k])));
+      for (int i = 1; i < N; i++) if (!(fabs(w->x[6 * i + k]) <= lim)) diverged = 1;
+    }
+    if (diverged) {
+      for (int i = 0; i < N - 1; i++) {
+        const double* A = p->A + 36 * i; const double* B = p->B + 12 * i; const double* g = p->g + 6 * i;
+        double r[3], M00 = 1e-12, M01 = 0.0, M11 = 1e-12, b0 = 0.0, b1 = 0.0;
+        for (int q = 0; q < 3; q++) {
+          const int c = 3 + q;
+          double a = g[c] - (p->x_ic[c] + (p->Xref[6 * (N - 1) + c] - p->x_ic[c]) * ((double)(i + 1) / (double)(N - 1)));
+          for (int k = 0; k < 6; k++) a += A[c + 6 * k] * w->x[6 * i + k];
+          r[q] = a;
+          M00 += B[c] * B[c]; M01 += B[c] * B[c + 6]; M11 += B[c + 6] * B[c + 6];
+          b0 -= B[c] * a; b1 -= B[c + 6] * a;
+        }
+        (void)r;
+        const double det = M00 * M11 - M01 * M01;
+        double uu[2] = {(M11 * b0 - M01 * b1) / det, (M00 * b1 - M01 * b0) / det};
+        for (int k = 0; k < 2; k++) {
+          if (!(uu[k] <= p->uhi[k])) uu[k] = p->uhi[k];
+          if (!(uu[k] >= p->ulo[k])) uu[k] = p->ulo[k];
+          w->u[2 * i + k] = uu[k];
+        }
+        for (int rr = 0; rr < 6; rr++) {
+          double a = g[rr];
+          for (int k = 0; k < 6; k++) a += A[rr + 6 * k] * w->x[6 * i + k];
+          for (int k = 0; k < 2; k++) a += B[rr + 6 * k] * w->u[2 * i + k];
+          w->x[6 * (i + 1) + rr] = a;
+        }
+      }
+    }
+  }
   /* channel scales max(1, |channel|) of the parity metric, from the initial iterate */
   double chx[6] = {1, 1, 1, 1, 1, 1}, chu[2] = {1, 1}, chd[2] = {1, 1};
   for (int i = 0; i < N; i++) for (int k = 0; k < 6; k++) chx[k] = fmax(chx[k], fabs(w->x[6 * i + k]));

@@ -337,6 +337,56 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     GLANES_END(NW)
   }
 
+  // A rollout that leaves the neighbourhood of the linearisation is useless as a start and would set the channel scales
+  // of the stopping test (explicit Euler on the stiff lateral dynamics is unstable at dt = 0.025: |x| reaches 1e5 over 19
+  // stages).  Any channel beyond 100 x max(1, |x_ic|, |X_ref[N-1]|) => roll out again with controls chosen stage by stage
+  // (2x2 least squares, clipped into the box) so that v_x, v_y, omega follow the chord x_ic -> X_ref[N-1]; the iterate
+  // stays dynamically feasible.  Never taken on the shipped (RK4) configurations.  Same rule in oracle/oracle_port.c.
+  {
+    LaneVar<double, NT> dv[1];
+    GLANES_BEGIN(NT)
+      double far = 0.0;
+      if (lane < 6) {
+        const double lim = 100.0 * fmax(1.0, fmax(fabs(in.x_ic[lane]), fabs(in.cen[lane])));
+        for (int i = 1; i < N; i++) if (!(fabs(X[lane * d + i]) <= lim)) far = 1.0;
+      }
+      dv[0](lane) = far;
+    GLANES_END(NW)
+    const int op1[1] = {LMPC_RED_MAX};
+    group_reduce<NW, 1>(dv, op1, RED);
+    if (dv[0](0) > 0.0) {
+      const double ich = 1.0 / (double)(N - 1);
+      for (int i = 0; i < NS; i++) {
+        GLANES_BEGIN(NT)
+          if (lane < 2) {
+            const double* A = ABG + 54 * i; const double* B = A + 36; const double* g = A + 48;
+            double M00 = 1e-12, M01 = 0.0, M11 = 1e-12, b0 = 0.0, b1 = 0.0;
+            for (int c = 3; c < 6; c++) {
+              double a = g[c] - (in.x_ic[c] + (in.cen[c] - in.x_ic[c]) * ((double)(i + 1) * ich));
+              for (int k = 0; k < 6; k++) a += A[c + 6 * k] * X[k * d + i];
+              M00 += B[c] * B[c]; M01 += B[c] * B[c + 6]; M11 += B[c + 6] * B[c + 6];
+              b0 -= B[c] * a; b1 -= B[c + 6] * a;
+            }
+            const double det = M00 * M11 - M01 * M01;
+            double uu = lane ? (M00 * b1 - M01 * b0) / det : (M11 * b0 - M01 * b1) / det;
+            if (!(uu <= P.uhi[lane])) uu = P.uhi[lane];
+            if (!(uu >= P.ulo[lane])) uu = P.ulo[lane];
+            U[lane * d + i] = uu;
+          }
+        GLANES_END(NW)
+        GLANES_BEGIN(NT)
+          if (lane < 6) {
+            const double* A = ABG + 54 * i; const double* B = A + 36; const double* g = A + 48;
+            double a = g[lane];
+            for (int k = 0; k < 6; k++) a += A[lane + 6 * k] * X[k * d + i];
+            for (int k = 0; k < 2; k++) a += B[lane + 6 * k] * U[k * d + i];
+            X[lane * d + i + 1] = a;
+          }
+        GLANES_END(NW)
+      }
+    }
+  }
+
   // ---------------------------------------------------------------- initial slacks / multipliers, channel scales
   double th = th0, yth = mu0 / th0, dth = 0.0, dyth = 0.0, dtha = 0.0, dytha = 0.0;
   LaneVar<ArrK, NT> lam, ylam, omg_;   // lambda block: iterate and weights in registers ...

@@ -238,3 +238,35 @@ def test_emulated_qp_kernel_hull_slack_variants(emu, pkg, hs):
     assert n >= 6 and worst < 1e-6, (n, worst)
     if not any(hs):
         assert nfail >= 1        # seed 0xC0 holds one initial state that cannot reach the hull in N steps
+
+
+@pytest.mark.parametrize("name", ["barc_lmpc", "barc_tracking"])
+def test_emulated_qp_kernel_euler_integrator(emu, pkg, name):
+    """`integrator_type: euler` (single_track_planar_model.cpp:362-366; no shipped parameter file selects it).  Explicit
+    Euler on the BARC's lateral dynamics is unstable at dt = 0.025: the linear rollout from x_ic grows to 1e5 over 19
+    stages, which used to cost 30 iterations and set the channel scales of the stopping test (errors up to 5e-4 with
+    status 0).  With the guarded start the kernel needs the usual 10-14 iterations; what is left is the conditioning of
+    the problem itself (rounding x growth), which the polish cannot always certify: the LMPC case lands below 1e-6
+    throughout, the tracking case on at least 6 of 8 instances and never worse than 1e-3."""
+    from conftest import make_case
+    from oracle import Oracle
+    veh, cfg, track, mode = make_case(pkg, name, None, None)      # the kernel runs at its default tolerance
+    veh = dict(veh, integrator=1)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    if cfg["learning"]:
+        for l in pkg.workload.load_laps():
+            od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 8, 0xEE, track, pkg.workload.load_laps(), mode=mode)
+    errs, its = [], []
+    for b in range(8):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        k = _emu_solve(emu, pkg, od, veh, cfg, inp)
+        assert k["status"] == 0
+        errs.append(max(relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"])))
+        its.append(k["iters"])
+    errs = np.array(errs)
+    assert len(errs) >= 7 and max(its) <= 20, (len(errs), its)
+    assert errs.max() < 1e-3 and (errs < 1e-6).sum() >= (len(errs) if name == "barc_lmpc" else 6), errs

@@ -175,6 +175,35 @@ def test_hull_slack_variants_match_dense_oracle(pkg, laps, barc_track, hs):
     print(f"[hull slack {hs}] worst relative error vs dense oracle over {n} instances ({nfail} infeasible, reported): {worst:.2e}")
 
 
+@pytest.mark.parametrize("name", ["barc_lmpc", "barc_tracking"])
+def test_euler_integrator_matches_dense_oracle(pkg, laps, name):
+    """`integrator_type: euler` through the C ABI (linearisation and QP): unstable discretisation of the BARC's lateral
+    dynamics at dt = 0.025, see tests/test_emulator.py::test_emulated_qp_kernel_euler_integrator for the bar."""
+    from oracle import Oracle
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    veh, cfg, track, mode = make_case(pkg, name, None, None)
+    veh = dict(veh, integrator=1)
+    m = BatchedRacingMPC(veh, cfg, max_batch=16)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    if cfg["learning"]:
+        for l in laps:
+            m.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+            od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, 16, 0xEE, track, laps, mode=mode)
+    out = m.solve(batch)
+    errs = []
+    for b in range(16):
+        d = od.step(pkg.workload.instance(batch, b), impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        assert out["status"][b] == 0
+        errs.append(max(relerr(out["X_optm"][b], d["X"]), relerr(out["U_optm"][b], d["U"]), relerr(out["dU_optm"][b], d["dU"])))
+    errs = np.array(errs)
+    assert len(errs) >= 12 and out["iters"].max() <= 20, (len(errs), out["iters"])
+    assert errs.max() < 1e-3 and (errs < TOL).sum() >= (len(errs) if name == "barc_lmpc" else len(errs) - 3), errs
+    print(f"[{name}, euler] {len(errs)} instances: median {np.median(errs):.2e}, worst {errs.max():.2e}, below 1e-6: {(errs < TOL).sum()}, iterations max {out['iters'].max()}")
+
+
 def test_full_size_batch_properties_config2(pkg):
     """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): port parity on a sample plus
     size-independent invariants on every instance."""
