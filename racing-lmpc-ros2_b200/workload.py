@@ -31,6 +31,27 @@ def synthesise_laps(laps, n_laps, seed=0xB200 + 4, sigma_ey=0.02, sigma_vx=0.05)
     return out
 
 
+def synthesise_track_laps(track, vehicle, dt, n_laps=3, seed=0xB200 + 6, vel_scale=0.9):
+    """Laps for a track without recorded ones (IAC LMPC on Putnam): the table's line driven at vel_scale x its speed
+    profile, sampled every dt from s = 0 to L; e_y / e_psi / v_y small seeded noise, omega = v kappa, steering holding the
+    local curvature.  Lap j is a little faster than lap j-1 (what a learning run records)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    L = track["length"]
+    out = []
+    for j in range(n_laps):
+        sc = vel_scale * (1.0 + 0.02 * j)
+        s, t, xs, us, ks, ts = 0.0, 0.0, [], [], [], []
+        while s < L:
+            v = float(track_lookup(track, s, "speed")) * sc
+            k = float(track_lookup(track, s, "curvature"))
+            xs.append([s, 0.0, 0.0, v, 0.0, v * k]); us.append([0.5, float(np.arctan(vehicle["wheel_base"] * k))]); ks.append(k); ts.append(t)
+            s += v * dt; t += dt
+        x = np.array(xs); n = x.shape[0]
+        x[:, 1] += rng.standard_normal(n) * 0.1; x[:, 2] += rng.standard_normal(n) * 0.005; x[:, 4] += rng.standard_normal(n) * 0.02
+        out.append(dict(x=x, u=np.array(us), k=np.array(ks), t=np.array(ts)))
+    return out
+
+
 def load_track(name):
     z = np.load(os.path.join(_GOLD, "tracks.npz"))
     return dict(s=z[f"{name}_s"], speed=z[f"{name}_speed"], curvature=z[f"{name}_curvature"],

@@ -63,6 +63,22 @@ def make_case(pkg, name, tol=None, N=None):
     return veh, cfg, pkg.workload.load_track(tk), mode
 
 
+def make_extra_case(pkg, name):
+    """The two shipped parameter sets that BASELINE.json's configs do not name (parity cases only):
+    "hawaii_kart_tracking": racing_mpc/hawaii_kart_tracking_mpc.param.yaml on mgkt_optm.txt (the reference's own
+      test_racing_mpc.cpp drives this track), N = 10, dt = 0.1;
+    "iac_lmpc": racing_mpc/iac_car_lmpc.param.yaml, N = 60 at dt = 0.1 (sim_putnam_short_lmpc.launch.py:81) on the Putnam
+      table with three synthesised laps; the 6 s horizon from a constant-steering reference needs up to ~40 interior-point
+      iterations in the dense oracle and the kernel alike, so the cap is raised to 60.
+    Returns vehicle, config, track, dt, laps (None for tracking)."""
+    if name == "hawaii_kart_tracking":
+        return (pkg.configs.HAWAII_KART_VEHICLE, pkg.configs.hawaii_kart_tracking_config(10),
+                pkg.workload.load_track("mgkt_optm"), 0.1, None)
+    assert name == "iac_lmpc"
+    veh, track = pkg.configs.IAC_VEHICLE, pkg.workload.load_track("putnam_optm")
+    return veh, dict(pkg.configs.iac_lmpc_config(60), max_iter=60), track, 0.1, pkg.workload.synthesise_track_laps(track, veh, 0.1)
+
+
 def make_oracle(pkg, name, tol=None, N=None, with_laps=True):
     from oracle import Oracle
     veh, cfg, track, mode = make_case(pkg, name, tol, N)

@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference):  python tests/golden/ma
 Sources (data, not code):
   src/mpc/racing_mpc/test_data/barc_ss/ss_lap_{1,2,3}_{x,u,k,t}.txt   recorded BARC LMPC laps
   src/vehicle_dynamics_models/racing_trajectory/test_data/barc/02_barc_center.txt, 15_barc_optm.txt
-  src/vehicle_dynamics_models/racing_trajectory/test_data/putnam/10_putnam_optm.txt
+  src/vehicle_dynamics_models/racing_trajectory/test_data/putnam/10_putnam_optm.txt, mgkt_optm.txt
 Track tables keep only what the synthetic-input generator needs: abscissa (col 6), speed (4),
 centre-line curvature (periodic cubic spline of cols 0-1), and the signed lateral offsets of the left/right boundary points
 (racing_trajectory.cpp:64-79: left = +|p - p_left|, right = -|p - p_right|), total length (col 7 row 0).
@@ -27,7 +27,7 @@ def main():
     tracks = {}
     td = f"{REF}/vehicle_dynamics_models/racing_trajectory/test_data"
     for name, path in (("barc_center", "barc/02_barc_center.txt"), ("barc_optm", "barc/15_barc_optm.txt"),
-                       ("putnam_optm", "putnam/10_putnam_optm.txt")):
+                       ("putnam_optm", "putnam/10_putnam_optm.txt"), ("mgkt_optm", "mgkt_optm.txt")):
         t = np.loadtxt(f"{td}/{path}")
         p = t[:, 0:2]
         tracks[f"{name}_s"] = t[:, 6]

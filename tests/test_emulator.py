@@ -270,3 +270,28 @@ def test_emulated_qp_kernel_euler_integrator(emu, pkg, name):
     errs = np.array(errs)
     assert len(errs) >= 7 and max(its) <= 20, (len(errs), its)
     assert errs.max() < 1e-3 and (errs < 1e-6).sum() >= (len(errs) if name == "barc_lmpc" else 6), errs
+
+
+@pytest.mark.parametrize("name,nb", [("hawaii_kart_tracking", 8), ("iac_lmpc", 4)])
+def test_emulated_qp_kernel_other_shipped_parameter_sets(emu, pkg, name, nb):
+    """The go-kart tracking set (rear-only braking, control weights 1e-12, N = 10, margin 0) and the IAC LMPC set (N = 60,
+    K = 96, its own hull-slack weights) against the dense oracle; see conftest.make_extra_case."""
+    from conftest import make_extra_case
+    from oracle import Oracle
+    veh, cfg, track, dt, laps = make_extra_case(pkg, name)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    for l in laps or []:
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, nb, 0xB200 + 7, track, laps, dt=dt, mode="track")
+    worst, n = 0.0, 0
+    for b in range(nb):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        k = _emu_solve(emu, pkg, od, veh, cfg, inp)
+        assert k["status"] == 0
+        worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"]))
+        assert abs(k["cost"] - d["cost"]) < 1e-7 * max(1, abs(d["cost"]))
+        n += 1
+    assert n >= nb - 1 and worst < 1e-6, (n, worst)

@@ -204,6 +204,34 @@ def test_euler_integrator_matches_dense_oracle(pkg, laps, name):
     print(f"[{name}, euler] {len(errs)} instances: median {np.median(errs):.2e}, worst {errs.max():.2e}, below 1e-6: {(errs < TOL).sum()}, iterations max {out['iters'].max()}")
 
 
+@pytest.mark.parametrize("name,nb", [("hawaii_kart_tracking", 24), ("iac_lmpc", 12)])
+def test_other_shipped_parameter_sets_match_dense_oracle(pkg, name, nb):
+    """racing_mpc/hawaii_kart_tracking_mpc.param.yaml and racing_mpc/iac_car_lmpc.param.yaml through the C ABI against the
+    dense oracle (conftest.make_extra_case)."""
+    from conftest import make_extra_case
+    from oracle import Oracle
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    veh, cfg, track, dt, laps = make_extra_case(pkg, name)
+    m = BatchedRacingMPC(veh, cfg, max_batch=nb)
+    od = Oracle(veh, dict(cfg, tol=1e-11))
+    for l in laps or []:
+        m.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+        od.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    batch = pkg.workload.make_batch(veh, cfg, nb, 0xB200 + 7, track, laps, dt=dt, mode="track")
+    out = m.solve(batch)
+    worst, n = 0.0, 0
+    for b in range(nb):
+        d = od.step(pkg.workload.instance(batch, b), impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        assert out["status"][b] == 0
+        worst = max(worst, relerr(out["X_optm"][b], d["X"]), relerr(out["U_optm"][b], d["U"]), relerr(out["dU_optm"][b], d["dU"]))
+        assert abs(out["cost"][b] - d["cost"]) < 1e-7 * max(1, abs(d["cost"]))
+        n += 1
+    assert n >= nb - 2 and worst < TOL, (n, worst)
+    print(f"[{name}] worst relative error vs dense oracle over {n} instances: {worst:.2e} (iterations mean {out['iters'].mean():.1f}, max {out['iters'].max()})")
+
+
 def test_full_size_batch_properties_config2(pkg):
     """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): port parity on a sample plus
     size-independent invariants on every instance."""
