@@ -1,6 +1,6 @@
 // Compile/link check of the header-only C++ adapter (racing_mpc_b200.hpp) against liblmpc_b200.so.
 // On a box without a GPU construction must throw (no CPU fallback); with a GPU (GPU test) it solves
-// one tick read from stdin-less hard-coded data produced by the Python side (argv: a raw doubles file).
+// one tick read from a raw file produced by the Python side (argv[1]); argv[2] = "full" selects full_dynamics.
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -13,8 +13,9 @@ int main(int argc, char** argv) {
   std::ifstream f(argv[1], std::ios::binary);
   f.read((char*)&cfg->c, sizeof cfg->c);
   f.read((char*)&mdl->p, sizeof mdl->p);
+  const bool full = argc > 2 && !std::strcmp(argv[2], "full");   // full_dynamics = true: the SQP path (racing_mpc.cpp:67-84)
   try {
-    RacingMPC mpc(cfg, mdl, false, 0, 1);
+    RacingMPC mpc(cfg, mdl, full, 0, 1);
     const int N = cfg->c.N;
     int nl = 0; f.read((char*)&nl, sizeof nl);
     for (int l = 0; l < nl; l++) {

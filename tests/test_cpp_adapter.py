@@ -63,18 +63,26 @@ def test_adapter_compiles_and_refuses_without_a_gpu(pkg, adapter_exe, tmp_path):
 
 
 @pytest.mark.gpu
-def test_adapter_tick_equals_python_mirror(pkg, adapter_exe, tmp_path):
+@pytest.mark.parametrize("mode", ["qp", "full"])
+def test_adapter_tick_equals_python_mirror(pkg, adapter_exe, tmp_path, mode):
+    """mode "qp": RacingMPC(config, model, false) -> lmpc_solve_batch; "full": full_dynamics = true -> lmpc_solve_sqp_batch
+    (what the node uses for its first tick, racing_mpc_node.cpp:53-56,299-314)."""
     from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
     veh, cfg, track, batch = _write_tick(pkg, str(tmp_path / "tick.bin"))
-    r = subprocess.run([adapter_exe, str(tmp_path / "tick.bin")], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    m1 = re.search(r"OK iters=(\S+) cost=(\S+) x1=(\S+)", r.stdout)
-    assert m1 and "OK2" in r.stdout, r.stdout
+    r = subprocess.run([adapter_exe, str(tmp_path / "tick.bin")] + (["full"] if mode == "full" else []),
+                       capture_output=True, text=True, timeout=300)
     m = BatchedRacingMPC(veh, cfg, max_batch=1)
     for l in pkg.workload.load_laps():
         m.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
-    out = m.solve(batch)
-    assert out["status"][0] == 0
+    out = m.solve(batch) if mode == "qp" else m.solve_sqp(batch, max_sqp_iter=30, tol=1e-9)
+    if out["status"][0] != 0:            # not solved: the adapter must omit X_optm too (racing_mpc.cpp:358-371)
+        assert r.returncode == 1 and "FAIL: not solved" in r.stdout, (r.returncode, r.stdout)
+        assert mode == "full"            # the plain tick of this seed is known to solve
+        return
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    m1 = re.search(r"OK iters=(\S+) cost=(\S+) x1=(\S+)", r.stdout)
+    assert m1 and "OK2" in r.stdout, r.stdout
     assert abs(float(m1.group(2)) - out["cost"][0]) <= 1e-10 * max(1.0, abs(out["cost"][0]))
     assert abs(float(m1.group(3)) - out["X_optm"][0][cfg["N"] - 1][3]) <= 1e-10
-    assert int(float(m1.group(1))) == int(out["iters"][0])
+    if mode == "qp":
+        assert int(float(m1.group(1))) == int(out["iters"][0])
