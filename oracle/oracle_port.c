@@ -205,7 +205,22 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
   const double sfloor = getenv("ORC_SFLOOR") ? atof(getenv("ORC_SFLOOR")) : 1e-2;
   const double mu0 = getenv("ORC_MU0") ? atof(getenv("ORC_MU0")) : 0.1;
   const double th0 = getenv("ORC_TH0") ? atof(getenv("ORC_TH0")) : 0.01;
-  w->th = th0; w->yth = mu0 / w->th;
+  w->th = th0;
+  if (soft) {
+    /* a start whose rollout leaves the track: the boundary slack sigma_b absorbs the violation from the beginning
+     * (boundary rows strictly feasible at the start) instead of being dragged there by an infeasible-start crawl */
+    const double thoff = getenv("ORC_THOFF") ? atof(getenv("ORC_THOFF")) : 0.1;
+    double viol = -1e300;
+    for (int i = 0; i < N; i++)
+      for (int sl = 20; sl < MAXROW; sl++) {
+        const int j = RID(w, i, sl);
+        if (!w->act[j]) continue;
+        const double gv = ((sl & 1) ? -1.0 : 1.0) * w->x[6 * i + 1] - w->rh[j];
+        if (gv > viol) viol = gv;
+      }
+    if (thoff >= 0.0 && viol + thoff > w->th) w->th = viol + thoff;
+  }
+  w->yth = mu0 / w->th;
   for (int j = 0; j < K; j++) { w->lam[j] = 1.0 / K; w->ylam[j] = mu0 * K; }
   double R0 = 1.0; /* size of the initial dual residual (pi0 = 0): bounds the tracked reduction */
   {

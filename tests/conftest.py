@@ -68,8 +68,8 @@ def make_extra_case(pkg, name):
     "hawaii_kart_tracking": racing_mpc/hawaii_kart_tracking_mpc.param.yaml on mgkt_optm.txt (the reference's own
       test_racing_mpc.cpp drives this track), N = 10, dt = 0.1;
     "iac_lmpc": racing_mpc/iac_car_lmpc.param.yaml, N = 60 at dt = 0.1 (sim_putnam_short_lmpc.launch.py:81) on the Putnam
-      table with three synthesised laps; the 6 s horizon from a constant-steering reference needs up to ~40 interior-point
-      iterations in the dense oracle and the kernel alike, so the cap is raised to 60.
+      table with three synthesised laps; the 6 s horizon from a constant-steering reference leaves the track, the dense
+      oracle needs 17-44 iterations, the kernel 12-38 (boundary-slack start), so the cap is raised to 60.
     Returns vehicle, config, track, dt, laps (None for tracking)."""
     if name == "hawaii_kart_tracking":
         return (pkg.configs.HAWAII_KART_VEHICLE, pkg.configs.hawaii_kart_tracking_config(10),

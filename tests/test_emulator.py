@@ -300,7 +300,9 @@ def test_emulated_qp_kernel_other_shipped_parameter_sets(emu, pkg, name, nb):
 @pytest.mark.parametrize("name", ["hawaii_kart_tracking", "iac_lmpc"])
 def test_extra_parameter_sets_reproduce_golden_vectors(emu, pkg, name):
     """Committed golden vectors of the two extra parameter sets (tests/golden/make_golden.py): the dense oracle reproduces
-    them, the port and the emulated kernel land on them within the bar."""
+    them, the port and the emulated kernel land on them within the bar.  iac_lmpc instance 3 (reference end point far
+    outside the hull, rollout 69 m off the track, cost 3.5e3) is the case the boundary-slack start was made for: 87
+    structured iterations before it, 37 with it (the dense oracle needs 44)."""
     from conftest import make_extra_case
     from oracle import Oracle
     z = np.load(os.path.join(ROOT, "tests", "golden", f"golden_{name}.npz"))
@@ -317,12 +319,6 @@ def test_extra_parameter_sets_reproduce_golden_vectors(emu, pkg, name):
         p = op.step(inp, impl="port")
         k = _emu_solve(emu, pkg, od, veh, cfg, inp)
         for r, X, U, dU in ((p, p["X"], p["U"], p["dU"]), (k, k["X"], k["U"], k["dU"])):
-            if r["status"] == 1:
-                # iac_lmpc instance 3 (reference end point far outside the hull, cost 3.5e3): the dense oracle needs 44
-                # iterations, the structured interior point 87 -- beyond the cap of 60 it reports MAX_ITER (and solves
-                # to 4e-12 with a cap of 100).  Reported, not silent.
-                assert name == "iac_lmpc" and d["iters"] > 40
-                continue
             assert r["status"] == 0
             assert max(relerr(X, z["out_X"][b]), relerr(U, z["out_U"][b]), relerr(dU, z["out_dU"][b])) < 1e-6
             assert abs(r["cost"] - z["out_cost"][b]) < 1e-7 * max(1, abs(z["out_cost"][b]))
