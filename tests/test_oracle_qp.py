@@ -91,3 +91,14 @@ def test_infeasible_initial_state_and_missing_safe_set(pkg):
     o2, *_ = make_oracle(pkg, "barc_lmpc", with_laps=False)
     assert o2.step(inp, impl="dense")["status"] == 3
     assert o2.step(inp, impl="port")["status"] == 3
+
+
+def test_boundary_slack_start_keeps_long_horizons_short(pkg):
+    """Start-point rule shared by port and kernel: a rollout that leaves the track starts with sigma_b covering the
+    violation.  IAC tracking N = 40 (BASELINE configs[2]), 256 instances of the full-size test's seed: every instance
+    solves, no instance needs more than 10 iterations (16 before the rule), mean below 6."""
+    o, veh, cfg, track, mode = make_oracle(pkg, "iac_tracking")
+    batch = pkg.workload.make_batch(veh, cfg, 256, 0xB200 + 3, track, pkg.workload.load_laps(), mode=mode)
+    r = o.step_batch(batch, impl="port", nthreads=4)
+    assert (r["status"] == 0).all()
+    assert r["iters"].max() <= 10 and r["iters"].mean() < 6.0, (r["iters"].max(), r["iters"].mean())
