@@ -322,3 +322,16 @@ def test_extra_parameter_sets_reproduce_golden_vectors(emu, pkg, name):
             assert r["status"] == 0
             assert max(relerr(X, z["out_X"][b]), relerr(U, z["out_U"][b]), relerr(dU, z["out_dU"][b])) < 1e-6
             assert abs(r["cost"] - z["out_cost"][b]) < 1e-7 * max(1, abs(z["out_cost"][b]))
+
+
+def test_emulated_kernel_and_port_share_the_start_rules(emu, pkg):
+    """The kernel and the port carry the same start-point rules (guarded rollout, boundary-slack start): on IAC tracking
+    N = 40, where the rollouts leave the track, their iteration counts stay within two of each other and below 11."""
+    od, veh, cfg, track, mode = make_oracle(pkg, "iac_tracking")
+    batch = pkg.workload.make_batch(veh, cfg, 12, 0xB200 + 3, track, pkg.workload.load_laps(), mode=mode)
+    for b in range(12):
+        inp = pkg.workload.instance(batch, b)
+        p = od.step(inp, impl="port")
+        k = _emu_solve(emu, pkg, od, veh, cfg, inp)
+        assert p["status"] == 0 and k["status"] == 0
+        assert abs(k["iters"] - p["iters"]) <= 2 and k["iters"] <= 11, (b, k["iters"], p["iters"])
