@@ -128,7 +128,7 @@ def cpu_arm(pkg, steps, warmup, sample_instances, seed=0xC0DE):
         orc.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
     cores = os.cpu_count() or 1
     for _ in range(warmup):
-        orc.step_batch({k: v[:max(cores, 64)] for k, v in data.items()}, impl="port", nthreads=cores)
+        orc.step_batch(data, impl="port", nthreads=cores)
     t0 = time.perf_counter()
     nfail = 0
     for _ in range(steps):
@@ -136,7 +136,128 @@ def cpu_arm(pkg, steps, warmup, sample_instances, seed=0xC0DE):
         nfail += int(r["nfail"])
     dt = time.perf_counter() - t0
     return dict(value=steps * sample_instances / dt, seconds=dt, cores=cores, failed=nfail,
-                sample=f"{steps} x {sample_instances} instances of the same workload (oracle port, {cores} threads)")
+                sample=f"{steps} steps x {sample_instances} instances of the same workload (oracle port, {cores} threads; {warmup} untimed warm-up steps)")
+
+
+def probe_reference_stack():
+    """SURVEY.md 8c / BASELINE.md 2: never assume the real reference stack is absent -- look for it at run time."""
+    found = {"casadi": False, "osqp": False, "baseline_ref": os.path.isdir(os.path.join(ROOT, "baseline", "_ref")),
+             "oracle_ref": os.path.isdir(os.path.join(ROOT, "oracle", "_ref"))}
+    for mod in ("casadi", "osqp"):
+        try:
+            __import__(mod)
+            found[mod] = True
+        except Exception:
+            pass
+    found["usable"] = bool(found["casadi"])
+    found["note"] = ("CasADi importable: oracle/casadi_reference.py can state the reference's Opti('conic')+OSQP problem literally"
+                     if found["casadi"] else
+                     "CasADi / OSQP not importable and no baseline/_ref: the reference's solver stack is absent on this box; the CPU arm is the oracle port (kind 'port')")
+    return found
+
+
+def timed_steps(stream, flush, steps, body):
+    """`steps` repetitions of body(k), each bracketed by CUDA events on `stream`, the L2 flushed (untimed) before each."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for k in range(steps):
+            flush.fill_(float(k))            # untimed L2 flush
+            ev[k][0].record(stream)
+            body(k)
+            ev[k][1].record(stream)
+    stream.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def extra_config_line(pkg, name, dev, local_rank, stream, flush, dist, world, rank, peak, steps=5, warmup=3):
+    """One line of the `configs` object: BASELINE configs[2..4] at the per-GPU share they name, device-resident inputs,
+    CUDA events, L2 flushed between steps, max over ranks.  Returns a dict (rank 0) or None."""
+    import torch
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    from racing_lmpc_ros2_b200.distributed import ShardedSolver
+    from racing_lmpc_ros2_b200.binding import make_reg_spec
+    laps = pkg.workload.load_laps()
+    exchange = False
+    if name == "config3_iac_tracking_N40":
+        veh, cfg = pkg.configs.IAC_VEHICLE, pkg.configs.iac_tracking_config(40)
+        track = pkg.workload.load_track("putnam_optm")
+        Bn, named_gpus, mode, use_laps, spec = 4096, 1, "track", [], None
+        desc = "BASELINE configs[2]: IAC Putnam full-course tracking MPC, N=40, 4096 instances per GPU"
+    elif name == "config4_50lap_regression":
+        veh = pkg.configs.BARC_VEHICLE
+        cfg = dict(pkg.configs.barc_lmpc_config(20), num_ss_pts_per_lap=2, max_lap_stored=50)
+        track = pkg.workload.load_track("barc_center")
+        use_laps = pkg.workload.synthesise_laps(laps, 50)
+        spec = make_reg_spec([3, 4, 5], [[3, 4, 5]] * 3, [[0], [1], [1]], 0.6)
+        Bn, named_gpus, mode = 2048, 4, "barc"
+        desc = ("BASELINE configs[3]: BARC LMPC, 50-lap safe set (~66 k points; 2 nearest per lap over 48 laps = 96 columns), "
+                "error-dynamics regression on every stage (lmpc_set_error_dynamics), 8192 instances on 4 GPUs = 2048 per GPU")
+    else:
+        veh, cfg = pkg.configs.BARC_VEHICLE, pkg.configs.barc_lmpc_config(20)
+        track = pkg.workload.load_track("barc_center")
+        use_laps, spec = laps, None
+        Bn, named_gpus, mode, exchange = 8192, 8, "barc", True
+        desc = "BASELINE configs[4]: Monte-Carlo LMPC, 65536 perturbed agents, N=20, sharded over 8 GPUs = 8192 per GPU, trajectories of all ranks exchanged every step"
+    mpc = BatchedRacingMPC(veh, cfg, max_batch=Bn, device=local_rank)
+    for l in use_laps:
+        mpc.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    if spec is not None:
+        mpc.set_error_dynamics(spec)
+    data = pkg.workload.make_batch(veh, cfg, Bn, 0xB200 + 40 + 7919 * rank, track, laps, mode=mode)
+    d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
+    mpc.set_stream(stream)
+    sh = ShardedSolver(mpc, dist if world > 1 else None, Bn, dev, backend="peer") if exchange else None
+    out = mpc.alloc_device_outputs(Bn, dev) if not exchange else None
+
+    def body(k):
+        if exchange:
+            sh.step(d_in, k); sh.wait(k)
+        else:
+            mpc.solve(d_in, out)
+
+    with torch.cuda.stream(stream):
+        for k in range(warmup):
+            body(k)
+    stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    mpc.set_timing(True)
+    ms = timed_steps(stream, flush, steps, body)
+    (ms_lin, ms_ss, ms_qp), nrec = mpc.kernel_ms()
+    mpc.set_timing(False)
+    t = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    o = sh.local(steps - 1) if exchange else out
+    status = o["status"].cpu().numpy(); iters = o["iters"].cpu().numpy()
+    if exchange:
+        assert mpc.gather_error() == 0
+    mpc.close()
+    N, K = cfg["N"], (cfg["num_ss_pts"] if cfg["learning"] else 0)
+    qp_ms = ms_qp / max(nrec, 1)
+    total_ms = float(t.item())
+    summ = load_summary(name)
+    flops = summ.get("fp64_flops_per_launch") if summ.get("batch") == Bn else None
+    line = {"workload": desc, "n_gpus": world, "per_gpu_batch": Bn, "global_batch": Bn * world,
+            "is_the_named_configuration": world == named_gpus, "named_n_gpus": named_gpus,
+            "value": Bn * world * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+            "solved_fraction": float(((status == 0) | (status == 5)).mean()), "solved_exact_fraction": float((status == 0).mean()),
+            "status_histogram": np.bincount(status, minlength=7).tolist(),
+            "ipm_iters_mean": float(iters.mean()), "ipm_iters_max": int(iters.max()),
+            "kernel_ms": {"lmpc_qp_kernel": qp_ms, "linearise_and_regression": ms_lin / max(nrec, 1), "ss_query_wait": ms_ss / max(nrec, 1)},
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_step": b_alg(N, K, bool(K)), "achieved": b_alg(N, K, bool(K)) * Bn / (qp_ms * 1e-3) / 1e9 if qp_ms > 0 else None,
+                         "peak": peak, "unit": "GB/s", "frac": (b_alg(N, K, bool(K)) * Bn / (qp_ms * 1e-3) / 1e9 / peak) if qp_ms > 0 else None,
+                         "fp64_flops_per_launch": flops}}
+    return line if rank == 0 else None
+
+
+def load_summary(name=None):
+    path = os.path.join(ROOT, "profiles", "qp_kernel_summary.json" if not name else f"qp_kernel_summary_{name}.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
 
 
 def main():
@@ -146,6 +267,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="instances per GPU (default: BASELINE config 2)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "nccl-overlap"],
+                    help="how the ranks exchange trajectories: fused into the QP kernel over NVLink peer memory (default), or ncclAllGather after / beside the solve (A/B)")
+    ap.add_argument("--same-seed", action="store_true", help="A/B aid: every rank solves rank 0's batch (isolates the max-over-ranks effect)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -154,24 +279,30 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import racing_lmpc_ros2_b200 as pkg
 
+    exchange_desc = {"peer": "trajectories of all ranks exchanged every step by the QP kernel's epilogue (stores into every peer's gather buffer over NVLink peer memory, sequence flag, one-warp wait kernel); solve + exchange + wait inside every timed window",
+                     "nccl": "one ncclAllGather of the result slab per step, stream-ordered after the solve, inside the timed window",
+                     "nccl-overlap": "one ncclAllGather per step issued asynchronously beside the next solve and waited inside that step's window (round 1's scheme)"}[args.gather]
     config_desc = {"workload": f"BASELINE configs[1]: BARC LMPC, N={N_HORIZON}, 6-state Frenet bicycle, K=96 safe-set columns "
                                f"(3 recorded laps), {args.batch} random initial states per GPU",
                    "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "N": N_HORIZON, "K": 96,
-                   "parallelism": f"instances sharded over {max(world, 1)} GPU(s), safe set replicated, one all-gather of trajectories per step (overlapped with the next step's solve, waited inside its timed window)",
+                   "parallelism": f"instances sharded over {max(world, 1)} GPU(s), safe set replicated; {exchange_desc}",
+                   "gather": args.gather, "same_seed_on_all_ranks": bool(args.same_seed),
                    "l2": "256 MiB scratch written between timed steps (untimed) to flush the 126 MB L2", "tol": 1e-7, "polish": "active-set (augmented-Lagrangian) polish after the interior point"}
+    ref_stack = probe_reference_stack()
 
     # ------------------------------------------------------------------ CPU ("reference") arm
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = 4096
-        res = cpu_arm(pkg, steps=max(1, min(args.steps, 20)), warmup=1, sample_instances=sample)
+        sample = args.batch * max(args.gpus, 1)     # one step = the arm's global batch
+        res = cpu_arm(pkg, steps=max(1, min(args.steps, 20)), warmup=max(1, min(args.warmup, 3)), sample_instances=sample)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.batch * max(world, 1) / res["value"],
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / res["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_desc,
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
-                                 "note": "CPU restatement -- reference stack (CasADi/OSQP) unavailable in this environment"},
+                                 "failed_instances": res["failed"],
+                                 "note": "CPU restatement (oracle/oracle_port.c, same algorithm as the kernel) -- the reference's CasADi/OSQP stack was probed for at run time and is absent", "reference_stack_probe": ref_stack},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -180,6 +311,7 @@ def main():
     import torch
     import torch.distributed as dist
     from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    from racing_lmpc_ros2_b200.distributed import ShardedSolver, unpack_flat_slab
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the solve path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -189,7 +321,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    veh, cfg, track, laps, data = workload(pkg, 0xB200 + 2 + 7919 * rank, args.batch)
+    seed = 0xB200 + 2 + (0 if args.same_seed else 7919 * rank)
+    veh, cfg, track, laps, data = workload(pkg, seed, args.batch)
     mpc = BatchedRacingMPC(veh, cfg, max_batch=args.batch, device=local_rank)
     # safe set: rank 0 owns the laps, every rank receives them (replicated), then ingests locally
     for l in laps:
@@ -201,56 +334,28 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     mpc.set_stream(stream)
     d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
-    # two output sets: while the trajectories of step k are gathered (NCCL, its own stream), step k + 1 solves into the other
-    d_outs = [mpc.alloc_device_outputs(args.batch, dev) for _ in range(2 if world > 1 else 1)]
-    d_out = d_outs[0]
     N, K = cfg["N"], cfg["num_ss_pts"]
-    # X, U, dU, cost, status of the rank live in one allocation (d_out["slab"]): the gather needs no packing kernel
-    gathered = [torch.empty(world * d_out["slab"].numel(), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    sharded = ShardedSolver(mpc, dist if world > 1 else None, args.batch, dev, backend=args.gather)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-    pending = [None]
 
     def step(k):
-        """Solve, then the one collective of the path (all-gather of the converged trajectories).  The gather of step k
-        overlaps the solve of step k + 1 and is waited for INSIDE that step's timed window (the last one in a window of
-        its own, drain()), so every gather is inside the timed region."""
-        o = d_outs[k % len(d_outs)]
-        mpc.solve(d_in, o)
-        if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()
-            pending[0] = dist.all_gather_into_tensor(gathered[k % 2], o["slab"], async_op=True)
-
-    def drain():
-        if pending[0] is not None:
-            pending[0].wait()
-            pending[0] = None
+        """Solve + the one exchange of the path + the wait for every peer's results: all inside the timed window."""
+        sharded.step(d_in, k)
+        sharded.wait(k)
 
     with torch.cuda.stream(stream):
         for k in range(args.warmup):
             step(k)
-        drain()
     stream.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     mpc.set_timing(True)
     launches0 = mpc.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    ev_tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    with torch.cuda.stream(stream):
-        for k in range(args.steps):
-            flush.fill_(float(k))            # untimed L2 flush
-            ev[k][0].record(stream)
-            step(k)
-            ev[k][1].record(stream)
-        ev_tail[0].record(stream)            # the gather of the last step, timed on its own
-        drain()
-        ev_tail[1].record(stream)
-    stream.synchronize()
+    ms_steps = timed_steps(stream, flush, args.steps, step)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -258,51 +363,82 @@ def main():
     (ms_lin, ms_ss, ms_qp), nrec = mpc.kernel_ms()
     mpc.set_timing(False)
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + ev_tail[0].elapsed_time(ev_tail[1])
+    dev_ms = sum(ms_steps)
+    own_ms = dev_ms
+    qp_ms = ms_qp / max(nrec, 1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([qp_ms, own_ms / args.steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allr = [torch.zeros_like(per_rank) for _ in range(world)]
+        dist.all_gather(allr, per_rank)
+        per_rank_qp = [float(a[0]) for a in allr]; per_rank_step = [float(a[1]) for a in allr]
+    else:
+        per_rank_qp = [qp_ms]; per_rank_step = [own_ms / args.steps]
     dev_ms = float(t.item())
-    last = (args.steps - 1) % len(d_outs)
-    d_out = d_outs[last]
-    status = d_out["status"].cpu().numpy()
-    iters = d_out["iters"].cpu().numpy()
-    if world > 1:   # untimed check of the collective: this rank's block of the gathered buffer is its own solution
-        from racing_lmpc_ros2_b200.distributed import unpack_flat_slab
-        g = unpack_flat_slab(gathered[(args.steps - 1) % 2].cpu().numpy(), world, args.batch, N)
-        lo = rank * args.batch
-        assert np.array_equal(g["X_optm"][lo:lo + args.batch], d_out["X_optm"].cpu().numpy())
-        assert np.array_equal(g["status"][lo:lo + args.batch], status)
-    solved = int((status == 0).sum())
+    last = args.steps - 1
+    lo_ = sharded.local(last)
+    status = lo_["status"].cpu().numpy()
+    iters = lo_["iters"].cpu().numpy()
+    X_own = lo_["X_optm"].cpu().numpy()
+    if args.gather == "peer":
+        assert mpc.gather_error() == 0, "a gather wait timed out"
+    # untimed check of the exchange: every rank's block of this rank's gathered set equals that rank's own solution
+    g = unpack_flat_slab(sharded.gathered(last).cpu().numpy(), max(world, 1), args.batch, N, per=sharded.per)
+    lo = rank * args.batch
+    assert np.array_equal(g["X_optm"][lo:lo + args.batch], X_own)
+    assert np.array_equal(g["status"][lo:lo + args.batch], status)
+    if world > 1:
+        chk = torch.from_numpy(np.array([float(X_own.sum()), float(status.sum())])).to(dev)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        for r in range(world):
+            blk = g["X_optm"][r * args.batch:(r + 1) * args.batch]
+            assert float(blk.sum()) == float(allc[r][0]), f"rank {rank}: block of rank {r} differs from what rank {r} solved"
+            assert float(g["status"][r * args.batch:(r + 1) * args.batch].sum()) == float(allc[r][1])
+    solved = int(((status == 0) | (status == 5)).sum())
     total_instances = args.batch * max(world, 1)
     value = total_instances * args.steps / (dev_ms * 1e-3)
 
-    # ---- e2e: host (pinned) buffers through the C-ABI host path, wall clock around the synchronous call
+    # ---- e2e: host (pinned) buffers through the C-ABI host path, wall clock around the synchronous call.  N > 1: the call
+    # is lmpc_solve_gather_batch -- H2D, kernels with the fused exchange, wait for every peer, D2H of the gathered
+    # trajectories of ALL ranks plus this rank's multipliers / safe-set columns.
     mpc.set_stream(None)
     h_in = mpc.alloc_host_inputs(data, pinned=True)     # one pinned arena in struct order: a single H2D copy per step
     h_out = mpc.alloc_host_outputs(args.batch, pinned=True)
-    for _ in range(3):
-        mpc.solve(h_in, h_out)
+    g_host = torch.empty(world * sharded.per, dtype=torch.float64).pin_memory().numpy() if (world > 1 and args.gather == "peer") else None
+
+    def e2e_call(k):
+        if g_host is not None:
+            mpc.solve_gather(h_in, h_out, k % 2, wait=True, gathered_host=g_host)
+        else:
+            mpc.solve(h_in, h_out)
+            if world > 1:     # NCCL A/B modes: gather from a device copy of the host outputs is not the product path; keep the solve only
+                pass
+
+    for k in range(3):
+        e2e_call(k)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        mpc.solve(h_in, h_out)      # H2D of every input, 3 kernels, D2H of every output (safe-set columns behind the QP kernel), stream sync
+    for k in range(args.steps):
+        e2e_call(k + 3)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     h2d = int(sum(v.nbytes for v in h_in.values()))
-    d2h = int(sum(v.nbytes for v in h_out.values()))
+    if g_host is not None:
+        d2h = int(g_host.nbytes + sum(h_out[k].nbytes for k in ("convex_combi_optm", "ss_x", "ss_j", "iters")))
+        ge = unpack_flat_slab(g_host, world, args.batch, N, per=sharded.per)
+        assert np.array_equal(ge["status"][lo:lo + args.batch], status) and np.array_equal(ge["X_optm"][lo:lo + args.batch], X_own)
+        assert mpc.gather_error() == 0
+    else:
+        d2h = int(sum(v.nbytes for v in h_out.values()))
+        assert np.array_equal(h_out["status"], status)
     e2e_value = total_instances * args.steps / e2e_s
-    assert np.array_equal(h_out["status"], status)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     # ---- roofline of the dominant kernel (lmpc_qp_kernel), live CUDA-event duration
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -310,33 +446,46 @@ def main():
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-    qp_ms = ms_qp / max(nrec, 1)
+    fp64 = None
+    if rank == 0:
+        summary = load_summary()
+        # fp64-pipe view: counted fp64 flops of the profiled launch (same seed and batch as this run,
+        # profiles/qp_kernel_summary.json) over the live kernel time, against a DFMA rate measured on this device now
+        try:
+            dfma_peak = mpc.measure_fp64_peak()
+            flops = summary.get("fp64_flops_per_launch") if summary.get("batch") == args.batch else None
+            fp64 = {"peak_tflops": dfma_peak, "peak_source": "lmpc_measure_fp64_peak (DFMA chains, this device, this run)",
+                    "flops_per_launch": flops,
+                    "achieved_tflops": (flops / (qp_ms * 1e-3) / 1e12) if flops and qp_ms > 0 else None}
+            fp64["frac"] = (fp64["achieved_tflops"] / dfma_peak) if fp64["achieved_tflops"] and dfma_peak > 0 else None
+        except Exception as ex:   # measurement aid only
+            fp64 = {"error": str(ex)}
+    mpc.close()
+
+    # ---- BASELINE configs[2..4] at their per-GPU share (every rank takes part: the lines are max-over-ranks too)
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        for name in ("config3_iac_tracking_N40", "config4_50lap_regression", "config5_montecarlo_65536"):
+            try:
+                configs[name] = extra_config_line(pkg, name, dev, local_rank, stream, flush, dist, world, rank, peak)
+            except Exception as ex:    # a failing side line must not take the headline with it
+                configs[name] = {"error": repr(ex)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     alg_bytes = b_alg(N, K) * args.batch
     achieved = alg_bytes / (qp_ms * 1e-3) / 1e9 if qp_ms > 0 else 0.0
-    traffic = None
-    summary = {}
-    summ = os.path.join(ROOT, "profiles", "qp_kernel_summary.json")
-    if os.path.exists(summ):
-        try:
-            summary = json.load(open(summ))
-            traffic = summary.get("dram_bytes_per_launch")
-        except Exception:
-            summary = {}
-    # fp64-pipe view: counted fp64 flops of the profiled launch (same seed and batch as this run,
-    # profiles/qp_kernel_summary.json) over the live kernel time, against a DFMA rate measured on this device now
-    fp64 = None
-    try:
-        dfma_peak = mpc.measure_fp64_peak()
-        flops = summary.get("fp64_flops_per_launch") if summary.get("batch") == args.batch else None
-        fp64 = {"peak_tflops": dfma_peak, "peak_source": "lmpc_measure_fp64_peak (DFMA chains, this device, this run)",
-                "flops_per_launch": flops,
-                "achieved_tflops": (flops / (qp_ms * 1e-3) / 1e12) if flops and qp_ms > 0 else None}
-        fp64["frac"] = (fp64["achieved_tflops"] / dfma_peak) if fp64["achieved_tflops"] and dfma_peak > 0 else None
-    except Exception as ex:   # measurement aid only
-        fp64 = {"error": str(ex)}
     roofline = {"kernel": "lmpc_qp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": summary.get("dram_bytes_per_launch"),
+                "traffic_source": "ncu --set full capture of the same launch (profiles/qp_kernel_summary.json), not re-measured in this run",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_step": b_alg(N, K), "kernel_ms": qp_ms,
+                "kernel_ms_per_rank": per_rank_qp, "kernel_ms_min_max": [min(per_rank_qp), max(per_rank_qp)],
+                "step_ms_per_rank": per_rank_step,
                 "kernel_share_of_step": (ms_qp / max(ms_lin + ms_ss + ms_qp, 1e-12)),
                 "other_kernels_ms": {"lmpc_linearise_kernel": ms_lin / max(nrec, 1), "lmpc_ss_query_kernel": ms_ss / max(nrec, 1)},
                 "fp64": fp64,
@@ -347,14 +496,16 @@ def main():
     if world == 1:
         res = cpu_arm(pkg, steps=3, warmup=1, sample_instances=4096)
         cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"],
-               "note": "CPU restatement -- reference stack (CasADi/OSQP) unavailable in this environment"}
+               "note": "CPU restatement -- reference stack (CasADi/OSQP) probed at run time and absent", "reference_stack_probe": ref_stack}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(world, 1), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_desc,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "includes_exchange": bool(g_host is not None) or world == 1},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "solved_fraction": solved / args.batch, "ipm_iters_mean": float(iters.mean()), "ipm_iters_max": int(iters.max())}
+            "solved_fraction": solved / args.batch, "ipm_iters_mean": float(iters.mean()), "ipm_iters_max": int(iters.max()),
+            "configs": configs}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -45,6 +45,7 @@
 #ifndef LMPC_B200_H_
 #define LMPC_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -53,7 +54,9 @@ extern "C" {
 
 #define LMPC_NX 6
 #define LMPC_NU 2
-#define LMPC_MAX_N 64         /* horizon cap of the kernels (N is a runtime parameter below it) */
+#define LMPC_MAX_N 128        /* horizon cap of the kernels (N is a runtime parameter below it; the shipped files go to n: 80,
+                               * iac_car_tracking_mpc.param.yaml:7).  lmpc_create also rejects a horizon whose working set
+                               * exceeds the 227 KB of shared memory a CTA may use. */
 #define LMPC_MAX_SS_PTS 128   /* num_ss_pts cap */
 
 /* Per-call / per-handle error codes. */
@@ -75,7 +78,14 @@ enum lmpc_instance_status {
   LMPC_MAX_ITER = 1,
   LMPC_INFEASIBLE_IC = 2,     /* x_ic violates the hard box on x_0 (racing_mpc.cpp:147,199-201) */
   LMPC_NO_SAFE_SET = 3,       /* learning mode with an empty safe set */
-  LMPC_NUMERIC = 4            /* factorisation broke down before convergence */
+  LMPC_NUMERIC = 4,           /* factorisation broke down before convergence */
+  LMPC_SOLVED_INACCURATE = 5, /* the interior point converged (tol, then 1e-2 tol) but the active-set polish could not
+                               * certify an active set: the trajectory is the interior-point iterate (typically 1e-7..1e-4
+                               * from the optimum).  OSQP's "solved inaccurate" / "polish unsuccessful".  Outputs are
+                               * written; the adapter publishes them (they are far inside the reference's own eps 1e-3). */
+  LMPC_SQP_MAX_ITER = 6       /* lmpc_solve_sqp_batch only: the last QP solved but the SQP iteration hit max_sqp_iter
+                               * before its step test passed -- the trajectory violates the nonlinear dynamics (IPOPT's
+                               * "Maximum_Iterations_Exceeded" under error_on_fail, racing_mpc.cpp:71) */
 };
 
 enum lmpc_memspace { LMPC_MEM_HOST = 0, LMPC_MEM_DEVICE = 1 };
@@ -139,7 +149,8 @@ typedef struct lmpc_batch_out {
   double* dU_optm;             /* [B][N-1][2] */
   double* convex_combi_optm;   /* [B][num_ss_pts]   (learning) */
   double* ss_x;                /* [B][num_ss_pts][6] safe-set columns used by the QP (padded) */
-  double* ss_j;                /* [B][num_ss_pts]    their cost-to-go J - J[0] */
+  double* ss_j;                /* [B][num_ss_pts]    their raw cost-to-go J (what the reference's out["ss_j"] holds,
+                                * racing_mpc.cpp:257; the shift J - J[0] of :280 happens inside the QP kernel) */
   double* cost;                /* [B] objective value (the reference never returns it) */
   int32_t* status;             /* [B] lmpc_instance_status */
   int32_t* iters;              /* [B] interior-point iterations (stats["iter_count"]) */
@@ -267,6 +278,31 @@ int lmpc_prepare_batch(lmpc_handle* h, int B, const lmpc_loop_options* opt, cons
                        const double* X_last, const double* U_last, double* x_ic, double* u_ic, double* X_ref, double* U_ref,
                        double* T_ref, double* bound_left, double* bound_right, double* curvatures, double* vel_ref,
                        double* total_length);
+
+/* ---- multi-GPU: sharded batch, every rank receives every rank's converged trajectories (the reference
+ *      is a single process and has no counterpart).  One process per GPU of one NVSwitch domain.  The exchange is fused
+ *      into the QP kernel: its epilogue stores each instance's X, U, dU, cost, status into every peer's gather buffer
+ *      through NVLink peer mappings and publishes a sequence number; receivers wait on local memory.
+ *      Set-up: every rank calls lmpc_gather_init (same world, B, sets), the ranks exchange the 64-byte IPC handles by
+ *      any means (torch.distributed.all_gather in distributed.py), every rank calls lmpc_gather_connect.
+ *      Gathered set layout: [world][slab], slab = [X [B][N][6] | U [B][N-1][2] | dU [B][N-1][2] | cost [B] |
+ *      status int32 [B]] padded to a multiple of 256 bytes (slab_bytes). ---- */
+#define LMPC_IPC_HANDLE_BYTES 64
+int lmpc_gather_init(lmpc_handle* h, int world, int rank, int B, int sets, void* ipc_handle_out /*[64]*/, size_t* slab_bytes);
+int lmpc_gather_connect(lmpc_handle* h, const void* ipc_handles_all /*[world][64]*/);
+/* device pointer of gathered set `set` ([world][slab]) and the slab length in doubles */
+int lmpc_gather_buffer(lmpc_handle* h, int set, double** device_ptr, size_t* doubles_per_rank);
+/* lmpc_solve_batch whose trajectory outputs (X_optm, U_optm, dU_optm, cost, status) are produced in this rank's block
+ * of gathered set `set` and mirrored to every peer.  wait != 0: also enqueue the wait for this exchange (afterwards the
+ * whole set is valid on this rank, stream-ordered); wait == 0: call lmpc_gather_wait(seq) later (e.g. after enqueuing the
+ * next solve into another set).  Two sets make back-to-back solves safe (a set is overwritten two exchanges later).
+ * DEVICE memspace: out->X_optm/U_optm/dU_optm/cost/status are ignored (may be NULL).  HOST memspace: they receive this
+ * rank's results unless gathered_host is given (with wait != 0), which receives the whole set [world][slab] instead. */
+int lmpc_solve_gather_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int set, int wait,
+                            double* gathered_host, uint64_t* seq_out, int memspace);
+int lmpc_gather_wait(lmpc_handle* h, uint64_t seq);
+/* synchronises; *peer_timed_out = 0, or 1 + the rank a wait gave up on (after about two seconds) */
+int lmpc_gather_error(lmpc_handle* h, int32_t* peer_timed_out);
 
 /* Per-kernel device timing (measurement aid): when enabled, CUDA events are recorded on the handle's
  * stream around the three kernels of every lmpc_solve_batch; lmpc_get_kernel_ms synchronises and

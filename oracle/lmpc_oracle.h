@@ -129,7 +129,7 @@ typedef struct orc_step_out {
   int polished;     /* dense path: 1 if active-set polish accepted */
 } orc_step_out;
 
-enum { ORC_OK = 0, ORC_MAX_ITER = 1, ORC_INFEASIBLE_IC = 2, ORC_NO_SAFE_SET = 3, ORC_NUMERIC = 4 };
+enum { ORC_OK = 0, ORC_MAX_ITER = 1, ORC_INFEASIBLE_IC = 2, ORC_NO_SAFE_SET = 3, ORC_NUMERIC = 4, ORC_INACCURATE = 5, ORC_SQP_MAX_ITER = 6 };
 
 /* Dense statement of the reference QP, dense Mehrotra IPM, active-set polish, KKT check. */
 int orc_step_dense(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss,

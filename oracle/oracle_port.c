@@ -310,7 +310,7 @@ polish_failed:
       memcpy(w->y, w->ysave, sizeof w->y); memcpy(w->ylam, w->ylsave, sizeof w->ylam); w->yth = w->ythsave;
       polishing = 0;
       if (numfail_polish) { status = ORC_NUMERIC; break; }
-      if (polish_tries >= 2 || it >= max_iter) { status = ORC_OK; break; }
+      if (polish_tries >= 2 || it >= max_iter) { status = ORC_INACCURATE; break; }
       step_tol2 *= 1e-2; tol2 *= 1e-2;
       continue;
     }

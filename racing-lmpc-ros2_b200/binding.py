@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liblmpc_b200.so")
 
 LMPC_MEM_HOST, LMPC_MEM_DEVICE = 0, 1
-STATUS_NAMES = {0: "SOLVED", 1: "MAX_ITER", 2: "INFEASIBLE_IC", 3: "NO_SAFE_SET", 4: "NUMERIC"}
+STATUS_NAMES = {0: "SOLVED", 1: "MAX_ITER", 2: "INFEASIBLE_IC", 3: "NO_SAFE_SET", 4: "NUMERIC", 5: "SOLVED_INACCURATE", 6: "SQP_MAX_ITER"}
 
 
 class VehicleParams(C.Structure):
@@ -101,7 +101,9 @@ EXPORTS = [
     "lmpc_track_set", "lmpc_track_load", "lmpc_track_total_length", "lmpc_track_eval_batch",
     "lmpc_frenet_to_global_batch", "lmpc_global_to_frenet_batch", "lmpc_closed_loop_run", "lmpc_prepare_batch",
     "lmpc_recorder_config", "lmpc_recorder_step", "lmpc_recorder_lap_count", "lmpc_safe_set_regress_batch", "lmpc_set_error_dynamics",
+    "lmpc_gather_init", "lmpc_gather_connect", "lmpc_gather_buffer", "lmpc_solve_gather_batch", "lmpc_gather_wait", "lmpc_gather_error",
 ]
+LMPC_IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -154,6 +156,12 @@ def load_library(path=None):
     L.lmpc_recorder_lap_count.argtypes = [vp]
     L.lmpc_safe_set_regress_batch.argtypes = [vp, C.c_int, C.POINTER(RegSpec), vp, vp, vp, vp, vp, vp, C.c_int]
     L.lmpc_set_error_dynamics.argtypes = [vp, C.POINTER(RegSpec)]
+    L.lmpc_gather_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_size_t)]
+    L.lmpc_gather_connect.argtypes = [vp, vp]
+    L.lmpc_gather_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lmpc_solve_gather_batch.argtypes = [vp, C.c_int, C.POINTER(BatchIn), C.POINTER(BatchOut), C.c_int, C.c_int, vp, C.POINTER(C.c_uint64), C.c_int]
+    L.lmpc_gather_wait.argtypes = [vp, C.c_uint64]
+    L.lmpc_gather_error.argtypes = [vp, C.POINTER(C.c_int32)]
     if path is None:
         _lib = L
     return L

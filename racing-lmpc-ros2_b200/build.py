@@ -12,9 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(CSRC, "liblmpc_b200.so")
 SOURCES = ["lmpc_capi.cu", "lmpc_qp_tu0.cu", "lmpc_qp_tu1.cu", "lmpc_qp_tu2.cu", "lmpc_qp_tu3.cu"]
-DEPS = SOURCES + ["lmpc_kernels.cuh", "lmpc_qp_kernel.cuh", "lmpc_qp_launch.h", "lmpc_qp_core.cuh", "lmpc_ss_core.cuh",
-                  "lmpc_model.cuh", "lmpc_track.cuh", "lmpc_loop.cuh", "lmpc_warp.cuh", "lmpc_host_params.h",
-                  os.path.join("..", "..", "include", "lmpc_b200.h")]
+# every header of csrc/ is a dependency of every translation unit (globbed: a hand-kept list went stale once)
+DEPS = SOURCES + sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "lmpc_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

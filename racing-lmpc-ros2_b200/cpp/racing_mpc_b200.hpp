@@ -138,7 +138,7 @@ class RacingMPC {
     stats["iter_count"] = iters;
     stats["status"] = status;
     stats["cost"] = cost;
-    if (status == LMPC_SOLVED) {                                                   // racing_mpc.cpp:345-352
+    if (status == LMPC_SOLVED || status == LMPC_SOLVED_INACCURATE) {                                                   // racing_mpc.cpp:345-352
       solved_ = true;
       out["X_optm"] = X; out["U_optm"] = U; out["dU_optm"] = dU;
       if (config_->c.learning) out["convex_combi_optm"] = lam;

@@ -76,6 +76,17 @@ struct lmpc_handle {
   // device staging for host-memory callers
   DevBuf st_in, st_out;
   size_t qp_smem = 0;
+  // multi-GPU result exchange over peer memory (lmpc_gather_*): one allocation
+  //   [sets][world][slab] | flags: u64 [world] | done counter | error word
+  struct Gather {
+    int world = 0, rank = 0, B = 0, sets = 0;
+    size_t slab_bytes = 0, set_bytes = 0, flags_off = 0, total_bytes = 0;
+    void* base = nullptr;
+    void* peer[LMPC_MAX_PEERS] = {nullptr};   // IPC mappings of the peers' allocations (null for self)
+    bool connected = false;
+    unsigned long long seq = 0;
+    int active_set = -1;                      // >= 0 while lmpc_solve_gather_batch routes the trajectory outputs
+  } gat;
   // optional per-kernel timing: events recorded on the stream around the three kernels of each solve
   bool timing = false;
   std::vector<cudaEvent_t> tev;   // 4 events per recorded solve (ring)
@@ -182,6 +193,8 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
+  for (int p = 0; p < LMPC_MAX_PEERS; p++) if (h->gat.peer[p]) cudaIpcCloseMemHandle(h->gat.peer[p]);
+  if (h->gat.base) cudaFree(h->gat.base);
   for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->reg_slab, &h->ws_reg, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
     if (b->p) cudaFree(b->p);
   delete h;
@@ -368,7 +381,9 @@ extern "C" int lmpc_safe_set_load(lmpc_handle* h, const char* prefix, double L) 
     h->err = "cannot load lap " + p;
     return LMPC_ERR_IO;
   }
-  return lmpc_safe_set_add_lap(h, nx, x.data(), u.data(), k.data(), t.data(), L);
+  const int rc = lmpc_safe_set_add_lap(h, nx, x.data(), u.data(), k.data(), t.data(), L);
+  if (rc == LMPC_OK) h->rec.lap_count++;   // SafeSetRecorder::load, safe_set.cpp:269: recorded laps are numbered after the loaded ones
+  return rc;
 }
 
 extern "C" int lmpc_safe_set_clear(lmpc_handle* h) {
@@ -576,8 +591,13 @@ extern "C" int lmpc_safe_set_query_batch(lmpc_handle* h, int B, const double* qu
   int rc = launch_ss_query(h, tab, B, dq, 2, max_total, max_total, dx, dj);
   if (rc != LMPC_OK) return rc;
   if (memspace == LMPC_MEM_HOST) {
-    CK(cudaMemcpyAsync(ss_x, dx, sizeof(double) * nx, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(ss_j, dj, sizeof(double) * nj, cudaMemcpyDeviceToHost, h->stream));
+    // only the `count` columns the query found travel back: the caller's columns beyond them stay untouched (header contract)
+    if (tab.count > 0) {
+      CK(cudaMemcpy2DAsync(ss_x, sizeof(double) * 6 * (size_t)max_total, dx, sizeof(double) * 6 * (size_t)max_total,
+                           sizeof(double) * 6 * (size_t)tab.count, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpy2DAsync(ss_j, sizeof(double) * (size_t)max_total, dj, sizeof(double) * (size_t)max_total,
+                           sizeof(double) * (size_t)tab.count, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     if (count) for (int b = 0; b < B; b++) count[b] = tab.count;
   } else if (count) {
@@ -806,6 +826,18 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   a.bl = io.din[5]; a.br = io.din[6]; a.vref = io.din[8]; a.ABg = abg; a.ssx = io.ssx; a.ssj = io.ssj; a.cen = cen;
   a.X = io.dout[0]; a.U = io.dout[1]; a.dU = io.dout[2]; a.lam = io.dout[3]; a.cost = io.dout[6];
   a.status = io.d_status; a.iters = io.d_iters; a.ss_count = *ss_count_io; a.B = B; a.skip = skip;
+  a.n_mirror = 0; a.done = nullptr; a.seq = 0;
+  if (h->gat.active_set >= 0) {   // lmpc_solve_gather_batch: X, U, dU, cost, status live in this rank's block of the gather buffer
+    const lmpc_handle::Gather& G = h->gat;
+    for (int p = 0; p < G.world; p++) {
+      if (p == G.rank) continue;
+      a.mirror_off[a.n_mirror] = (long long)((char*)G.peer[p] - (char*)G.base);
+      a.peer_flag[a.n_mirror] = (unsigned long long*)((char*)G.peer[p] + G.flags_off) + G.rank;
+      a.n_mirror++;
+    }
+    a.done = (unsigned int*)((char*)G.base + G.flags_off + sizeof(unsigned long long) * LMPC_MAX_PEERS);
+    a.seq = G.seq;
+  }
   a.scratch = (double*)h->ws_qpscr.p;
   launch_qp(h, a);
   h->launches++;
@@ -832,6 +864,159 @@ extern "C" int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, 
   rc = run_tick_kernels(h, B, io, io.din[2], io.din[3], io.din[10] ? io.din[10] : io.din[3], true, nullptr, &ss_count);
   if (rc != LMPC_OK) return rc;
   return stage_out(h, B, out, memspace, io);
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU result exchange
+// One process per GPU; instances are sharded and independent, the only exchange is "every rank receives every rank's
+// converged trajectories" (SURVEY.md 8e).  Instead of a collective AFTER the solve, the QP kernel's epilogue stores each
+// instance's result into every peer's gather buffer through NVLink peer mappings (lmpc_qp_kernel.cuh) and the last CTA
+// publishes a sequence number in the peers' flag arrays; a one-warp wait kernel on the receiving side spins on LOCAL
+// memory.  No SM-resident communication kernel runs beside the solve, no packing kernel, no extra launch on the sender.
+// Waits (on the device, one lane per peer) until every peer has published sequence number >= seq in this rank's LOCAL
+// flag array.  A peer that never arrives would hang the stream: after `timeout_cycles` the lane gives up and records
+// 1 + peer in *err (checked by the host at the next synchronisation).
+__global__ void lmpc_gather_wait_kernel(const unsigned long long* __restrict__ flags, int world, int rank, unsigned long long seq,
+                                        long long timeout_cycles, int* err) {
+  const int p = (int)threadIdx.x;
+  if (p >= world || p == rank) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+    if (v >= seq) break;
+    if (clock64() - t0 > timeout_cycles) { atomicExch(err, 1 + p); break; }
+    __nanosleep(100);
+  }
+}
+
+
+static size_t gather_slab_bytes(const lmpc_handle* h, int B) {
+  const size_t N = (size_t)h->P.N, NS = (size_t)h->P.NS, Bz = (size_t)B;
+  return sizeof(double) * (Bz * (6 * N + 4 * NS + 1) + (Bz + 1) / 2);   // X | U | dU | cost | status (int32, padded): solver.alloc_device_outputs' slab
+}
+
+extern "C" int lmpc_gather_init(lmpc_handle* h, int world, int rank, int B, int sets, void* ipc_handle_out, size_t* slab_bytes) {
+  if (!h || world < 1 || world > LMPC_MAX_PEERS || rank < 0 || rank >= world || B < 1 || B > h->max_batch || sets < 1 || sets > 4 || !ipc_handle_out)
+    return LMPC_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == LMPC_IPC_HANDLE_BYTES, "IPC handle size");
+  CK(cudaSetDevice(h->device));
+  lmpc_handle::Gather& G = h->gat;
+  if (G.base) { h->err = "gather already initialised on this handle"; return LMPC_ERR_INVALID; }
+  G.world = world; G.rank = rank; G.B = B; G.sets = sets;
+  G.slab_bytes = (gather_slab_bytes(h, B) + 255) & ~(size_t)255;
+  G.set_bytes = G.slab_bytes * (size_t)world;
+  G.flags_off = G.set_bytes * (size_t)sets;
+  G.total_bytes = G.flags_off + sizeof(unsigned long long) * LMPC_MAX_PEERS + 256;
+  // cudaMalloc (not the stream-ordered allocator): legacy IPC handles exist for these allocations only
+  if (cudaMalloc(&G.base, G.total_bytes) != cudaSuccess) { G.base = nullptr; h->err = "cudaMalloc (gather buffer) failed"; return LMPC_ERR_ALLOC; }
+  CK(cudaMemset(G.base, 0, G.total_bytes));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t ih;
+  if (world > 1) CK(cudaIpcGetMemHandle(&ih, G.base)); else memset(&ih, 0, sizeof ih);
+  memcpy(ipc_handle_out, &ih, sizeof ih);
+  if (slab_bytes) *slab_bytes = G.slab_bytes;
+  G.connected = world == 1;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_gather_connect(lmpc_handle* h, const void* ipc_handles_all) {
+  if (!h || !h->gat.base || !ipc_handles_all) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  lmpc_handle::Gather& G = h->gat;
+  for (int p = 0; p < G.world; p++) {
+    if (p == G.rank || G.peer[p]) continue;
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, (const char*)ipc_handles_all + (size_t)p * LMPC_IPC_HANDLE_BYTES, sizeof ih);
+    CK(cudaIpcOpenMemHandle(&G.peer[p], ih, cudaIpcMemLazyEnablePeerAccess));
+  }
+  G.connected = true;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_gather_buffer(lmpc_handle* h, int set, double** device_ptr, size_t* doubles_per_rank) {
+  if (!h || !h->gat.base || set < 0 || set >= h->gat.sets || !device_ptr) return LMPC_ERR_INVALID;
+  *device_ptr = (double*)((char*)h->gat.base + h->gat.set_bytes * (size_t)set);
+  if (doubles_per_rank) *doubles_per_rank = h->gat.slab_bytes / sizeof(double);
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_gather_wait(lmpc_handle* h, uint64_t seq) {
+  if (!h || !h->gat.base) return LMPC_ERR_INVALID;
+  lmpc_handle::Gather& G = h->gat;
+  if (G.world == 1) return LMPC_OK;
+  CK(cudaSetDevice(h->device));
+  const unsigned long long* flags = (const unsigned long long*)((char*)G.base + G.flags_off);
+  int* err = (int*)((char*)G.base + G.flags_off + sizeof(unsigned long long) * LMPC_MAX_PEERS + 8);
+  lmpc_gather_wait_kernel<<<1, 32, 0, h->stream>>>(flags, G.world, G.rank, (unsigned long long)seq, 4000000000ll /* ~2 s */, err);
+  h->launches++;
+  CK(cudaGetLastError());
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_gather_error(lmpc_handle* h, int32_t* peer_timed_out) {
+  if (!h || !h->gat.base || !peer_timed_out) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  int e = 0;
+  CK(cudaMemcpy(&e, (char*)h->gat.base + h->gat.flags_off + sizeof(unsigned long long) * LMPC_MAX_PEERS + 8, sizeof e, cudaMemcpyDeviceToHost));
+  *peer_timed_out = e;
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_solve_gather_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int set,
+                                       int wait, double* gathered_host, uint64_t* seq_out, int memspace) {
+  if (!h || !in || !out || B < 1) return LMPC_ERR_INVALID;
+  lmpc_handle::Gather& G = h->gat;
+  if (!G.base || !G.connected || set < 0 || set >= G.sets || B != G.B) { if (h) h->err = "gather not initialised / connected, or batch size differs from lmpc_gather_init's"; return LMPC_ERR_INVALID; }
+  CK(cudaSetDevice(h->device));
+  // the trajectory outputs are routed into this rank's block of the chosen set
+  const size_t Bz = (size_t)B, N = (size_t)h->P.N, NS = (size_t)h->P.NS;
+  double* blk = (double*)((char*)G.base + G.set_bytes * (size_t)set + G.slab_bytes * (size_t)G.rank);
+  lmpc_batch_out o2 = *out;
+  lmpc_batch_out dev = *out;
+  dev.X_optm = blk; dev.U_optm = blk + 6 * N * Bz; dev.dU_optm = dev.U_optm + 2 * NS * Bz; dev.cost = dev.dU_optm + 2 * NS * Bz;
+  dev.status = (int32_t*)(dev.cost + Bz);
+  // placeholders so that the argument check passes; the host path's own X/U/dU/cost/status copies are skipped below
+  if (!o2.X_optm) o2.X_optm = dev.X_optm;
+  if (!o2.U_optm) o2.U_optm = dev.U_optm;
+  if (!o2.dU_optm) o2.dU_optm = dev.dU_optm;
+  if (!o2.status) o2.status = dev.status;
+  int rc = check_batch_args(h, B, in, &o2);
+  if (rc != LMPC_OK) return rc;
+  DevIO io;
+  rc = stage_in(h, B, in, &o2, memspace, io);
+  if (rc != LMPC_OK) return rc;
+  io.dout[0] = dev.X_optm; io.dout[1] = dev.U_optm; io.dout[2] = dev.dU_optm; io.dout[6] = dev.cost; io.d_status = dev.status;
+  G.seq++;
+  G.active_set = set;
+  int ss_count = 0;
+  rc = run_tick_kernels(h, B, io, io.din[2], io.din[3], io.din[10] ? io.din[10] : io.din[3], true, nullptr, &ss_count);
+  G.active_set = -1;
+  if (rc != LMPC_OK) return rc;
+  if (seq_out) *seq_out = G.seq;
+  if (wait) { rc = lmpc_gather_wait(h, G.seq); if (rc != LMPC_OK) return rc; }
+  if (memspace == LMPC_MEM_HOST) {
+    // host callers: lambda, iterations and (behind the QP kernel, side stream) the safe-set columns as in lmpc_solve_batch;
+    // the trajectories of ALL ranks as one copy of the gathered set when asked for, else this rank's block
+    const bool learn = h->P.learning != 0;
+    if (out->convex_combi_optm && io.dout[3] && learn) CK(cudaMemcpyAsync(out->convex_combi_optm, io.dout[3], sizeof(double) * io.nout[3], cudaMemcpyDeviceToHost, h->stream));
+    if (out->iters) CK(cudaMemcpyAsync(out->iters, io.d_iters, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    if (!io.ss_copied && learn) {
+      if (out->ss_x) CK(cudaMemcpyAsync(out->ss_x, io.ssx, sizeof(double) * io.nout[4], cudaMemcpyDeviceToHost, h->stream));
+      if (out->ss_j) CK(cudaMemcpyAsync(out->ss_j, io.ssj, sizeof(double) * io.nout[5], cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (gathered_host && wait) CK(cudaMemcpyAsync(gathered_host, (char*)G.base + G.set_bytes * (size_t)set, G.set_bytes, cudaMemcpyDeviceToHost, h->stream));
+    else {
+      if (out->X_optm) CK(cudaMemcpyAsync(out->X_optm, dev.X_optm, sizeof(double) * 6 * N * Bz, cudaMemcpyDeviceToHost, h->stream));
+      if (out->U_optm) CK(cudaMemcpyAsync(out->U_optm, dev.U_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+      if (out->dU_optm) CK(cudaMemcpyAsync(out->dU_optm, dev.dU_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+      if (out->cost) CK(cudaMemcpyAsync(out->cost, dev.cost, sizeof(double) * Bz, cudaMemcpyDeviceToHost, h->stream));
+      if (out->status) CK(cudaMemcpyAsync(out->status, dev.status, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (io.ss_copied) CK(cudaStreamSynchronize(h->side));
+  }
+  return LMPC_OK;
 }
 
 // ------------------------------------------------------------------------------------------ SQP to convergence

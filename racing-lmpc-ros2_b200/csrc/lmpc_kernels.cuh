@@ -142,7 +142,7 @@ __global__ void lmpc_sqp_update_kernel(int B, int N, double tol, const double* _
   if (b >= B || done[b]) return;
   const int k = its[b];
   its[b] = k + 1;
-  if (status[b] != LMPC_SOLVED) { done[b] = 2; return; }
+  if (status[b] != LMPC_SOLVED && status[b] != LMPC_SOLVED_INACCURATE) { done[b] = 2; return; }
   const int NS = N - 1, nx = 6 * N, nd = 6 * N + 2 * NS;
   const double* xn = X + (size_t)nx * b; const double* un = U + (2 * (size_t)NS) * b;
   double* xk = Xk + (size_t)nx * b; double* uk = Uk + (2 * (size_t)NS) * b; double* dpv = Dprev + (size_t)nd * b;

@@ -102,7 +102,7 @@ __global__ void lmpc_plant_kernel(LmpcModel M, LmpcTrack T, LmpcLoopParams O, in
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int NS = N - 1;
-  const bool ok = status[b] == LMPC_SOLVED;
+  const bool ok = status[b] == LMPC_SOLVED || status[b] == LMPC_SOLVED_INACCURATE;
   double* xl = S.X_last + (6 * (size_t)N) * b; double* ul = S.U_last + (2 * (size_t)NS) * b;
   const double* xs = ok ? X_optm + (6 * (size_t)N) * b : I.X_ref + (6 * (size_t)N) * b;
   const double* us = ok ? U_optm + (2 * (size_t)NS) * b : I.U_ref + (2 * (size_t)NS) * b;

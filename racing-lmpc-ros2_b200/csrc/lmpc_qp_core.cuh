@@ -27,6 +27,7 @@
 #define LMPC_NQ (1 + LMPC_MB)   // + simplex multiplier
 #define LMPC_KPL_MAX 4          // safe-set columns per lane
 #define LMPC_NRED 36            // widest multi-value reduction
+#define LMPC_MAX_PEERS 8        // GPUs of one NVSwitch domain that exchange results through peer memory
 #ifndef LMPC_PMAX
 #define LMPC_PMAX 6             // active-set refinement rounds of the polish
 #endif
@@ -1304,7 +1305,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       th = th_save; yth = yth_save;
       polishing = 0; classified = 0;
       if (numfail_polish) { status = LMPC_NUMERIC; it++; break; }
-      if (polish_tries >= 2 || it >= P.max_iter) { status = LMPC_SOLVED; it++; break; }
+      if (polish_tries >= 2 || it >= P.max_iter) { status = LMPC_SOLVED_INACCURATE; it++; break; }
       tol_step *= 1e-2; tol_mu *= 1e-2;
       continue;
     }

@@ -12,7 +12,22 @@ struct LmpcQpBatch {
   int ss_count;
   int B;
   const int* skip;   // optional [B]: non-zero = leave this instance's outputs untouched (converged SQP instances)
+  // Fused result exchange over NVLink peer memory (lmpc_solve_gather_batch).  The trajectory outputs X, U,
+  // dU, cost, status point into this rank's block of its gather buffer; every peer maps a buffer of the same layout, so
+  // adding mirror_off[m] (bytes) to an output address gives the same element in peer m's buffer.  After its local
+  // stores each CTA stores its result into the peers (fire-and-forget writes through the NVSwitch), fences at system
+  // scope and counts itself on `done`; the CTA that completes the count publishes `seq` in every peer's flag slot of this
+  // rank.  The peers' wait kernel spins on its LOCAL flags only.  n_mirror = 0: plain solve.
+  int n_mirror;
+  long long mirror_off[LMPC_MAX_PEERS - 1];
+  unsigned long long* peer_flag[LMPC_MAX_PEERS - 1];   // address (in peer m's memory) of this rank's flag slot
+  unsigned int* done;                                  // local CTA counter (reset by the last CTA)
+  unsigned long long seq;
 };
+
+LMPC_DEV void lmpc_st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 template <int NW, int KPL, int NTPL, int RSTPL>
 __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_constant__ LmpcQpParams P, const __grid_constant__ LmpcQpBatch a) {
@@ -36,4 +51,30 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
   out.cost = a.cost ? a.cost + b : nullptr;
   out.status = a.status + b; out.iters = a.iters + b;
   lmpc_qp_solve<NW, KPL, NTPL, RSTPL>(P, in, sm, out);
+  if (a.n_mirror > 0) {
+    // ---- the collective, fused: this instance's 1.6 KB of results go straight into every peer's gather buffer
+    if (NW == 1) __syncwarp(); else __syncthreads();   // the group's own global stores are visible to all its lanes
+    const int tid = (int)threadIdx.x, NT = 32 * NW;
+    for (int m = 0; m < a.n_mirror; m++) {
+      const long long off = a.mirror_off[m];
+#define LMPC_MIR(ptr) (*reinterpret_cast<double*>(reinterpret_cast<char*>(ptr) + off))
+      for (int q = tid; q < 6 * N; q += NT) LMPC_MIR(out.X + q) = out.X[q];
+      for (int q = tid; q < 2 * NS; q += NT) { LMPC_MIR(out.U + q) = out.U[q]; LMPC_MIR(out.dU + q) = out.dU[q]; }
+      if (tid == 0) {
+        if (out.cost) LMPC_MIR(out.cost) = *out.cost;
+        *reinterpret_cast<int*>(reinterpret_cast<char*>(out.status) + off) = *out.status;
+      }
+#undef LMPC_MIR
+    }
+    if (NW == 1) __syncwarp(); else __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();                                   // this group's peer stores before the count
+      const unsigned int prev = atomicAdd(a.done, 1u);
+      if (prev == (unsigned int)a.B - 1u) {                     // last CTA of the launch: everyone's stores are ordered before this
+        *a.done = 0u;                                           // ready for the next launch (stream-ordered after this one)
+        __threadfence_system();
+        for (int m = 0; m < a.n_mirror; m++) lmpc_st_release_sys_u64(a.peer_flag[m], a.seq);
+      }
+    }
+  }
 }

@@ -37,12 +37,13 @@ def unpack_slab(slab, N):
                 status=slab[:, -1].astype(np.int32))
 
 
-def unpack_flat_slab(flat, world, Bn, N):
-    """Inverse of the layout BatchedRacingMPC.alloc_device_outputs gives out["slab"], after an all-gather of it over
-    `world` ranks: flat is (world * slab_len,) float64 (numpy).  Returns the global instance-major outputs."""
+def unpack_flat_slab(flat, world, Bn, N, per=None):
+    """Inverse of the layout BatchedRacingMPC.alloc_device_outputs gives out["slab"] (and lmpc_gather_init gives one
+    rank's block, there padded to `per` doubles), after a gather over `world` ranks: flat is (world * per,) float64
+    (numpy).  Returns the global instance-major outputs."""
     NS = N - 1
     n64 = Bn * (6 * N + 4 * NS + 1)
-    per = n64 + (Bn + 1) // 2
+    per = per or (n64 + (Bn + 1) // 2)
     flat = np.ascontiguousarray(flat).reshape(world, per)
     X, U, dU, cost, status = [], [], [], [], []
     for r in range(world):
@@ -52,7 +53,7 @@ def unpack_flat_slab(flat, world, Bn, N):
         U.append(f[o:o + Bn * 2 * NS].reshape(Bn, NS, 2)); o += Bn * 2 * NS
         dU.append(f[o:o + Bn * 2 * NS].reshape(Bn, NS, 2)); o += Bn * 2 * NS
         cost.append(f[o:o + Bn]); o += Bn
-        status.append(f[o:].copy().view(np.int32)[:Bn])
+        status.append(f[o:o + (Bn + 1) // 2].copy().view(np.int32)[:Bn])
     return dict(X_optm=np.concatenate(X), U_optm=np.concatenate(U), dU_optm=np.concatenate(dU), cost=np.concatenate(cost),
                 status=np.concatenate(status))
 
@@ -110,3 +111,100 @@ def solve_sharded(solve_fn, batch, N, dist=None, device=None):
         l, h = shard_bounds(total, world, r)
         rows.append(g[r * per:r * per + (h - l)])
     return unpack_slab(np.vstack(rows), N)
+
+
+class _DevPtr:
+    """A raw device allocation as a __cuda_array_interface__ object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+class ShardedSolver:
+    """The N-GPU form of the path (one process per GPU): this rank solves its shard of the batch and every rank ends
+    up with the trajectories (X, U, dU, cost, status) of ALL ranks -- the one exchange SURVEY.md 8e names.
+
+    backend "peer" (default): the exchange is fused into the QP kernel -- its epilogue stores every instance's result
+        into all peers' gather buffers over NVLink peer mappings (lmpc_solve_gather_batch); nothing but a one-warp wait
+        kernel runs for the collective, and no communication kernel sits on the SMs beside the solve.
+    backend "nccl": solve into a local slab, then ncclAllGather of the slab (torch.distributed), stream-ordered after the
+        solve.  "nccl-overlap": the same, issued asynchronously so that it runs beside the NEXT solve (round 1's scheme,
+        kept for A/B: the resident NCCL kernel takes SM slots from a one-wave QP grid).
+    Every rank must use the same per-rank batch size.  step(k) enqueues solve k and its exchange; wait(k) makes gathered(k)
+    valid in stream order.  Two buffer sets: step(k + 1) may be enqueued before wait(k).
+    """
+
+    def __init__(self, mpc, dist, Bn, device, backend="peer", sets=2):
+        import torch
+        self.mpc, self.dist, self.Bn, self.dev, self.backend, self.sets = mpc, dist, int(Bn), device, backend, int(sets)
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.N = mpc.N
+        self._seq = {}
+        self._pending = {}
+        if backend == "peer":
+            handle, self.per = mpc.gather_init(self.world, self.rank, self.Bn, self.sets)
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle)
+                mpc.gather_connect(handles)
+                dist.barrier()    # every rank has mapped every peer before the first remote store
+            self.gbuf = []
+            for s in range(self.sets):
+                ptr, per = mpc.gather_buffer_ptr(s)
+                self.gbuf.append(torch.as_tensor(_DevPtr(ptr, per * self.world), device=device))
+            shp = mpc._shapes(self.Bn)
+            self.outs = [{k: torch.empty(shp[k], dtype=torch.float64, device=device) for k in ("convex_combi_optm", "ss_x", "ss_j")}
+                         for _ in range(self.sets)]
+            for o in self.outs:
+                o["iters"] = torch.empty(self.Bn, dtype=torch.int32, device=device)
+        elif backend in ("nccl", "nccl-overlap"):
+            self.outs = [mpc.alloc_device_outputs(self.Bn, device) for _ in range(self.sets)]
+            self.per = self.outs[0]["slab"].numel()
+            self.gbuf = [torch.empty(self.world * self.per, dtype=torch.float64, device=device) for _ in range(self.sets)]
+        else:
+            raise ValueError(backend)
+
+    def step(self, d_in, k):
+        s = k % self.sets
+        if self.backend == "peer":
+            self._seq[k] = self.mpc.solve_gather(d_in, self.outs[s], s, wait=False)
+        else:
+            self.mpc.solve(d_in, self.outs[s])
+            if self.world > 1:
+                h = self.dist.all_gather_into_tensor(self.gbuf[s], self.outs[s]["slab"], async_op=(self.backend == "nccl-overlap"))
+                if self.backend == "nccl-overlap":
+                    self._pending[k] = h
+            else:
+                self.gbuf[s].copy_(self.outs[s]["slab"])
+
+    def wait(self, k):
+        if self.backend == "peer":
+            seq = self._seq.pop(k, None)
+            if seq is not None:
+                self.mpc.gather_wait(seq)
+        else:
+            h = self._pending.pop(k, None)
+            if h is not None:
+                h.wait()
+
+    def gathered(self, k):
+        """(world, per) view of set k % sets: row r is rank r's slab (distributed.unpack_flat_slab(.., per=self.per))."""
+        return self.gbuf[k % self.sets].view(self.world, self.per)
+
+    def local(self, k):
+        """This rank's own outputs of step k as tensors (views into the gathered set for the trajectory keys)."""
+        s = k % self.sets
+        if self.backend != "peer":
+            return self.outs[s]
+        import torch
+        N, NS, Bn = self.N, self.N - 1, self.Bn
+        row = self.gathered(k)[self.rank]
+        o = dict(self.outs[s])
+        a = 0
+        o["X_optm"] = row[a:a + Bn * 6 * N].view(Bn, N, 6); a += Bn * 6 * N
+        o["U_optm"] = row[a:a + Bn * 2 * NS].view(Bn, NS, 2); a += Bn * 2 * NS
+        o["dU_optm"] = row[a:a + Bn * 2 * NS].view(Bn, NS, 2); a += Bn * 2 * NS
+        o["cost"] = row[a:a + Bn]; a += Bn
+        o["status"] = row[a:a + (Bn + 1) // 2].view(torch.int32)[:Bn]
+        return o

@@ -7,8 +7,8 @@ ticks at a time, on top of the C ABI (include/lmpc_b200.h).
 
 `batch` uses the reference's input keys (racing_mpc.cpp:215-228); each value is instance-major
 (X_ref: (B, N, 6) == B column-major 6 x N DMs).  numpy arrays take the HOST path (H2D / D2H inside the
-call); torch CUDA tensors take the DEVICE path (zero copies, work enqueued on the current torch
-stream).  Output keys: X_optm, U_optm, dU_optm, convex_combi_optm, ss_x, ss_j, cost, status, iters.
+call); torch CUDA tensors take the DEVICE path (zero copies, work enqueued on the stream passed to
+set_stream(), else on torch's current stream).  Output keys: X_optm, U_optm, dU_optm, convex_combi_optm, ss_x, ss_j, cost, status, iters.
 There is no CPU fallback: construction raises without the CUDA library and a GPU.
 """
 import ctypes as C
@@ -51,6 +51,8 @@ class BatchedRacingMPC:
             self._h = C.c_void_p()
             _check(self.lib, None, rc, "lmpc_create")
         self._solved = False
+        self._stream_explicit = False     # set_stream() was called: the device path then leaves the handle's stream alone
+        self._pending_status = None       # status tensor of the last device-path solve (read lazily by solved())
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -69,6 +71,7 @@ class BatchedRacingMPC:
         ptr = 0
         if stream is not None:
             ptr = int(getattr(stream, "cuda_stream", stream))
+        self._stream_explicit = stream is not None
         _check(self.lib, self._h, self.lib.lmpc_set_stream(self._h, C.c_void_p(ptr)), "lmpc_set_stream")
 
     def synchronize(self):
@@ -95,7 +98,13 @@ class BatchedRacingMPC:
         return int(self.lib.lmpc_launch_count(self._h))
 
     def solved(self):
-        """RacingMPC::solved(): latches true after the first successful solve."""
+        """RacingMPC::solved(): latches true after the first successful solve (status SOLVED or SOLVED_INACCURATE of
+        at least one instance).  After a device-path solve this reads that solve's status tensor (synchronises)."""
+        if not self._solved and self._pending_status is not None:
+            st = self._pending_status.cpu().numpy()
+            self._pending_status = None
+            if ((st == 0) | (st == 5)).any():
+                self._solved = True
         return self._solved
 
     # ------------------------------------------------------------------ safe set
@@ -339,7 +348,7 @@ class BatchedRacingMPC:
             setattr(bo, k, out[k].ctypes.data)
         rc = self.lib.lmpc_solve_batch(self._h, Bn, C.byref(bi), C.byref(bo), B.LMPC_MEM_HOST)
         _check(self.lib, self._h, rc, "lmpc_solve_batch")
-        if (out["status"] == 0).any():
+        if ((out["status"] == 0) | (out["status"] == 5)).any():
             self._solved = True
         return out
 
@@ -394,10 +403,75 @@ class BatchedRacingMPC:
         out["iters"] = torch.empty(Bn, dtype=torch.int32, device=dev)
         return out
 
+    # ------------------------------------------------------------------ multi-GPU result exchange (peer memory)
+    def gather_init(self, world, rank, Bn, sets=2):
+        """Allocates the gather buffer ([sets][world][slab]) and returns (ipc_handle bytes, slab length in doubles)."""
+        buf = (C.c_ubyte * B.LMPC_IPC_HANDLE_BYTES)()
+        sb = C.c_size_t()
+        rc = self.lib.lmpc_gather_init(self._h, int(world), int(rank), int(Bn), int(sets), buf, C.byref(sb))
+        _check(self.lib, self._h, rc, "lmpc_gather_init")
+        self._gather = dict(world=int(world), rank=int(rank), B=int(Bn), sets=int(sets), slab_doubles=sb.value // 8)
+        return bytes(buf), sb.value // 8
+
+    def gather_connect(self, handles):
+        """handles: the `world` IPC handles (bytes, rank order) every rank obtained from gather_init."""
+        blob = b"".join(handles)
+        assert len(blob) == B.LMPC_IPC_HANDLE_BYTES * self._gather["world"]
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _check(self.lib, self._h, self.lib.lmpc_gather_connect(self._h, arr), "lmpc_gather_connect")
+
+    def gather_buffer_ptr(self, s):
+        p = C.c_void_p(); n = C.c_size_t()
+        _check(self.lib, self._h, self.lib.lmpc_gather_buffer(self._h, int(s), C.byref(p), C.byref(n)), "lmpc_gather_buffer")
+        return p.value, n.value
+
+    def gather_wait(self, seq):
+        _check(self.lib, self._h, self.lib.lmpc_gather_wait(self._h, int(seq)), "lmpc_gather_wait")
+
+    def gather_error(self):
+        e = C.c_int32()
+        _check(self.lib, self._h, self.lib.lmpc_gather_error(self._h, C.byref(e)), "lmpc_gather_error")
+        return e.value
+
+    def solve_gather(self, batch, out, s, wait=True, gathered_host=None):
+        """lmpc_solve_gather_batch: like solve(), with X_optm / U_optm / dU_optm / cost / status produced in this rank's
+        block of gathered set `s` and mirrored into every peer's buffer by the QP kernel.  Device tensors or numpy
+        (host path; gathered_host: optional numpy array of world * slab doubles receiving the whole set).  Returns the
+        sequence number of the exchange (for gather_wait when wait=False)."""
+        first = batch["x_ic"]
+        host = isinstance(first, np.ndarray)
+        ptr = (lambda a: a.ctypes.data) if host else (lambda a: a.data_ptr())
+        if not host and not self._stream_explicit:
+            import torch
+            cur = torch.cuda.current_stream(first.device).cuda_stream
+            _check(self.lib, self._h, self.lib.lmpc_set_stream(self._h, C.c_void_p(int(cur))), "lmpc_set_stream")
+        bi = B.BatchIn()
+        for k in IN_KEYS:
+            setattr(bi, k, ptr(batch[k]))
+        warm = batch.get("U_optm_ref", None)
+        bi.U_warm = ptr(warm) if warm is not None else None
+        bo = B.BatchOut()
+        for k in ("convex_combi_optm", "ss_x", "ss_j", "iters"):
+            setattr(bo, k, ptr(out[k]))
+        if host and gathered_host is None:
+            for k in ("X_optm", "U_optm", "dU_optm", "cost", "status"):
+                setattr(bo, k, ptr(out[k]))
+        seq = C.c_uint64()
+        rc = self.lib.lmpc_solve_gather_batch(self._h, int(first.shape[0]), C.byref(bi), C.byref(bo), int(s), 1 if wait else 0,
+                                              gathered_host.ctypes.data if gathered_host is not None else None, C.byref(seq),
+                                              B.LMPC_MEM_HOST if host else B.LMPC_MEM_DEVICE)
+        _check(self.lib, self._h, rc, "lmpc_solve_gather_batch")
+        return seq.value
+
     def _solve_device(self, batch, out=None):
-        """torch CUDA tensors in, torch CUDA tensors out; asynchronous on the handle's stream."""
+        """torch CUDA tensors in, torch CUDA tensors out; asynchronous.  Work is enqueued on the stream given to
+        set_stream(); when none was given, on torch's CURRENT stream of the tensors' device (so inputs produced on a
+        non-default torch stream are ordered before the kernels)."""
         import torch
         Bn = int(batch["x_ic"].shape[0])
+        if not self._stream_explicit:
+            cur = torch.cuda.current_stream(batch["x_ic"].device).cuda_stream
+            _check(self.lib, self._h, self.lib.lmpc_set_stream(self._h, C.c_void_p(int(cur))), "lmpc_set_stream")
         for k in IN_KEYS:
             t = batch[k]
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
@@ -414,5 +488,5 @@ class BatchedRacingMPC:
             setattr(bo, k, out[k].data_ptr())
         rc = self.lib.lmpc_solve_batch(self._h, Bn, C.byref(bi), C.byref(bo), B.LMPC_MEM_DEVICE)
         _check(self.lib, self._h, rc, "lmpc_solve_batch")
-        self._solved = True
+        self._pending_status = out["status"]    # not latched here: the solve has not run yet (see solved())
         return out
