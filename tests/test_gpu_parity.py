@@ -268,9 +268,44 @@ def test_shipped_horizon_and_hard_boundary_match_dense_oracle(pkg, laps, name, N
     print(f"[{name} N={N} {over}] worst relative error vs dense oracle over {nb} instances: {worst:.2e} (iterations mean {out['iters'].mean():.1f}, max {out['iters'].max()})")
 
 
+def _compare_whole_batch_with_dense_oracle(pkg, o, cfg, batch, out, tag):
+    """EVERY instance of a full-size batch against the dense oracle (an algorithm that shares nothing with the kernel:
+    dense Mehrotra IPM on the literal QP, LU, active-set polish, KKT certificate), all host cores.  Nothing is skipped:
+      * oracle certified (status 0, KKT residual < 1e-9) and kernel SOLVED: the trajectories must agree to 1e-6;
+      * oracle NOT certified (its own polish failed on a degenerate instance): the kernel's point must be feasible for the
+        dense QP (1e-8) and reach a cost no worse than the oracle's (it is then at least as good an answer);
+      * kernel not SOLVED: counted, bounded (0.3 %), and never allowed where the oracle is certified AND the kernel claims
+        more than SOLVED_INACCURATE."""
+    B = batch["x_ic"].shape[0]
+    ref = o.step_batch(batch, impl="dense", nthreads=os.cpu_count() or 4)
+    cert = (ref["status"] == 0) & (ref["kkt"] < 1e-9)
+    st = out["status"]
+    per = np.zeros(B)
+    for b in range(B):
+        per[b] = max(relerr(out["X_optm"][b], ref["X"][b]), relerr(out["U_optm"][b], ref["U"][b]), relerr(out["dU_optm"][b], ref["dU"][b]))
+    both = cert & (st == 0)
+    assert both.mean() > 0.98, (tag, both.mean(), np.bincount(st, minlength=7), np.bincount(ref["status"], minlength=7))
+    assert per[both].max() < TOL, (tag, per[both].max(), int(np.argmax(np.where(both, per, 0))))
+    n_unc = 0
+    for b in np.nonzero(~cert & (st == 0))[0]:
+        cost, inf = o.check_candidate(pkg.workload.instance(batch, b), out["X_optm"][b], out["U_optm"][b], out["dU_optm"][b],
+                                      out["convex_combi_optm"][b] if cfg["learning"] else None)
+        assert inf < 1e-8, (tag, b, inf)
+        if ref["status"][b] == 0:
+            assert cost <= ref["cost"][b] + 1e-7 * max(1.0, abs(ref["cost"][b])), (tag, b, cost, ref["cost"][b])
+        n_unc += 1
+    bad = st != 0
+    assert bad.mean() <= 0.003, (tag, np.bincount(st, minlength=7))
+    for b in np.nonzero(bad & cert)[0]:
+        assert st[b] == 5 and per[b] < 1e-3, (tag, b, st[b], per[b])      # an honest "inaccurate", never a wrong SOLVED
+    print(f"[{tag}] {B} instances vs the dense oracle: {int(both.sum())} certified+solved, worst rel err {per[both].max():.2e}, median {np.median(per[both]):.1e}; "
+          f"{n_unc} solved where the oracle's polish was uncertified (feasible, cost <= oracle's); kernel status histogram {np.bincount(st, minlength=7).tolist()}, "
+          f"oracle status histogram {np.bincount(ref['status'], minlength=7).tolist()}")
+
+
 def test_full_size_batch_properties_config2(pkg):
-    """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): port parity on a sample plus
-    size-independent invariants on every instance."""
+    """BASELINE config 2 at full size (1024 x BARC LMPC, N=20, K=96): size-independent invariants on every instance and
+    every instance against the dense oracle."""
     m, veh, cfg, track, mode = _mpc(pkg, "barc_lmpc", 1024)
     o, *_ = make_oracle(pkg, "barc_lmpc", tol=1e-10)
     batch = pkg.workload.make_batch(veh, cfg, 1024, 0xB200 + 2, track, pkg.workload.load_laps(), mode=mode)
@@ -292,9 +327,7 @@ def test_full_size_batch_properties_config2(pkg):
         A, Bm, g, _ = m.linearise(Xr[b, :-1], batch["U_ref"][b], batch["curvatures"][b, :-1], batch["T_ref"][b])
         pred = np.einsum("irc,ic->ir", A, X[b, :-1]) + np.einsum("irc,ic->ir", Bm, U[b]) + g
         assert np.abs(pred - X[b, 1:]).max() < 1e-9 * max(1, np.abs(X[b]).max())
-    ref = o.step_batch({k: v[:128] for k, v in batch.items()}, impl="port", nthreads=os.cpu_count() or 4)
-    e = max(relerr(X[:128], ref["X"]), relerr(U[:128], ref["U"]), relerr(dU[:128], ref["dU"]))
-    assert e < TOL, e
+    _compare_whole_batch_with_dense_oracle(pkg, o, cfg, batch, out, "config 2")
     # idempotence / determinism: the same batch again gives bit-identical results
     out2 = m.solve(batch)
     assert np.array_equal(out2["X_optm"], X) and np.array_equal(out2["iters"], out["iters"])
@@ -307,10 +340,7 @@ def test_full_size_batch_config3_iac_tracking(pkg):
     batch = pkg.workload.make_batch(veh, cfg, 4096, 0xB200 + 3, track, pkg.workload.load_laps(), mode=mode)
     out = m.solve(batch)
     assert (out["status"] == 0).mean() > 0.99
-    ref = o.step_batch({k: v[:96] for k, v in batch.items()}, impl="port", nthreads=os.cpu_count() or 4)
-    sel = (out["status"][:96] == 0) & (ref["status"] == 0)
-    e = max(relerr(out["X_optm"][:96][sel], ref["X"][sel]), relerr(out["U_optm"][:96][sel], ref["U"][sel]), relerr(out["dU_optm"][:96][sel], ref["dU"][sel]))
-    assert e < TOL, e
+    _compare_whole_batch_with_dense_oracle(pkg, o, cfg, batch, out, "config 3")
 
 
 def test_failed_instances_do_not_poison_the_batch(pkg):
