@@ -152,6 +152,7 @@ struct LmpcQpOut {
   double* cost;    // 1 (may be null)
   int* status;     // 1
   int* iters;      // 1
+  int* stats;      // optional [4] (diagnostics; null in the product): interior-point iterations, polish rounds, polish attempts, unused
 };
 
 struct alignas(16) LmpcD2 { double x, y; };   // 16-byte shared-memory loads (LDS.128)
@@ -471,7 +472,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // weight rho and the gradient y + rho (g'v - h), inactive rows are dropped, basic safe-set columns are free --
   // followed by up to PMAX active-set refinements.  During the polish the row arrays are re-purposed:
   // sign(RSs) < 0 marks an active row, RSy holds the multiplier estimate, RSi keeps the saved y.
-  int polishing = 0, polish_tries = 0, classified = 0;
+  int polishing = 0, polish_tries = 0, classified = 0, n_polish_rounds = 0;
   double tol_step = P.tol, tol_mu = 0.1 * P.tol;   // complementarity level at which the polish takes over
   int numfail_polish = 0;
   double* const SAVE_XU = in.scratch + 6 * P.K;          // [N][8] saved iterate (restored if the polish fails); global memory, not registers
@@ -1226,6 +1227,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       status = LMPC_NUMERIC;
       break;
     }
+    if (polishing) n_polish_rounds++;
     if (polishing && !polish_failed) {
       // ---------- full Newton step of the augmented-Lagrangian model, multiplier update, active-set refinement
       const double ftol = 1e-10, dtol = 1e-9;
@@ -1417,7 +1419,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   if (soft) cost += P.qb * th * th;
   if (learn && P.hull_slack)
     for (int a = 0; a < nh; a++) { const int c = P.hidx[a]; const double sh = X[c * d + N - 1] - in.cen[c] - ro[1 + a](0); cost += P.chs[c] * sh * sh; }
-  LANE0_ONLY(if (out.cost) *out.cost = cost; *out.status = status; *out.iters = it;)
+  LANE0_ONLY(if (out.cost) *out.cost = cost; *out.status = status; *out.iters = it;
+             if (out.stats) { out.stats[0] = it - n_polish_rounds; out.stats[1] = n_polish_rounds; out.stats[2] = polish_tries; out.stats[3] = 0; })
 #undef LO
 #undef ROW_GBEGIN
 #undef ROW_GEND

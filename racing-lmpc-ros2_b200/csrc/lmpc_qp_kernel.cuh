@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
   out.X = a.X + (6 * (size_t)N) * b; out.U = a.U + (2 * (size_t)NS) * b; out.dU = a.dU + (2 * (size_t)NS) * b;
   out.lam = (a.lam && P.learning) ? a.lam + (size_t)K * b : nullptr;
   out.cost = a.cost ? a.cost + b : nullptr;
-  out.status = a.status + b; out.iters = a.iters + b;
+  out.status = a.status + b; out.iters = a.iters + b; out.stats = nullptr;
   lmpc_qp_solve<NW, KPL, NTPL, RSTPL>(P, in, sm, out);
   if (a.n_mirror > 0) {
     // ---- the collective, fused: this instance's 1.6 KB of results go straight into every peer's gather buffer

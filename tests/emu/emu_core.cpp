@@ -10,6 +10,8 @@
 int g_lmpc_emu_reverse = 0;
 
 extern "C" void emu_set_reverse(int r) { g_lmpc_emu_reverse = r; }
+static int g_emu_stats[4];   // diagnostics of the last emu_qp_solve: interior-point iterations, polish rounds, polish attempts
+extern "C" const int* emu_last_stats() { return g_emu_stats; }
 
 extern "C" void emu_linearise(const lmpc_vehicle_params* v, const double* x, const double* u, double kappa, double dt,
                               double* A, double* B, double* g, double* xn) {
@@ -38,7 +40,7 @@ extern "C" int emu_qp_solve(const lmpc_mpc_config* c, const lmpc_vehicle_params*
   std::vector<double> sm((size_t)P.lay.total, 0.0 / 0.0);   // NaN-filled: reads of unwritten scratch show up
   std::vector<double> scr((size_t)LMPC_QP_SCRATCH(P.N, P.K > 0 ? P.K : 1), 0.0 / 0.0);
   LmpcQpIn in = {x_ic, u_ic, U0, T, bl, br, vref, ABg, ssx, ssj_raw, cen, ss_count, scr.data()};
-  LmpcQpOut out = {X, U, dU, lam, cost, status, iters};
+  LmpcQpOut out = {X, U, dU, lam, cost, status, iters, g_emu_stats};
   const int kpl = (P.K + 32 * nw - 1) / (32 * nw);
   const bool fixed = (nw & 0x100) == 0 && P.RS == 16 && (P.N == 20 || P.N == 40);   // same rule as the C ABI
   if (nw == 1) {
