@@ -269,6 +269,10 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="instances per GPU (default: BASELINE config 2)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "nccl-overlap"],
                     help="how the ranks exchange trajectories: fused into the QP kernel over NVLink peer memory (default), or ncclAllGather after / beside the solve (A/B)")
+    ap.add_argument("--inputs", default="pool", choices=["pool", "fixed"],
+                    help="pool: a different random batch every timed step, one contiguous timed region (default); fixed: one batch, L2 flushed (untimed) between steps")
+    ap.add_argument("--sync", default="slack", choices=["slack", "barrier"],
+                    help="slack: a rank waits for its peers' results of the PREVIOUS step after enqueuing its next one (two buffer sets); barrier: every step ends with the wait for its own exchange")
     ap.add_argument("--same-seed", action="store_true", help="A/B aid: every rank solves rank 0's batch (isolates the max-over-ranks effect)")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[2..4] lines")
     args = ap.parse_args()
@@ -287,7 +291,10 @@ def main():
                    "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "N": N_HORIZON, "K": 96,
                    "parallelism": f"instances sharded over {max(world, 1)} GPU(s), safe set replicated; {exchange_desc}",
                    "gather": args.gather, "same_seed_on_all_ranks": bool(args.same_seed),
-                   "l2": "256 MiB scratch written between timed steps (untimed) to flush the 126 MB L2", "tol": 1e-7, "polish": "active-set (augmented-Lagrangian) polish after the interior point"}
+                   "inputs": args.inputs, "sync": args.sync,
+                   "l2": ("a different random batch every timed step (pool of min(64, steps + warmup) batches per GPU, batch j = seed + 104729 j; "
+                          "the warm-up uses the other end of the pool), the L2 flushed once before the ONE contiguous timed region: no step finds its inputs in the L2"
+                          if args.inputs == "pool" else "256 MiB scratch written between timed steps (untimed) to flush the 126 MB L2"), "tol": 1e-7, "polish": "active-set (augmented-Lagrangian) polish after the interior point"}
     ref_stack = probe_reference_stack()
 
     # ------------------------------------------------------------------ CPU ("reference") arm
@@ -333,29 +340,62 @@ def main():
 
     stream = torch.cuda.Stream(device=dev)
     mpc.set_stream(stream)
-    d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
     N, K = cfg["N"], cfg["num_ss_pts"]
-    sharded = ShardedSolver(mpc, dist if world > 1 else None, args.batch, dev, backend=args.gather)
+    # Inputs: "pool" (default) = a different random batch every step (seed + 104729 * j), so no step finds its inputs in
+    # the L2 and no single slow instance is solved over and over; "fixed" = round 1's scheme (one batch, the L2 flushed
+    # between steps).  Batch 0 of the pool is the round-1 batch (the one profiles/qp_kernel_summary.json was captured on).
+    n_pool = 1 if args.inputs == "fixed" else min(64, args.steps + args.warmup)
+    pool = [data] + [pkg.workload.make_batch(veh, cfg, args.batch, seed + 104729 * j, track, laps, mode="barc") for j in range(1, n_pool)]
+    d_pool = [{k: torch.from_numpy(v).to(dev) for k, v in b.items()} for b in pool]
+    slack = args.sync == "slack" and args.inputs == "pool"
+    # buffer sets: 2 when every step ends with its own wait; 4 with one step of slack (a consumer of set k enqueued after
+    # wait(k) is then stream-ordered before the solve whose completion lets a peer overwrite that set)
+    sharded = ShardedSolver(mpc, dist if world > 1 else None, args.batch, dev, backend=args.gather, sets=4 if slack else 2)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
-    def step(k):
-        """Solve + the one exchange of the path + the wait for every peer's results: all inside the timed window."""
-        sharded.step(d_in, k)
-        sharded.wait(k)
+    def batch_of(k):          # timed step k -> pool index; the warm-up steps use the END of the pool
+        return d_pool[k % n_pool]
 
     with torch.cuda.stream(stream):
-        for k in range(args.warmup):
-            step(k)
+        for j in range(args.warmup):
+            k = n_pool - 1 - j if n_pool > 1 else j
+            sharded.step(d_pool[k % n_pool], j); sharded.wait(j)
     stream.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     mpc.set_timing(True)
     launches0 = mpc.launch_count
+    K0 = 4 * ((args.warmup + 3) // 4)       # step numbering continues after the warm-up (buffer set = step % sets)
+    with torch.cuda.stream(stream):
+        flush.fill_(1.0)                     # untimed: nothing the timed steps read is left in the L2
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    ms_steps = timed_steps(stream, flush, args.steps, step)
+    if n_pool > 1:
+        # ONE contiguous timed region: K steps on K different batches, every exchange and every wait inside it
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for k in range(args.steps):
+                sharded.step(batch_of(k), K0 + k)
+                if not slack:
+                    sharded.wait(K0 + k)
+                else:
+                    if k > 0:
+                        sharded.wait(K0 + k - 1)
+                    if k == args.steps - 1:
+                        sharded.wait(K0 + k)
+            ev1.record(stream)
+        stream.synchronize()
+        dev_ms = ev0.elapsed_time(ev1)
+    else:
+        # fixed inputs (round 1's scheme): the L2 is flushed (untimed) between steps, each step timed on its own and ended
+        # by the wait for its own exchange
+        def fixed_step(k):
+            sharded.step(d_pool[0], K0 + k)
+            sharded.wait(K0 + k)
+        dev_ms = sum(timed_steps(stream, flush, args.steps, fixed_step))
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -363,7 +403,6 @@ def main():
     (ms_lin, ms_ss, ms_qp), nrec = mpc.kernel_ms()
     mpc.set_timing(False)
     clocks = sampler.stop()
-    dev_ms = sum(ms_steps)
     own_ms = dev_ms
     qp_ms = ms_qp / max(nrec, 1)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -376,11 +415,23 @@ def main():
     else:
         per_rank_qp = [qp_ms]; per_rank_step = [own_ms / args.steps]
     dev_ms = float(t.item())
-    last = args.steps - 1
+    last = K0 + args.steps - 1
+    last_batch = pool[(args.steps - 1) % n_pool]
     lo_ = sharded.local(last)
     status = lo_["status"].cpu().numpy()
     iters = lo_["iters"].cpu().numpy()
     X_own = lo_["X_optm"].cpu().numpy()
+    # the profiled batch (pool batch 0 = round 1's batch) on its own, untimed for the headline: its kernel time is what the
+    # fp64 roofline divides the ncu-counted flops of that same launch by; its outputs are what the e2e leg must reproduce
+    mpc.set_timing(True)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            ref0 = mpc.solve(d_pool[0])
+    stream.synchronize()
+    (_, _, ms_qp0), nrec0 = mpc.kernel_ms()
+    mpc.set_timing(False)
+    qp_ms_batch0 = ms_qp0 / max(nrec0, 1)
+    status0 = ref0["status"].cpu().numpy(); X0 = ref0["X_optm"].cpu().numpy()
     if args.gather == "peer":
         assert mpc.gather_error() == 0, "a gather wait timed out"
     # untimed check of the exchange: every rank's block of this rank's gathered set equals that rank's own solution
@@ -406,38 +457,46 @@ def main():
     mpc.set_stream(None)
     h_in = mpc.alloc_host_inputs(data, pinned=True)     # one pinned arena in struct order: a single H2D copy per step
     h_out = mpc.alloc_host_outputs(args.batch, pinned=True)
-    g_host = torch.empty(world * sharded.per, dtype=torch.float64).pin_memory().numpy() if (world > 1 and args.gather == "peer") else None
+    fused = world > 1 and args.gather == "peer"
+    g_host = torch.empty(world * sharded.per, dtype=torch.float64).pin_memory().numpy() if fused else None
 
-    def e2e_call(k):
-        if g_host is not None:
-            mpc.solve_gather(h_in, h_out, k % 2, wait=True, gathered_host=g_host)
+    def e2e_call(k, all_to_host=False):
+        """N > 1: H2D of this rank's inputs, kernels with the fused exchange, wait for every peer (the gathered set is then
+        valid in this rank's HBM), D2H of this rank's own outputs.  all_to_host: D2H of the trajectories of ALL ranks instead."""
+        if fused:
+            mpc.solve_gather(h_in, h_out, k % 2, wait=True, gathered_host=g_host if all_to_host else None)
         else:
-            mpc.solve(h_in, h_out)
-            if world > 1:     # NCCL A/B modes: gather from a device copy of the host outputs is not the product path; keep the solve only
-                pass
+            mpc.solve(h_in, h_out)    # N = 1, or the NCCL A/B modes (their collective is device-path only)
 
-    for k in range(3):
-        e2e_call(k)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_call(k + 3)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    def e2e_leg(all_to_host):
+        for k in range(3):
+            e2e_call(k, all_to_host)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            e2e_call(k + 3, all_to_host)
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    e2e_s = e2e_leg(False)
     h2d = int(sum(v.nbytes for v in h_in.values()))
-    if g_host is not None:
-        d2h = int(g_host.nbytes + sum(h_out[k].nbytes for k in ("convex_combi_optm", "ss_x", "ss_j", "iters")))
-        ge = unpack_flat_slab(g_host, world, args.batch, N, per=sharded.per)
-        assert np.array_equal(ge["status"][lo:lo + args.batch], status) and np.array_equal(ge["X_optm"][lo:lo + args.batch], X_own)
+    d2h = int(sum(v.nbytes for v in h_out.values()))
+    assert np.array_equal(h_out["status"], status0) and np.array_equal(h_out["X_optm"], X0)
+    e2e_all = None
+    if fused:
         assert mpc.gather_error() == 0
-    else:
-        d2h = int(sum(v.nbytes for v in h_out.values()))
-        assert np.array_equal(h_out["status"], status)
+        s_all = e2e_leg(True)
+        ge = unpack_flat_slab(g_host, world, args.batch, N, per=sharded.per)
+        assert np.array_equal(ge["status"][lo:lo + args.batch], status0) and np.array_equal(ge["X_optm"][lo:lo + args.batch], X0)
+        assert mpc.gather_error() == 0
+        e2e_all = {"value": total_instances * args.steps / s_all, "unit": UNIT,
+                   "d2h_bytes_per_step": int(g_host.nbytes + sum(h_out[k].nbytes for k in ("convex_combi_optm", "ss_x", "ss_j", "iters"))),
+                   "note": "variant: every rank copies the trajectories of ALL ranks to its host (world x slab) instead of its own shard"}
     e2e_value = total_instances * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel (lmpc_qp_kernel), live CUDA-event duration
@@ -456,7 +515,8 @@ def main():
             flops = summary.get("fp64_flops_per_launch") if summary.get("batch") == args.batch else None
             fp64 = {"peak_tflops": dfma_peak, "peak_source": "lmpc_measure_fp64_peak (DFMA chains, this device, this run)",
                     "flops_per_launch": flops,
-                    "achieved_tflops": (flops / (qp_ms * 1e-3) / 1e12) if flops and qp_ms > 0 else None}
+                    "kernel_ms_of_the_profiled_batch": qp_ms_batch0,
+                    "achieved_tflops": (flops / (qp_ms_batch0 * 1e-3) / 1e12) if flops and qp_ms_batch0 > 0 else None}
             fp64["frac"] = (fp64["achieved_tflops"] / dfma_peak) if fp64["achieved_tflops"] and dfma_peak > 0 else None
         except Exception as ex:   # measurement aid only
             fp64 = {"error": str(ex)}
@@ -502,7 +562,9 @@ def main():
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_desc,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes_exchange": bool(g_host is not None) or world == 1},
+                    "includes_exchange": bool(fused) or world == 1,
+                    "what": "per rank and step: H2D of the rank's inputs (pinned), the three kernels with the fused exchange, wait for every peer's results, D2H of the rank's own outputs; wall clock, max over ranks",
+                    "all_ranks_to_every_host": e2e_all},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "solved_fraction": solved / args.batch, "ipm_iters_mean": float(iters.mean()), "ipm_iters_max": int(iters.max()),
             "configs": configs}

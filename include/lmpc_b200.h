@@ -224,6 +224,18 @@ int lmpc_discrete_dynamics_batch(lmpc_handle* h, int n, const double* x, const d
 int lmpc_linearise_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa,
                          const double* dt, double* A, double* Bm, double* g, double* x_next, int memspace);
 
+/* BaseVehicleModel::to_base_control / from_base_control (single_track_planar_model.cpp:390-417, simplify_lon_control):
+ * derived control (u_lon, delta) [n][2] <-> base control (Fd, Fb, delta) [n][3].  to_base: Fd = u_lon / (1 + e^-u_lon),
+ * Fb = u_lon / (1 + e^u_lon) (as written: no x1000, unlike the dynamics' tanh split, :214-217); from_base: the
+ * larger-magnitude one of (Fd, Fb).  to_base_state / from_base_state are the identity for this model (:411-414). */
+int lmpc_to_base_control_batch(lmpc_handle* h, int n, const double* u, double* u_base, int memspace);
+int lmpc_from_base_control_batch(lmpc_handle* h, int n, const double* u_base, double* u, int memspace);
+/* A handle that serves the model functions only (vehicle_model_factory::load_vehicle_model("single_track_planar_model"),
+ * vehicle_model_factory.cpp:31-50: the node builds the model before any MPC configuration exists). */
+int lmpc_model_create(const lmpc_vehicle_params* vehicle, int device_ordinal, lmpc_handle** out);
+/* Columns the tick's safe-set query finds before padding = out["ss_x"].size2() of the reference (racing_mpc.cpp:249-262). */
+int lmpc_safe_set_tick_count(lmpc_handle* h, int32_t* count);
+
 /* ---- the hot path: B independent MPC ticks ---- */
 int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out,
                      int memspace);

@@ -252,7 +252,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
    * weight rho and the gradient y + rho (g'v - h), inactive rows are dropped, basic safe-set columns are free. */
   const int do_polish = getenv("ORC_POLISH") ? atoi(getenv("ORC_POLISH")) : 1;
   const double prho = getenv("ORC_PRHO") ? atof(getenv("ORC_PRHO")) : 1e7;
-  int polishing = 0, polish_tries = 0, numfail_polish = 0;
+  int polishing = 0, polish_tries = 0, numfail_polish = 0, prev_changed = 0;
   double step_tol2 = step_tol, tol2 = tol;
   for (it = 0; it < max_iter || polishing; it++) {
     /* ---------- residuals, mu ---------- */
@@ -288,7 +288,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     if (!polishing) { mu_m3 = mu_m2; mu_m2 = mu_m1; mu_m1 = mu; }
     if (polishing == 1) {   /* first polish round: classify from the interior-point iterate */
       memcpy(w->xsave, w->x, sizeof w->xsave); memcpy(w->usave, w->u, sizeof w->usave); memcpy(w->lsave, w->lam, sizeof w->lsave); w->thsave = w->th;
-      memcpy(w->ysave, w->y, sizeof w->y); memcpy(w->ylsave, w->ylam, sizeof w->ylam); w->ythsave = w->yth; polish_tries++;
+      memcpy(w->ysave, w->y, sizeof w->y); memcpy(w->ylsave, w->ylam, sizeof w->ylam); w->ythsave = w->yth; polish_tries++; prev_changed = 0;
       for (int j = 0; j < N * MAXROW; j++) w->pact[j] = w->act[j] && w->y[j] > w->s[j];
       w->pact_th = soft && w->yth > w->th;
       for (int j = 0; j < K; j++) w->pnb[j] = !(w->lam[j] >= w->ylam[j]);
@@ -681,8 +681,11 @@ polish_failed:
           else if (r > ftol) { w->pact[j] = 1; changed++; }
           if (!w->pact[j] && r > 1e-9) viol++;
         }
-      if ((changed || dymax > 1e-4) && polishing < PMAX) { polishing++; continue; }
-      out->polished = (changed == 0 && viol == 0) ? polishing : 0;
+      /* same rule as the kernel (lmpc_qp_core.cuh): a polish whose active set is coming apart is abandoned at once */
+      const int diverging = polishing >= 2 && changed > 8 && changed > 2 * prev_changed;
+      prev_changed = changed;
+      if (!diverging && (changed || dymax > 1e-4) && polishing < PMAX) { polishing++; continue; }
+      out->polished = (!diverging && changed == 0 && viol == 0) ? polishing : 0;
       if (out->polished) { status = ORC_OK; break; }
       goto polish_failed;
     }

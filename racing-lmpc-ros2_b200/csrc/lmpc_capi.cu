@@ -648,6 +648,59 @@ static int model_batch(lmpc_handle* h, int n, const double* x, const double* u, 
   return LMPC_OK;
 }
 
+// BaseVehicleModel::to_base_control / from_base_control (single_track_planar_model.cpp:390-417)
+static int control_map(lmpc_handle* h, int n, int dir, const double* in, double* out, int memspace) {
+  if (!h || n < 1 || !in || !out) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t wi = dir ? 3 : 2, wo = dir ? 2 : 3;
+  const double* din = in; double* dout = out;
+  if (memspace == LMPC_MEM_HOST) {
+    int rc = dev_reserve(h, h->st_in, sizeof(double) * wi * (size_t)n);
+    if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * wo * (size_t)n);
+    if (rc != LMPC_OK) return rc;
+    CK(cudaMemcpyAsync(h->st_in.p, in, sizeof(double) * wi * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    din = (const double*)h->st_in.p; dout = (double*)h->st_out.p;
+  }
+  lmpc_control_map_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, dir, din, dout);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (memspace == LMPC_MEM_HOST) {
+    CK(cudaMemcpyAsync(out, dout, sizeof(double) * wo * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
+extern "C" int lmpc_to_base_control_batch(lmpc_handle* h, int n, const double* u, double* u_base, int memspace) { return control_map(h, n, 0, u, u_base, memspace); }
+extern "C" int lmpc_from_base_control_batch(lmpc_handle* h, int n, const double* u_base, double* u, int memspace) { return control_map(h, n, 1, u_base, u, memspace); }
+
+// A handle for the model functions alone (the vehicle_model_factory product: no MPC configuration exists yet when the node
+// builds the model, racing_mpc_node.cpp:43-47): a minimal tracking configuration stands in.
+extern "C" int lmpc_model_create(const lmpc_vehicle_params* vehicle, int device_ordinal, lmpc_handle** out) {
+  if (!vehicle || !out) return LMPC_ERR_INVALID;
+  lmpc_mpc_config c;
+  memset(&c, 0, sizeof c);
+  c.N = 3; c.learning = 0; c.q_boundary = 1.0;
+  c.R[0] = c.R[3] = c.R_d[0] = c.R_d[3] = 1.0;
+  for (int k = 0; k < 6; k++) { c.x_max[k] = INFINITY; c.x_min[k] = -INFINITY; }
+  for (int k = 0; k < 2; k++) { c.u_max[k] = INFINITY; c.u_min[k] = -INFINITY; }
+  c.num_ss_pts = 0; c.num_ss_pts_per_lap = 1; c.max_lap_stored = 1;
+  return lmpc_create(&c, vehicle, device_ordinal, 1, out);
+}
+
+// columns the tick's safe-set query finds before padding (racing_mpc.cpp:249-262): min(num_ss_pts, sum over the newest laps
+// of min(num_ss_pts_per_lap, points of the lap)); what out["ss_x"].size2() is in the reference
+extern "C" int lmpc_safe_set_tick_count(lmpc_handle* h, int32_t* count) {
+  if (!h || !count) return LMPC_ERR_INVALID;
+  *count = 0;
+  const int K = h->cfg.num_ss_pts;
+  if (K < 1 || h->dev_laps.empty()) return LMPC_OK;
+  LmpcLapTable tab;
+  const int rc = make_lap_table(h, K, std::max(1, (int)h->cfg.num_ss_pts_per_lap), &tab);
+  if (rc != LMPC_OK) return rc;
+  *count = tab.count;
+  return LMPC_OK;
+}
+
 extern "C" int lmpc_discrete_dynamics_batch(lmpc_handle* h, int n, const double* x, const double* u, const double* kappa,
                                             const double* dt, double* x_next, int memspace) {
   return model_batch(h, n, x, u, kappa, dt, nullptr, nullptr, nullptr, x_next, memspace, false);
@@ -1007,9 +1060,14 @@ extern "C" int lmpc_solve_gather_batch(lmpc_handle* h, int B, const lmpc_batch_i
     }
     if (gathered_host && wait) CK(cudaMemcpyAsync(gathered_host, (char*)G.base + G.set_bytes * (size_t)set, G.set_bytes, cudaMemcpyDeviceToHost, h->stream));
     else {
-      if (out->X_optm) CK(cudaMemcpyAsync(out->X_optm, dev.X_optm, sizeof(double) * 6 * N * Bz, cudaMemcpyDeviceToHost, h->stream));
-      if (out->U_optm) CK(cudaMemcpyAsync(out->U_optm, dev.U_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
-      if (out->dU_optm) CK(cudaMemcpyAsync(out->dU_optm, dev.dU_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+      if (out->X_optm && out->U_optm == out->X_optm + 6 * N * Bz && out->dU_optm == out->U_optm + 2 * NS * Bz) {
+        // one arena (alloc_host_outputs): the three trajectory arrays are adjacent on both sides -> one copy
+        CK(cudaMemcpyAsync(out->X_optm, dev.X_optm, sizeof(double) * (6 * N + 4 * NS) * Bz, cudaMemcpyDeviceToHost, h->stream));
+      } else {
+        if (out->X_optm) CK(cudaMemcpyAsync(out->X_optm, dev.X_optm, sizeof(double) * 6 * N * Bz, cudaMemcpyDeviceToHost, h->stream));
+        if (out->U_optm) CK(cudaMemcpyAsync(out->U_optm, dev.U_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+        if (out->dU_optm) CK(cudaMemcpyAsync(out->dU_optm, dev.dU_optm, sizeof(double) * 2 * NS * Bz, cudaMemcpyDeviceToHost, h->stream));
+      }
       if (out->cost) CK(cudaMemcpyAsync(out->cost, dev.cost, sizeof(double) * Bz, cudaMemcpyDeviceToHost, h->stream));
       if (out->status) CK(cudaMemcpyAsync(out->status, dev.status, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
     }

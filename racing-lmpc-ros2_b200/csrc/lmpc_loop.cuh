@@ -32,11 +32,22 @@ LMPC_HD void lmpc_step_on_track(const LmpcModel& M, const LmpcTrack& T, const do
 // to_base_control followed by the actuation message's choice (racing_mpc_node.cpp:386-401): (u_lon, delta) ->
 // (u_a, u_steer); the simulator turns that back into the derived control with from_base_control
 // (racing_simulator_node.cpp:245-250, single_track_planar_model.cpp:401-407), which returns u_a itself.
+// to_base_control (single_track_planar_model.cpp:390-400, simplify_lon_control): (u_lon, delta) -> (Fd, Fb, delta) with the
+// logistic split Fd = u_lon / (1 + e^-u_lon), Fb = u_lon / (1 + e^u_lon) -- as written, WITHOUT the x1000 the dynamics use
+LMPC_HD void lmpc_to_base_control(const double* u, double* ub) {
+  ub[0] = u[0] * 1.0 / (1.0 + exp(-u[0]));
+  ub[1] = u[0] * 1.0 / (1.0 + exp(u[0]));
+  ub[2] = u[1];
+}
+// from_base_control (:401-407): the larger-magnitude one of (Fd, Fb), and the steering angle
+LMPC_HD void lmpc_from_base_control(const double* ub, double* u) {
+  u[0] = fabs(ub[0]) > fabs(ub[1]) ? ub[0] : ub[1];
+  u[1] = ub[2];
+}
 LMPC_HD void lmpc_actuation(const double* u, double* ua) {
-  const double fd = u[0] * 1.0 / (1.0 + exp(-u[0]));
-  const double fb = u[0] * 1.0 / (1.0 + exp(u[0]));
-  ua[0] = fabs(fd) > fabs(fb) ? fd : fb;
-  ua[1] = u[1];
+  double ub[3];
+  lmpc_to_base_control(u, ub);
+  lmpc_from_base_control(ub, ua);
 }
 
 // velocity reference of column i (racing_mpc_node.cpp:269-287)
@@ -131,6 +142,14 @@ __global__ void lmpc_plant_kernel(LmpcModel M, LmpcTrack T, LmpcLoopParams O, in
 }
 
 __global__ void lmpc_tick_advance_kernel(int* tick) { *tick += 1; }
+
+// the model's control maps for n items: dir 0 = to_base_control ([n][2] -> [n][3]), 1 = from_base_control ([n][3] -> [n][2])
+__global__ void lmpc_control_map_kernel(int n, int dir, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (dir == 0) { const double u[2] = {in[2 * (size_t)i], in[2 * (size_t)i + 1]}; double ub[3]; lmpc_to_base_control(u, ub); for (int c = 0; c < 3; c++) out[3 * (size_t)i + c] = ub[c]; }
+  else { const double ub[3] = {in[3 * (size_t)i], in[3 * (size_t)i + 1], in[3 * (size_t)i + 2]}; double u[2]; lmpc_from_base_control(ub, u); out[2 * (size_t)i] = u[0]; out[2 * (size_t)i + 1] = u[1]; }
+}
 
 // ---- track interpolation functions for n abscissae / poses
 __global__ void lmpc_track_eval_kernel(LmpcTrack T, int n, const double* __restrict__ s, double* __restrict__ out) {

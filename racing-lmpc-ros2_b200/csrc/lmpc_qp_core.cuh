@@ -475,6 +475,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   int polishing = 0, polish_tries = 0, classified = 0, n_polish_rounds = 0;
   double tol_step = P.tol, tol_mu = 0.1 * P.tol;   // complementarity level at which the polish takes over
   int numfail_polish = 0;
+  double prev_changed = 0.0;   // rows that changed side in the previous polish round
   double* const SAVE_XU = in.scratch + 6 * P.K;          // [N][8] saved iterate (restored if the polish fails); global memory, not registers
   double* const SAVE_L = in.scratch + 6 * P.K + 8 * N;   // [K] lambda, [K] its multiplier
   double th_save = 0.0, yth_save = 0.0;
@@ -508,7 +509,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       th_save = th; yth_save = yth;
       pact_th = (soft && yth > th) ? 1 : 0;
       if (soft && !pact_th) yth = 0.0;
-      classified = 1; polish_tries++;
+      classified = 1; polish_tries++; prev_changed = 0.0;
     }
     for (int pass = 0; pass < (polishing ? 1 : 2) && !fail; pass++) {
       const double smu = sigma * mu;
@@ -1283,8 +1284,13 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
 #ifdef LMPC_DEBUG_TRACE
       LANE0_ONLY(if (LMPC_TRACE_COND) printf("  polish round %d: changed %.0f viol %.0f th %.3e pact_th %d dymax %.3e (u %.3e)\n", polishing, changed, rc2[1](0), th, pact_th, dymax, dymax_u);)
 #endif
-      if ((changed > 0.5 || dymax > LMPC_PDY) && polishing < LMPC_PMAX) { polishing++; continue; }
-      if (changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }
+      // a polish whose active set is coming apart (more rows change side than in the round before, and more than a
+      // handful) will not settle: give up now instead of spending the remaining rounds (one such instance per ~1000 set the
+      // time of a one-wave batch: 6 wasted rounds = 3.3 iteration-equivalents)
+      const bool diverging = polishing >= 2 && changed > 8.5 && changed > 2.0 * prev_changed;
+      prev_changed = changed;
+      if (!diverging && (changed > 0.5 || dymax > LMPC_PDY) && polishing < LMPC_PMAX) { polishing++; continue; }
+      if (!diverging && changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }
       polish_failed = true;
     }
     if (polish_failed) {

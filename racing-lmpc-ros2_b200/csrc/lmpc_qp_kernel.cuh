@@ -55,17 +55,40 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
     // ---- the collective, fused: this instance's 1.6 KB of results go straight into every peer's gather buffer
     if (NW == 1) __syncwarp(); else __syncthreads();   // the group's own global stores are visible to all its lanes
     const int tid = (int)threadIdx.x, NT = 32 * NW;
-    for (int m = 0; m < a.n_mirror; m++) {
-      const long long off = a.mirror_off[m];
-#define LMPC_MIR(ptr) (*reinterpret_cast<double*>(reinterpret_cast<char*>(ptr) + off))
-      for (int q = tid; q < 6 * N; q += NT) LMPC_MIR(out.X + q) = out.X[q];
-      for (int q = tid; q < 2 * NS; q += NT) { LMPC_MIR(out.U + q) = out.U[q]; LMPC_MIR(out.dU + q) = out.dU[q]; }
-      if (tid == 0) {
-        if (out.cost) LMPC_MIR(out.cost) = *out.cost;
-        *reinterpret_cast<int*>(reinterpret_cast<char*>(out.status) + off) = *out.status;
+    // Values are read ONCE into registers (independent loads: one L2 round trip), then stored to every peer: a loop of
+    // load -> remote store per peer serialises on the load latency because the compiler may not move a load above a store
+    // it cannot prove disjoint (measured on 8 GPUs: +3.5 us per peer before this form).
+#define LMPC_MIR(ptr, off) (*reinterpret_cast<double*>(reinterpret_cast<char*>(ptr) + (off)))
+    for (int base = 0; base < 6 * N; base += 4 * NT) {
+      double v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const int q = base + tid + NT * j; v[j] = (q < 6 * N) ? out.X[q] : 0.0; }
+      for (int m = 0; m < a.n_mirror; m++) {
+        const long long off = a.mirror_off[m];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int q = base + tid + NT * j; if (q < 6 * N) LMPC_MIR(out.X + q, off) = v[j]; }
       }
-#undef LMPC_MIR
     }
+    for (int base = 0; base < 2 * NS; base += 2 * NT) {
+      double vu[2], vd[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) { const int q = base + tid + NT * j; const bool on = q < 2 * NS; vu[j] = on ? out.U[q] : 0.0; vd[j] = on ? out.dU[q] : 0.0; }
+      for (int m = 0; m < a.n_mirror; m++) {
+        const long long off = a.mirror_off[m];
+#pragma unroll
+        for (int j = 0; j < 2; j++) { const int q = base + tid + NT * j; if (q < 2 * NS) { LMPC_MIR(out.U + q, off) = vu[j]; LMPC_MIR(out.dU + q, off) = vd[j]; } }
+      }
+    }
+    if (tid == 0) {
+      const double cv = out.cost ? *out.cost : 0.0;
+      const int sv = *out.status;
+      for (int m = 0; m < a.n_mirror; m++) {
+        const long long off = a.mirror_off[m];
+        if (out.cost) LMPC_MIR(out.cost, off) = cv;
+        *reinterpret_cast<int*>(reinterpret_cast<char*>(out.status) + off) = sv;
+      }
+    }
+#undef LMPC_MIR
     if (NW == 1) __syncwarp(); else __syncthreads();
     if (tid == 0) {
       __threadfence_system();                                   // this group's peer stores before the count

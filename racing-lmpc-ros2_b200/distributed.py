@@ -130,8 +130,11 @@ class ShardedSolver:
     backend "nccl": solve into a local slab, then ncclAllGather of the slab (torch.distributed), stream-ordered after the
         solve.  "nccl-overlap": the same, issued asynchronously so that it runs beside the NEXT solve (round 1's scheme,
         kept for A/B: the resident NCCL kernel takes SM slots from a one-wave QP grid).
-    Every rank must use the same per-rank batch size.  step(k) enqueues solve k and its exchange; wait(k) makes gathered(k)
-    valid in stream order.  Two buffer sets: step(k + 1) may be enqueued before wait(k).
+    Every rank must use the same per-rank batch size.  step(k) enqueues solve k and its exchange (into buffer set
+    k % sets); wait(k) makes gathered(k) valid in stream order.  sets = 2 is safe when wait(k) is enqueued before
+    step(k + 1).  Running one step ahead -- step(k + 1) before wait(k), so that a rank does not idle while a slower peer
+    finishes -- needs sets = 4: a consumer of gathered(k) enqueued right after wait(k) is then ordered before this rank's
+    step(k + 2), whose completion is what allows a peer to start step(k + 4) and overwrite that set.
     """
 
     def __init__(self, mpc, dist, Bn, device, backend="peer", sets=2):

@@ -269,6 +269,25 @@ class BatchedRacingMPC:
         _check(self.lib, self._h, rc, "lmpc_discrete_dynamics_batch")
         return xn
 
+    def to_base_control(self, u):
+        """BaseVehicleModel::to_base_control (single_track_planar_model.cpp:390-400): (n, 2) -> (n, 3) = (Fd, Fb, delta)."""
+        u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1, 2)
+        ub = np.zeros((u.shape[0], 3))
+        _check(self.lib, self._h, self.lib.lmpc_to_base_control_batch(self._h, u.shape[0], u.ctypes.data, ub.ctypes.data, B.LMPC_MEM_HOST), "lmpc_to_base_control_batch")
+        return ub
+
+    def from_base_control(self, ub):
+        """BaseVehicleModel::from_base_control (:401-407): (n, 3) -> (n, 2)."""
+        ub = np.ascontiguousarray(ub, dtype=np.float64).reshape(-1, 3)
+        u = np.zeros((ub.shape[0], 2))
+        _check(self.lib, self._h, self.lib.lmpc_from_base_control_batch(self._h, ub.shape[0], ub.ctypes.data, u.ctypes.data, B.LMPC_MEM_HOST), "lmpc_from_base_control_batch")
+        return u
+
+    def ss_tick_count(self):
+        c = C.c_int32()
+        _check(self.lib, self._h, self.lib.lmpc_safe_set_tick_count(self._h, C.byref(c)), "lmpc_safe_set_tick_count")
+        return c.value
+
     def linearise(self, x, u, kappa, dt):
         """discrete_dynamics_jacobian: returns A (n,6,6), B (n,6,2), g (n,6), x_next (n,6)."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 6)

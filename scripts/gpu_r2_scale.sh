@@ -10,9 +10,10 @@ run() { # name, extra args
 }
 if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -s > gpurun_out/${TAG}_multigpu_test.txt 2>&1; tail -3 gpurun_out/${TAG}_multigpu_test.txt; fi
 timeout 300 python bench.py --steps 20 --warmup 5 --no-configs > gpurun_out/${TAG}_scale${N}_single.json 2> gpurun_out/${TAG}_scale${N}_single.err
-run peer
-run nccl --gather nccl --no-configs
-run nccl_overlap --gather nccl-overlap --no-configs
+run peer_pool_slack
+run peer_pool_barrier --sync barrier --no-configs
+run peer_fixed --inputs fixed --no-configs
+run nccl_pool --gather nccl --no-configs
 run peer_sameseed --same-seed --no-configs
 python - <<PY
 import json,glob

@@ -36,9 +36,44 @@ int main(int argc, char** argv) {
     mpc.solve(in, out, st);
     if (!out.count("X_optm") || !mpc.solved()) { std::printf("FAIL: not solved status=%g\n", st["status"]); return 1; }
     std::printf("OK iters=%g cost=%.12g x1=%.12g\n", st["iter_count"], st["cost"], out["X_optm"](3, N - 1));
+    std::printf("SS cols=%d found_rows=%d\n", out.at("ss_x").size2(), out.at("ss_x").size1());
     in.erase("X_optm_ref");   // second tick: warm start from the previous solution (T_ref path)
     mpc.solve(in, out, st);
     std::printf("OK2 iters=%g\n", st["iter_count"]);
+    // ---- the model surface (vehicle_model_factory + BaseVehicleModel functions) and create_warm_start
+    if (vehicle_model_factory::load_vehicle_model("double_track_planar_model", mdl->p) != nullptr) { std::printf("FAIL: factory accepted an unknown model\n"); return 1; }
+    auto m2 = vehicle_model_factory::load_vehicle_model("single_track_planar_model", mdl->p);
+    MatrixDict mi;
+    Matrix x(6, 1), u(2, 1);
+    for (int c = 0; c < 6; c++) x.data[c] = in["X_ref"](c, 0);
+    u.data[0] = in["U_ref"](0, 0); u.data[1] = in["U_ref"](1, 0);
+    mi["x"] = x; mi["u"] = u; mi["k"] = Matrix(in["curvatures"].data[0]); mi["dt"] = Matrix(in["T_ref"].data[0]);
+    const auto dd = m2->discrete_dynamics(mi);
+    const auto jj = m2->discrete_dynamics_jacobian(mi);
+    double chk = 0.0;   // g = xip1 - A x - B u (single_track_planar_model.cpp:379)
+    for (int r = 0; r < 6; r++) {
+      double a = jj.at("g")(r, 0);
+      for (int c = 0; c < 6; c++) a += jj.at("A")(r, c) * x.data[c];
+      for (int c = 0; c < 2; c++) a += jj.at("B")(r, c) * u.data[c];
+      chk = std::fmax(chk, std::fabs(a - dd.at("xip1")(r, 0)));
+    }
+    const auto ub = m2->to_base_control(mi);
+    MatrixDict bi2; bi2["x"] = x; bi2["u"] = ub.at("u_out");
+    const auto ud = m2->from_base_control(bi2);
+    std::printf("MODEL xip1_3=%.12g g_resid=%.3e fd=%.12g fb=%.12g back=%.12g same_state=%d\n", dd.at("xip1")(3, 0), chk, ub.at("u_out")(0, 0),
+                ub.at("u_out")(1, 0), ud.at("u_out")(0, 0), (int)(m2->to_base_state(mi).at("x_out")(3, 0) == x.data[3]));
+    MatrixDict wi, wo;
+    Matrix P0(2, N), Yaws(1, N), Radii(1, N);
+    for (int i = 0; i < N; i++) { P0(0, i) = 0.5 * i; P0(1, i) = 0.01 * i * i; Yaws.data[i] = 0.04 * i; Radii.data[i] = 12.0; }
+    wi["P0"] = P0; wi["Yaws"] = Yaws; wi["Radii"] = Radii; wi["current_vel"] = Matrix(1.0); wi["target_vel"] = Matrix(2.0);
+    mpc.create_warm_start(wi, wo);
+    std::printf("WARM vx_last=%.12g omega1=%.12g u0=%.12g steer=%.12g\n", wo.at("X_ref")(3, N - 1), wo.at("X_ref")(5, 1), wo.at("U_ref")(0, 0), wo.at("U_ref")(1, 0));
+    bool le = false, re = false;
+    wi["P0"] = Matrix(2, N + 1);
+    try { mpc.create_warm_start(wi, wo); } catch (const std::length_error&) { le = true; }
+    wi["P0"] = P0; wi["current_vel"] = Matrix(0.0);
+    try { mpc.create_warm_start(wi, wo); } catch (const std::range_error&) { re = true; }
+    std::printf("WARM_ERRORS %d %d\n", (int)le, (int)re);
     return 0;
   } catch (const std::runtime_error& e) {
     std::printf("CTOR_THROW %s\n", e.what());
