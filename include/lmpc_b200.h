@@ -247,7 +247,12 @@ int lmpc_solve_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_
  * iteration satisfies the KKT conditions of the nonlinear problem.  The safe-set columns are queried once, at the
  * caller's X_ref[:, N-1] (racing_mpc.cpp:249-255), exactly as the reference's solve() does before calling IPOPT.
  * sqp_iters [B] (optional): QP solves spent per instance.  defect [B] (optional): max |x_{i+1} - f_d(x_i, u_i)| of the
- * returned trajectory (the nonlinear constraint violation).  out->status is the status of the last QP of the instance. */
+ * returned trajectory (the nonlinear constraint violation).  out->status: the status of the last QP of the instance when
+ * that QP failed; LMPC_SOLVED (/ _INACCURATE) when the step test passed; LMPC_SQP_MAX_ITER when the instance was still
+ * moving after max_sqp_iter passes (IPOPT runs with max_iter 1000 and error_on_fail: racing_mpc.cpp:67-84; 100 passes
+ * cover 1023 of 1024 random BARC tracking ticks, mean 14).  The step length of the iteration follows the secant rule of
+ * lmpc_sqp_update_kernel (csrc/lmpc_kernels.cuh); an l1-merit backtracking line search was measured against it and
+ * rejected (mean 36 passes, 16 % at the cap: DESIGN.md). */
 int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out, int max_sqp_iter,
                          double sqp_tol, int32_t* sqp_iters, double* defect, int memspace);
 /* ---- track (RacingTrajectory: the degree-3 "bspline" interpolants over the abscissa and what is built from them,

@@ -812,14 +812,14 @@ int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* 
   }
   memcpy(Uk, in->U_ref, sizeof(double) * 2 * (size_t)nst);
   const double qp[2] = {Xk[6 * (N - 1)], Xk[6 * (N - 1) + 1]};
-  int st = ORC_MAX_ITER, its = 0;
+  int st = ORC_MAX_ITER, its = 0, converged = 0;
   double alpha = 1.0;
   for (int k = 0; k < max_sqp_iter; k++) {
     orc_step_in ik = *in;
     ik.X_ref = Xk; ik.U_ref = Uk; ik.ss_query_point = in->ss_query_point ? in->ss_query_point : qp;
     st = impl ? orc_step_dense(v, c, ss, &ik, out) : orc_step_port(v, c, ss, &ik, out);
     its++;
-    if (st != ORC_OK) break;
+    if (st != ORC_OK && st != ORC_INACCURATE) break;
     double step = 0.0, dd = 0.0, dp = 0.0, pp = 0.0;
     for (int q = 0; q < nd; q++) {
       const double nv = q < 6 * N ? out->X[q] : out->U[q - 6 * N], ov = q < 6 * N ? Xk[q] : Uk[q - 6 * N];
@@ -828,7 +828,7 @@ int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* 
       dd += d * d; dp += d * dprev[q]; pp += dprev[q] * dprev[q];
       dprev[q] = d;
     }
-    if (step < tol) break;
+    if (step < tol) { converged = 1; break; }
     if (k > 0) {
       /* successive displacements (anti)parallel: one mode d_k = (1 - alpha (1 + rho)) d_{k-1} dominates; the secant step
        * alpha / (1 - d_k.d_{k-1} / |d_{k-1}|^2) = 1 / (1 + rho) cancels it.  Otherwise halve on oscillation, double on progress. */
@@ -841,6 +841,9 @@ int orc_step_sqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* 
     for (int q = 0; q < 6 * N; q++) Xk[q] += alpha * dprev[q];
     for (int q = 0; q < 2 * nst; q++) Uk[q] += alpha * dprev[6 * N + q];
   }
+  /* a run whose step test never passed is not a solution of the nonlinear problem (IPOPT: Maximum_Iterations_Exceeded) */
+  if ((st == ORC_OK || st == ORC_INACCURATE) && !converged) st = ORC_SQP_MAX_ITER;
+  out->status = st;
   if (sqp_iters) *sqp_iters = its;
   if (defect) {
     double dmax = 0.0;

@@ -1112,6 +1112,9 @@ extern "C" int lmpc_solve_sqp_batch(lmpc_handle* h, int B, const lmpc_batch_in* 
     CK(cudaStreamSynchronize(h->stream));
     if (na == 0) break;
   }
+  // instances whose step test never passed within max_sqp_iter: LMPC_SQP_MAX_ITER instead of the last QP's SOLVED
+  lmpc_sqp_finalize_kernel<<<blocks, threads, 0, h->stream>>>(B, done, io.d_status);
+  h->launches++;
   if (defect) {
     lmpc_sqp_defect_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, io.dout[0], io.dout[1], io.din[4], io.din[7], dfc);
     h->launches++;

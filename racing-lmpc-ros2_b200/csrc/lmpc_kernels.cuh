@@ -171,6 +171,14 @@ __global__ void lmpc_sqp_update_kernel(int B, int N, double tol, const double* _
   atomicAdd(n_active, 1);
 }
 
+// after the last pass: an instance whose step test never passed is not a solution of the nonlinear problem (IPOPT's
+// "Maximum_Iterations_Exceeded" under error_on_fail, racing_mpc.cpp:71): LMPC_SQP_MAX_ITER
+__global__ void lmpc_sqp_finalize_kernel(int B, const int* __restrict__ done, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (done[b] == 0 && (status[b] == LMPC_SOLVED || status[b] == LMPC_SOLVED_INACCURATE)) status[b] = LMPC_SQP_MAX_ITER;
+}
+
 // defect of the nonlinear dynamics at the returned trajectory: max_i,c |x_{i+1} - f_d(x_i, u_i, kappa_i, T_i)|_c
 __global__ void lmpc_sqp_defect_kernel(LmpcModel M, int B, int N, const double* __restrict__ X, const double* __restrict__ U,
                                        const double* __restrict__ T_ref, const double* __restrict__ kappa, double* __restrict__ defect) {

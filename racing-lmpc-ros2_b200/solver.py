@@ -371,10 +371,11 @@ class BatchedRacingMPC:
             self._solved = True
         return out
 
-    def solve_sqp(self, batch, max_sqp_iter=20, tol=1e-9, out=None):
+    def solve_sqp(self, batch, max_sqp_iter=100, tol=1e-9, out=None):
         """RacingMPC(config, model, full_dynamics=True).solve (racing_mpc.cpp:67-84,162-166): the problem with the
         nonlinear dynamics constraint, solved by SQP on the tick's kernels (host buffers).  Adds `sqp_iters` (QP solves
-        per instance) and `defect` (max nonlinear-dynamics violation of the returned trajectory) to the outputs."""
+        per instance) and `defect` (max nonlinear-dynamics violation of the returned trajectory) to the outputs.  status 0
+        means the SQP's step test passed; an instance still moving after max_sqp_iter passes gets status 6 (SQP_MAX_ITER)."""
         Bn = int(np.asarray(batch["x_ic"]).shape[0])
         keep = {k: np.ascontiguousarray(batch[k], dtype=np.float64) for k in IN_KEYS}
         warm = batch.get("U_optm_ref", None)

@@ -457,12 +457,13 @@ def test_sqp_full_dynamics_matches_oracle(pkg, name, nb):
     m, veh, cfg, track, mode = _mpc(pkg, name, nb)
     o, *_ = make_oracle(pkg, name, tol=1e-10)
     batch = pkg.workload.make_batch(veh, cfg, nb, 0x5A9, track, pkg.workload.load_laps(), mode=mode)
-    MAXIT = 60
+    MAXIT = 100
     n0 = m.launch_count
     out = m.solve_sqp(batch, max_sqp_iter=MAXIT, tol=1e-9)
     assert m.launch_count - n0 >= 4
-    conv = (out["status"] == 0) & (out["sqp_iters"] < MAXIT)
-    assert conv.sum() >= int(0.75 * nb), (conv.sum(), out["sqp_iters"], out["status"])
+    conv = out["status"] == 0             # a run that ends at the cap reports LMPC_SQP_MAX_ITER (6), never SOLVED
+    assert ((out["status"] == 6) == ((out["sqp_iters"] >= MAXIT) & (out["status"] != 1) & (out["status"] != 4))).all() or (out["status"] != 6).all()
+    assert conv.sum() >= int(np.ceil(0.99 * nb)), (conv.sum(), out["sqp_iters"], out["status"])
     scale = max(1.0, np.abs(out["X_optm"][conv]).max())
     assert out["defect"][conv].max() < 1e-7 * scale, out["defect"][conv].max()
     one = m.solve(batch)
@@ -470,11 +471,10 @@ def test_sqp_full_dynamics_matches_oracle(pkg, name, nb):
     worst, n = 0.0, 0
     for b in np.where(conv)[0]:
         r = o.step_sqp(pkg.workload.instance(batch, b), max_sqp_iter=MAXIT, tol=1e-9)
-        if r["status"] != 0 or r["sqp_iters"] >= MAXIT:
-            continue
+        assert r["status"] == 0, (b, r["status"], r["sqp_iters"])
         worst = max(worst, relerr(out["X_optm"][b], r["X"]), relerr(out["U_optm"][b], r["U"]), relerr(out["dU_optm"][b], r["dU"]))
         n += 1
-    assert n >= int(0.7 * nb), n
+    assert n == conv.sum()
     assert worst < TOL, worst
     print(f"[{name}] SQP: {conv.sum()}/{nb} converged, mean {out['sqp_iters'][conv].mean():.1f} QP solves, worst rel err vs oracle {worst:.2e}")
 
