@@ -290,6 +290,27 @@ typedef struct lmpc_loop_options {
 int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
                          double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
                          double* log_u, int memspace);
+/* ---- per-agent safe sets and lap recording on the device (Monte-Carlo LMPC in which every agent learns from its OWN
+ *      laps).  In the reference each RacingMPC owns a SafeSetManager and a SafeSetRecorder (racing_mpc.hpp:99-100) fed by
+ *      every solve (racing_mpc.cpp:245-246, safe_set.cpp:278-322).  lmpc_agents_create gives each of B agents its own
+ *      circular buffer of max_lap_stored laps (capacity max_lap_samples each), seeded with the handle's current laps, and a
+ *      recorder; lmpc_closed_loop_run_agents is lmpc_closed_loop_run in which every tick feeds the agents' recorders with
+ *      (x_ic, u_ic, curvatures(0), t_ic = t0 + tick dt), stores completed laps (process_lap_data, safe_set.cpp:116-137) and
+ *      queries each agent's own laps -- all on the device.  log_rec (optional) [ticks][B][10]: what each recorder was fed.
+ *      The shared-set entry points (lmpc_solve_batch, lmpc_closed_loop_run with another B) keep using the handle's laps. ---- */
+int lmpc_agents_create(lmpc_handle* h, int B, int max_lap_samples);
+int lmpc_agents_destroy(lmpc_handle* h);
+int lmpc_closed_loop_run_agents(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                                double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                                double* log_u, double* log_rec, double t0, int memspace);
+/* the agent's which-th newest stored lap (0 = newest): n_out samples, x [n][6] (host buffer of capacity max_n; may be NULL) */
+int lmpc_agents_get_lap(lmpc_handle* h, int agent, int which, int max_n, int32_t* n_out, double* x);
+/* host arrays [B]: SafeSetRecorder::lap_count_, laps stored, flags (bit 3: a lap overflowed max_lap_samples) */
+int lmpc_agents_status(lmpc_handle* h, int32_t* lap_count, int32_t* stored, int32_t* flags);
+/* SafeSetManager::query for every agent on its own laps (host buffers): query [B][2] -> ss_x [B][max_total][6], ss_j, count [B] */
+int lmpc_agents_query_batch(lmpc_handle* h, const double* query, int max_total, int max_per_lap, double* ss_x, double* ss_j,
+                            int32_t* count);
+
 /* The preparation step on its own (DEVICE buffers only): fills the input keys of lmpc_solve_batch. */
 int lmpc_prepare_batch(lmpc_handle* h, int B, const lmpc_loop_options* opt, const double* x, const double* u_prev,
                        const double* X_last, const double* U_last, double* x_ic, double* u_ic, double* X_ref, double* U_ref,

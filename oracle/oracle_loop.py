@@ -56,13 +56,20 @@ def plant_step(orc, trk, opt, x, ua, laps):
     return x, laps
 
 
-def closed_loop(orc, trk, opt, ticks, x, u_prev, X_last, U_last, impl="port"):
+def closed_loop(orc, trk, opt, ticks, x, u_prev, X_last, U_last, impl="port", recorder=None, t0=0.0):
+    """recorder: an oracle_regress.Recorder -- the agent then learns from its own laps: every tick feeds the recorder with
+    (x_ic, u_ic, curvatures(0), t_ic) before the safe-set query, and a completed lap joins the agent's safe set (`orc`
+    must then be the agent's own Oracle), as RacingMPC::solve does (racing_mpc.cpp:245-255)."""
     x = np.array(x, dtype=float); u_prev = np.array(u_prev, dtype=float)
     X_last = np.array(X_last, dtype=float); U_last = np.array(U_last, dtype=float)
     laps, fails = 0, 0
     log_x, log_u = [], []
-    for _ in range(ticks):
+    for tick in range(ticks):
         inp = prepare(orc, trk, opt, x, u_prev, X_last, U_last)
+        if recorder is not None:
+            if recorder.step(inp["x_ic"], inp["u_ic"], float(inp["curvatures"][0]), t0 + opt["dt"] * tick, trk.L):
+                l = recorder.laps[-1]
+                orc.add_lap(l["x"], l["u"], l["k"], l["t"], trk.L)
         r = orc.step(inp, impl=impl)
         if r["status"] == 0:                                                        # racing_mpc_node.cpp:322-331
             X_last, U_last = r["X"], r["U"]

@@ -102,6 +102,7 @@ EXPORTS = [
     "lmpc_frenet_to_global_batch", "lmpc_global_to_frenet_batch", "lmpc_closed_loop_run", "lmpc_prepare_batch",
     "lmpc_recorder_config", "lmpc_recorder_step", "lmpc_recorder_lap_count", "lmpc_safe_set_regress_batch", "lmpc_set_error_dynamics",
     "lmpc_to_base_control_batch", "lmpc_from_base_control_batch", "lmpc_model_create", "lmpc_safe_set_tick_count",
+    "lmpc_agents_create", "lmpc_agents_destroy", "lmpc_closed_loop_run_agents", "lmpc_agents_get_lap", "lmpc_agents_status", "lmpc_agents_query_batch",
     "lmpc_gather_init", "lmpc_gather_connect", "lmpc_gather_buffer", "lmpc_solve_gather_batch", "lmpc_gather_wait", "lmpc_gather_error",
 ]
 LMPC_IPC_HANDLE_BYTES = 64
@@ -161,6 +162,12 @@ def load_library(path=None):
     L.lmpc_from_base_control_batch.argtypes = [vp, C.c_int, vp, vp, C.c_int]
     L.lmpc_model_create.argtypes = [C.POINTER(VehicleParams), C.c_int, C.POINTER(vp)]
     L.lmpc_safe_set_tick_count.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.lmpc_agents_create.argtypes = [vp, C.c_int, C.c_int]
+    L.lmpc_agents_destroy.argtypes = [vp]
+    L.lmpc_closed_loop_run_agents.argtypes = [vp, C.c_int, C.c_int, C.POINTER(LoopOptions)] + [vp] * 9 + [C.c_double, C.c_int]
+    L.lmpc_agents_get_lap.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), vp]
+    L.lmpc_agents_status.argtypes = [vp, vp, vp, vp]
+    L.lmpc_agents_query_batch.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
     L.lmpc_gather_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_size_t)]
     L.lmpc_gather_connect.argtypes = [vp, vp]
     L.lmpc_gather_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]

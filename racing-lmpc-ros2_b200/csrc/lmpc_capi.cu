@@ -21,6 +21,7 @@ namespace {
 
 struct HostLap {
   int n;
+  double L;   // total_length the lap was added with
   std::vector<double> ps, pe, xr, J;
   std::vector<int> canon;
   std::vector<double> x, u, k, t;   // the lap as given (regression points; u/k/t empty if the caller passed none)
@@ -87,6 +88,10 @@ struct lmpc_handle {
     unsigned long long seq = 0;
     int active_set = -1;                      // >= 0 while lmpc_solve_gather_batch routes the trajectory outputs
   } gat;
+  // per-agent safe sets + device-side lap recording (lmpc_agents_*; csrc/lmpc_agents.cuh)
+  LmpcAgentSets ag{};
+  DevBuf ag_buf, ag_cnt;       // one allocation for the agents' arrays; per-instance column counts of the tick
+  bool ag_on = false;
   // optional per-kernel timing: events recorded on the stream around the three kernels of each solve
   bool timing = false;
   std::vector<cudaEvent_t> tev;   // 4 events per recorded solve (ring)
@@ -195,7 +200,7 @@ extern "C" int lmpc_destroy(lmpc_handle* h) {
   if (h->side) cudaStreamDestroy(h->side);
   for (int p = 0; p < LMPC_MAX_PEERS; p++) if (h->gat.peer[p]) cudaIpcCloseMemHandle(h->gat.peer[p]);
   if (h->gat.base) cudaFree(h->gat.base);
-  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->reg_slab, &h->ws_reg, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out})
+  for (DevBuf* b : {&h->slab, &h->ws_abg, &h->ws_cen, &h->ws_ssx, &h->ws_ssj, &h->ws_sqp, &h->ws_qpscr, &h->reg_slab, &h->ws_reg, &h->track_dev, &h->ws_loop, &h->st_loop, &h->st_in, &h->st_out, &h->ag_buf, &h->ag_cnt})
     if (b->p) cudaFree(b->p);
   delete h;
   return LMPC_OK;
@@ -324,7 +329,7 @@ extern "C" int lmpc_safe_set_add_lap(lmpc_handle* h, int n, const double* x, con
                                      const double* t, double L) {
   if (!h || n < 1 || !x) return LMPC_ERR_INVALID;
   HostLap lap;
-  lap.n = n;
+  lap.n = n; lap.L = L;
   lap.x.assign(x, x + 6 * (size_t)n);   // u, k, t are read by the error-dynamics regression only
   if (u && k && t) { lap.u.assign(u, u + 2 * (size_t)n); lap.k.assign(k, k + n); lap.t.assign(t, t + n); }
   const size_t m = 3 * (size_t)n;
@@ -832,7 +837,21 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   // K2: safe-set query at X_ref[:, N-1] (racing_mpc.cpp:249-255), padded to K columns (:263-272).  Independent of K1:
   // forked onto the side stream here, joined before K3.
   const bool fork_ss = learn && first;
-  if (fork_ss) {
+  const bool per_agent = h->ag_on && B == h->ag.B;
+  if (fork_ss && per_agent) {
+    // every agent queries its OWN laps (lmpc_agents_query_kernel); the column count is per instance
+    const int per_lap = std::max(1, (int)h->cfg.num_ss_pts_per_lap);
+    const int max_used = std::min(h->ag.slots, ((int)K + per_lap - 1) / per_lap);
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    const int warps = B * max_used, threads = 128, blocks = (warps * 32 + threads - 1) / threads;
+    lmpc_agents_query_kernel<<<blocks, threads, 0, h->side>>>(h->ag, max_used, per_lap, (int)N, io.din[0], X_lin, io.din[9], nullptr, (int)K, (int)K,
+                                                               io.ssx, io.ssj, (int*)h->ag_cnt.p);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_join, h->side));
+    *ss_count_io = (int)K;
+  } else if (fork_ss) {
     LmpcLapTable tab;
     int rc = make_lap_table(h, (int)K, h->cfg.num_ss_pts_per_lap, &tab);
     if (rc != LMPC_OK) return rc;
@@ -879,6 +898,7 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   a.bl = io.din[5]; a.br = io.din[6]; a.vref = io.din[8]; a.ABg = abg; a.ssx = io.ssx; a.ssj = io.ssj; a.cen = cen;
   a.X = io.dout[0]; a.U = io.dout[1]; a.dU = io.dout[2]; a.lam = io.dout[3]; a.cost = io.dout[6];
   a.status = io.d_status; a.iters = io.d_iters; a.ss_count = *ss_count_io; a.B = B; a.skip = skip;
+  a.ss_count_v = (learn && per_agent) ? (const int*)h->ag_cnt.p : nullptr;
   a.n_mirror = 0; a.done = nullptr; a.seq = 0;
   if (h->gat.active_set >= 0) {   // lmpc_solve_gather_batch: X, U, dU, cost, status live in this rank's block of the gather buffer
     const lmpc_handle::Gather& G = h->gat;
@@ -1207,6 +1227,124 @@ extern "C" int lmpc_track_eval_batch(lmpc_handle* h, int n, const double* s, dou
 extern "C" int lmpc_frenet_to_global_batch(lmpc_handle* h, int n, const double* frenet, double* global, int memspace) { return track_batch(h, 1, n, frenet, 3, global, 3, memspace); }
 extern "C" int lmpc_global_to_frenet_batch(lmpc_handle* h, int n, const double* global, double* frenet, int memspace) { return track_batch(h, 2, n, global, 3, frenet, 3, memspace); }
 
+// ------------------------------------------------------------------------------------------ per-agent safe sets
+extern "C" int lmpc_agents_destroy(lmpc_handle* h) {
+  if (!h) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->ag_buf.p) { cudaFree(h->ag_buf.p); h->ag_buf = DevBuf(); }
+  h->ag_on = false; h->ag = LmpcAgentSets{};
+  return LMPC_OK;
+}
+
+extern "C" int lmpc_agents_create(lmpc_handle* h, int B, int max_lap_samples) {
+  if (!h || B < 1 || B > h->max_batch || max_lap_samples < 8) return LMPC_ERR_INVALID;
+  if (!h->P.learning) { h->err = "per-agent safe sets need a learning configuration"; return LMPC_ERR_INVALID; }
+  if (h->reg_in_tick) { h->err = "the in-tick error-dynamics regression reads the shared laps: disable it for per-agent safe sets"; return LMPC_ERR_INVALID; }
+  lmpc_agents_destroy(h);
+  CK(cudaSetDevice(h->device));
+  LmpcAgentSets A{};
+  A.B = B; A.slots = std::max(1, (int)h->cfg.max_lap_stored); A.cap = max_lap_samples;
+  for (const HostLap& l : h->laps) if (l.n > A.cap) { h->err = "a stored lap is longer than max_lap_samples"; return LMPC_ERR_INVALID; }
+  const size_t Bz = (size_t)B, pts = Bz * A.slots * 3 * (size_t)A.cap, rec = Bz * (size_t)A.cap;
+  const size_t n_dbl = pts * 9 + rec * 10 + Bz * 10 + Bz, n_int = pts + Bz * A.slots + 5 * Bz;
+  int rc = dev_reserve(h, h->ag_buf, sizeof(double) * n_dbl + sizeof(int) * n_int);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->ag_cnt, sizeof(int) * (size_t)h->max_batch);
+  if (rc != LMPC_OK) return rc;
+  double* d = (double*)h->ag_buf.p;
+  A.ps = d; d += pts; A.pe = d; d += pts; A.J = d; d += pts; A.xr = d; d += 6 * pts;
+  A.rec_x = d; d += 6 * rec; A.rec_u = d; d += 2 * rec; A.rec_k = d; d += rec; A.rec_t = d; d += rec;
+  A.carry = d; d += 10 * Bz; A.last_px = d; d += Bz;
+  int* q = (int*)d;
+  A.canon = q; q += pts; A.n = q; q += Bz * A.slots; A.head = q; q += Bz; A.count = q; q += Bz; A.rec_n = q; q += Bz; A.flags = q; q += Bz;
+  A.lap_count = q; q += Bz;
+  CK(cudaMemsetAsync(A.n, 0, sizeof(int) * (Bz * A.slots + 5 * Bz), h->stream));
+  h->ag = A; h->ag_on = true;
+  // every agent starts from the handle's laps (oldest first), as if each had called SafeSetRecorder::load on them; the
+  // recorder's lap counter starts after them (safe_set.cpp:269)
+  DevBuf tmp;
+  for (const HostLap& l : h->laps) {
+    rc = dev_reserve(h, tmp, sizeof(double) * 6 * (size_t)l.n);
+    if (rc != LMPC_OK) return rc;
+    CK(cudaMemcpyAsync(tmp.p, l.x.data(), sizeof(double) * 6 * (size_t)l.n, cudaMemcpyHostToDevice, h->stream));
+    lmpc_agents_add_lap_kernel<<<(B * 32 + 127) / 128, 128, 0, h->stream>>>(h->ag, nullptr, (const double*)tmp.p, l.n, l.L);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (tmp.p) cudaFree(tmp.p);
+  if (!h->laps.empty()) {
+    std::vector<int> lc((size_t)B, (int)h->laps.size());
+    CK(cudaMemcpyAsync(A.lap_count, lc.data(), sizeof(int) * Bz, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return LMPC_OK;
+}
+
+// read-back for tests and for saving learned laps: the agent's `which`-th newest stored lap (0 = newest); returns the
+// un-tripled samples x [n][6] (capacity max_n) and the lap's cost-to-go is implied (J_j = n - 1 - j)
+extern "C" int lmpc_agents_get_lap(lmpc_handle* h, int agent, int which, int max_n, int32_t* n_out, double* x) {
+  if (!h || !h->ag_on || agent < 0 || agent >= h->ag.B || which < 0 || !n_out) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const LmpcAgentSets& A = h->ag;
+  int cnt = 0, hd = 0;
+  CK(cudaMemcpy(&cnt, A.count + agent, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&hd, A.head + agent, sizeof(int), cudaMemcpyDeviceToHost));
+  if (which >= cnt) { *n_out = 0; return LMPC_OK; }
+  const int slot = (hd + cnt - 1 - which) % A.slots;
+  int n = 0;
+  CK(cudaMemcpy(&n, A.n + (size_t)agent * A.slots + slot, sizeof(int), cudaMemcpyDeviceToHost));
+  *n_out = n;
+  if (x) {
+    if (n > max_n) return LMPC_ERR_CAPACITY;
+    // the middle copy of the tripled set is the lap itself (x_repeat = [x - L e0, x, x + L e0])
+    CK(cudaMemcpy(x, A.xr + 6 * (lmpc_ag_slot(A, agent, slot) + (size_t)n), sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost));
+  }
+  return LMPC_OK;
+}
+
+// recorder state per agent: lap_count [B] (SafeSetRecorder::lap_count_), stored [B] laps in the safe set, flags [B]
+// (bit 3: a lap overflowed max_lap_samples and was truncated).  Host buffers.
+extern "C" int lmpc_agents_status(lmpc_handle* h, int32_t* lap_count, int32_t* stored, int32_t* flags) {
+  if (!h || !h->ag_on) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t nb = sizeof(int) * (size_t)h->ag.B;
+  if (lap_count) CK(cudaMemcpy(lap_count, h->ag.lap_count, nb, cudaMemcpyDeviceToHost));
+  if (stored) CK(cudaMemcpy(stored, h->ag.count, nb, cudaMemcpyDeviceToHost));
+  if (flags) CK(cudaMemcpy(flags, h->ag.flags, nb, cudaMemcpyDeviceToHost));
+  return LMPC_OK;
+}
+
+// SafeSetManager::query for every agent on its own laps: query [B][2] (s, e_y) -> ss_x [B][max_total][6], ss_j [B][max_total]
+// (raw J), count [B].  Host buffers.  Columns beyond count[b] are left untouched.
+extern "C" int lmpc_agents_query_batch(lmpc_handle* h, const double* query, int max_total, int max_per_lap, double* ss_x, double* ss_j, int32_t* count) {
+  if (!h || !h->ag_on || !query || !ss_x || !ss_j || !count || max_total < 1 || max_per_lap < 1) return LMPC_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const int B = h->ag.B;
+  const size_t nq = 2 * (size_t)B, nx = 6 * (size_t)max_total * B, nj = (size_t)max_total * B;
+  int rc = dev_reserve(h, h->st_in, sizeof(double) * nq);
+  if (rc == LMPC_OK) rc = dev_reserve(h, h->st_out, sizeof(double) * (nx + nj));
+  if (rc != LMPC_OK) return rc;
+  CK(cudaMemcpyAsync(h->st_in.p, query, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream));
+  double* dx = (double*)h->st_out.p; double* dj = dx + nx;
+  const int max_used = std::min(h->ag.slots, (max_total + max_per_lap - 1) / max_per_lap);
+  lmpc_agents_query_kernel<<<(B * max_used * 32 + 127) / 128, 128, 0, h->stream>>>(h->ag, max_used, max_per_lap, 0, nullptr, nullptr, nullptr,
+                                                                                   (const double*)h->st_in.p, max_total, max_total, dx, dj, (int*)h->ag_cnt.p);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(count, h->ag_cnt.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < B; b++) {
+    if (count[b] < 1) continue;
+    CK(cudaMemcpyAsync(ss_x + 6 * (size_t)max_total * b, dx + 6 * (size_t)max_total * b, sizeof(double) * 6 * (size_t)count[b], cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ss_j + (size_t)max_total * b, dj + (size_t)max_total * b, sizeof(double) * (size_t)count[b], cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return LMPC_OK;
+}
+
 // ------------------------------------------------------------------------------------------ closed loop
 static LmpcLoopParams loop_params(const lmpc_loop_options* o) {
   LmpcLoopParams P;
@@ -1216,9 +1354,26 @@ static LmpcLoopParams loop_params(const lmpc_loop_options* o) {
   return P;
 }
 
+static int closed_loop_impl(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                            double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                            double* log_u, double* log_rec, double t0, int memspace);
+
 extern "C" int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
                                     double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
                                     double* log_u, int memspace) {
+  return closed_loop_impl(h, B, ticks, opt, x, u_prev, X_last, U_last, lap_count, fail_count, log_x, log_u, nullptr, 0.0, memspace);
+}
+
+extern "C" int lmpc_closed_loop_run_agents(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                                           double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                                           double* log_u, double* log_rec, double t0, int memspace) {
+  if (!h || !h->ag_on || B != h->ag.B) { if (h) h->err = "lmpc_agents_create(B) first"; return LMPC_ERR_INVALID; }
+  return closed_loop_impl(h, B, ticks, opt, x, u_prev, X_last, U_last, lap_count, fail_count, log_x, log_u, log_rec, t0, memspace);
+}
+
+static int closed_loop_impl(lmpc_handle* h, int B, int ticks, const lmpc_loop_options* opt, double* x, double* u_prev,
+                            double* X_last, double* U_last, int32_t* lap_count, int32_t* fail_count, double* log_x,
+                            double* log_u, double* log_rec, double t0, int memspace) {
   if (!h || !opt || B < 1 || ticks < 1 || !x || !u_prev || !X_last || !U_last) return LMPC_ERR_INVALID;
   if (B > h->max_batch) return LMPC_ERR_CAPACITY;
   if (h->track.m == 0) { h->err = "no track set (lmpc_track_set / lmpc_track_load)"; return LMPC_ERR_INVALID; }
@@ -1244,16 +1399,18 @@ extern "C" int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc
   int32_t* d_tick = d_fail + Bz;
   // agent state: caller's device buffers, or a staged copy of the caller's host buffers
   LmpcLoopState S;
-  double *dlogx = log_x, *dlogu = log_u;
+  double *dlogx = log_x, *dlogu = log_u, *dlogr = log_rec;
+  const bool agents = h->ag_on && B == h->ag.B;
   const size_t n_state = 6 * Bz + 2 * Bz + 6 * N * Bz + 2 * NS * Bz;
   if (memspace == LMPC_MEM_HOST) {
-    const size_t n_log = (log_x ? 6 * Bz * (size_t)ticks : 0) + (log_u ? 2 * Bz * (size_t)ticks : 0);
+    const size_t n_log = (log_x ? 6 * Bz * (size_t)ticks : 0) + (log_u ? 2 * Bz * (size_t)ticks : 0) + (log_rec ? 10 * Bz * (size_t)ticks : 0);
     rc = dev_reserve(h, h->st_loop, sizeof(double) * (n_state + n_log));
     if (rc != LMPC_OK) return rc;
     double* q = (double*)h->st_loop.p;
     S.x = q; q += 6 * Bz; S.u_prev = q; q += 2 * Bz; S.X_last = q; q += 6 * N * Bz; S.U_last = q; q += 2 * NS * Bz;
     if (log_x) { dlogx = q; q += 6 * Bz * (size_t)ticks; }
     if (log_u) { dlogu = q; q += 2 * Bz * (size_t)ticks; }
+    if (log_rec) { dlogr = q; q += 10 * Bz * (size_t)ticks; }
     CK(cudaMemcpyAsync(S.x, x, sizeof(double) * 6 * Bz, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.u_prev, u_prev, sizeof(double) * 2 * Bz, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.X_last, X_last, sizeof(double) * 6 * N * Bz, cudaMemcpyHostToDevice, h->stream));
@@ -1278,6 +1435,14 @@ extern "C" int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc
     lmpc_prepare_kernel<<<pblocks, pthreads, 0, h->stream>>>(h->M, h->track, O, B, (int)N, S, I);
     h->launches++;
     CK(cudaGetLastError());
+    if (agents) {
+      // RacingMPC::solve feeds its recorder before the query (racing_mpc.cpp:245-255): a lap completed by this tick's
+      // sample is in the agent's safe set for this tick's solve
+      lmpc_agents_record_kernel<<<ablocks, pthreads, 0, h->stream>>>(h->ag, I.x_ic, I.u_ic, I.kap, (int)N, I.L, t0, opt->dt, d_tick, dlogr, ticks);
+      lmpc_agents_add_lap_kernel<<<(B * 32 + pthreads - 1) / pthreads, pthreads, 0, h->stream>>>(h->ag, I.L, nullptr, 0, 0.0);
+      h->launches += 2;
+      CK(cudaGetLastError());
+    }
     int ss_count = 0;
     rc = run_tick_kernels(h, B, io, I.X_ref, I.U_ref, I.U_ref, true, nullptr, &ss_count);
     if (rc != LMPC_OK) return rc;
@@ -1295,6 +1460,7 @@ extern "C" int lmpc_closed_loop_run(lmpc_handle* h, int B, int ticks, const lmpc
     if (fail_count) CK(cudaMemcpyAsync(fail_count, d_fail, sizeof(int32_t) * Bz, cudaMemcpyDeviceToHost, h->stream));
     if (log_x) CK(cudaMemcpyAsync(log_x, dlogx, sizeof(double) * 6 * Bz * (size_t)ticks, cudaMemcpyDeviceToHost, h->stream));
     if (log_u) CK(cudaMemcpyAsync(log_u, dlogu, sizeof(double) * 2 * Bz * (size_t)ticks, cudaMemcpyDeviceToHost, h->stream));
+    if (log_rec) CK(cudaMemcpyAsync(log_rec, dlogr, sizeof(double) * 10 * Bz * (size_t)ticks, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   } else {
     if (lap_count) CK(cudaMemcpyAsync(lap_count, d_lap, sizeof(int32_t) * Bz, cudaMemcpyDeviceToDevice, h->stream));

@@ -12,6 +12,7 @@
 #include "lmpc_qp_kernel.cuh"
 #include "lmpc_ss_core.cuh"
 #include "lmpc_reg_core.cuh"
+#include "lmpc_agents.cuh"
 
 #define LMPC_MAX_LAPS_USED 64   // laps one query can draw from (the table travels as a kernel parameter, 3.6 KB)
 

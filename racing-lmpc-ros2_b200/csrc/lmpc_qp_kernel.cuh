@@ -10,6 +10,7 @@ struct LmpcQpBatch {
   double* scratch;   // [B][LMPC_QP_SCRATCH(N, K)] workspace
   int *status, *iters;
   int ss_count;
+  const int* ss_count_v;   // optional [B]: columns found per instance (per-agent safe sets); overrides ss_count
   int B;
   const int* skip;   // optional [B]: non-zero = leave this instance's outputs untouched (converged SQP instances)
   // Fused result exchange over NVLink peer memory (lmpc_solve_gather_batch).  The trajectory outputs X, U,
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
   in.ABg = a.ABg + (54 * (size_t)NS) * b;
   in.ssx = P.learning ? a.ssx + (6 * (size_t)K) * b : nullptr;
   in.ssj = P.learning ? a.ssj + (size_t)K * b : nullptr;
-  in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count;
+  in.cen = a.cen + 6 * (size_t)b; in.ss_count = a.ss_count_v ? a.ss_count_v[b] : a.ss_count;
   in.scratch = a.scratch + (size_t)LMPC_QP_SCRATCH(N, K) * b;
   LmpcQpOut out;
   out.X = a.X + (6 * (size_t)N) * b; out.U = a.U + (2 * (size_t)NS) * b; out.dU = a.dU + (2 * (size_t)NS) * b;

@@ -256,6 +256,63 @@ class BatchedRacingMPC:
             out["log_x"] = lx; out["log_u"] = lu
         return out
 
+    # ------------------------------------------------------------------ per-agent safe sets (device-side learning)
+    def agents_create(self, Bn, max_lap_samples=1024):
+        """Give each of Bn agents its own safe set (seeded with the current laps) and lap recorder on the device."""
+        _check(self.lib, self._h, self.lib.lmpc_agents_create(self._h, int(Bn), int(max_lap_samples)), "lmpc_agents_create")
+        self._agents = (int(Bn), int(max_lap_samples))
+
+    def agents_destroy(self):
+        _check(self.lib, self._h, self.lib.lmpc_agents_destroy(self._h), "lmpc_agents_destroy")
+
+    def closed_loop_agents(self, opt, ticks, x, u_prev, X_last, U_last, lap_count=None, t0=0.0, log=True):
+        """closed_loop() in which every agent records its own laps and queries its own safe set (lmpc_closed_loop_run_agents).
+        Adds log_rec (ticks, B, 10): what each agent's recorder was fed (x_ic, u_ic, curvatures[0], t_ic)."""
+        x = np.array(x, dtype=np.float64, order="C"); u_prev = np.array(u_prev, dtype=np.float64, order="C")
+        X_last = np.array(X_last, dtype=np.float64, order="C"); U_last = np.array(U_last, dtype=np.float64, order="C")
+        Bn = x.shape[0]
+        laps = np.zeros(Bn, dtype=np.int32) if lap_count is None else np.array(lap_count, dtype=np.int32)
+        fails = np.zeros(Bn, dtype=np.int32)
+        lx = np.zeros((ticks, Bn, 6)) if log else None
+        lu = np.zeros((ticks, Bn, 2)) if log else None
+        lr = np.zeros((ticks, Bn, 10)) if log else None
+        rc = self.lib.lmpc_closed_loop_run_agents(self._h, Bn, int(ticks), C.byref(opt), x.ctypes.data, u_prev.ctypes.data,
+                                                  X_last.ctypes.data, U_last.ctypes.data, laps.ctypes.data, fails.ctypes.data,
+                                                  lx.ctypes.data if log else None, lu.ctypes.data if log else None,
+                                                  lr.ctypes.data if log else None, float(t0), B.LMPC_MEM_HOST)
+        _check(self.lib, self._h, rc, "lmpc_closed_loop_run_agents")
+        out = dict(x=x, u_prev=u_prev, X_last=X_last, U_last=U_last, lap_count=laps, fail_count=fails)
+        if log:
+            out["log_x"] = lx; out["log_u"] = lu; out["log_rec"] = lr
+        return out
+
+    def agents_status(self):
+        Bn = self._agents[0]
+        lc = np.zeros(Bn, dtype=np.int32); st = np.zeros(Bn, dtype=np.int32); fl = np.zeros(Bn, dtype=np.int32)
+        _check(self.lib, self._h, self.lib.lmpc_agents_status(self._h, lc.ctypes.data, st.ctypes.data, fl.ctypes.data), "lmpc_agents_status")
+        return dict(lap_count=lc, stored=st, flags=fl)
+
+    def agents_get_lap(self, agent, which=0):
+        """The agent's which-th newest stored lap (0 = newest) as (n, 6) states, or None."""
+        n = C.c_int32()
+        _check(self.lib, self._h, self.lib.lmpc_agents_get_lap(self._h, int(agent), int(which), 0, C.byref(n), None), "lmpc_agents_get_lap")
+        if n.value == 0:
+            return None
+        x = np.zeros((n.value, 6))
+        _check(self.lib, self._h, self.lib.lmpc_agents_get_lap(self._h, int(agent), int(which), n.value, C.byref(n), x.ctypes.data), "lmpc_agents_get_lap")
+        return x
+
+    def agents_query(self, queries, max_total=None, per_lap=None):
+        """SafeSetManager::query of every agent on its own laps: (B, 2) -> list of (ss_x (count_b, 6), ss_j (count_b,))."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 2)
+        Bn = q.shape[0]
+        mt = int(self.K if max_total is None else max_total)
+        pl = int(self.config["num_ss_pts_per_lap"] if per_lap is None else per_lap)
+        sx = np.zeros((Bn, mt, 6)); sj = np.zeros((Bn, mt)); cnt = np.zeros(Bn, dtype=np.int32)
+        rc = self.lib.lmpc_agents_query_batch(self._h, q.ctypes.data, mt, pl, sx.ctypes.data, sj.ctypes.data, cnt.ctypes.data)
+        _check(self.lib, self._h, rc, "lmpc_agents_query_batch")
+        return [(sx[b, :cnt[b]], sj[b, :cnt[b]]) for b in range(Bn)]
+
     # ------------------------------------------------------------------ model
     def discrete_dynamics(self, x, u, kappa, dt):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 6)

@@ -47,6 +47,14 @@ t = wall(run_loop, 2)
 print(f"closed loop (prepare + solve + plant on the device): {nb} agents x {ticks} ticks in {t*1e3:.1f} ms -> {nb*ticks/t:.3e} agent-ticks/s; "
       f"agents with a failed tick {float((res['o']['fail_count'] > 0).mean()):.4f}", flush=True)
 
+# the same loop with per-agent safe sets and device-side lap recording (every agent learns from its own laps)
+mpc.agents_create(nb, 1024)
+def run_loop_ag(): res["a"] = mpc.closed_loop_agents(opt, ticks, x, u_prev, X_last, U_last, log=False)
+t = wall(run_loop_ag, 2)
+print(f"closed loop, per-agent safe sets + recording on the device: {nb} agents x {ticks} ticks in {t*1e3:.1f} ms -> {nb*ticks/t:.3e} agent-ticks/s; "
+      f"agents with a failed tick {float((res['a']['fail_count'] > 0).mean()):.4f}", flush=True)
+mpc.agents_destroy()
+
 # ---- f3: error-dynamics regression, stand-alone and inside the tick
 spec = make_reg_spec([3, 4, 5], [[3, 4, 5]] * 3, [[0], [1], [1]], 0.6)
 n = 1024 * 19
