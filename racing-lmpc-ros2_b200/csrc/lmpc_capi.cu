@@ -65,7 +65,7 @@ struct lmpc_handle {
   DevBuf ws_abg, ws_cen, ws_ssx, ws_ssj, ws_sqp, ws_qpscr;
   // error-dynamics regression: points of all laps (built lazily after a safe-set change), optional in-tick plan
   DevBuf reg_slab, ws_reg;
-  LmpcRegView reg_view{nullptr, nullptr, 0, 0};
+  LmpcRegView reg_view{nullptr, nullptr, 0, 0, -1};
   bool reg_dirty = true;
   bool reg_in_tick = false;
   LmpcRegPlan reg_plan{};
@@ -466,20 +466,35 @@ static int ensure_reg_slab(lmpc_handle* h) {
     if (l.u.empty()) { h->err = "a stored lap has no u / k / t: the regression needs them"; return LMPC_ERR_INVALID; }
     M += (size_t)(l.n - 1);
   }
-  h->reg_view = LmpcRegView{nullptr, nullptr, 0, 0};
+  h->reg_view = LmpcRegView{nullptr, nullptr, 0, 0, -1};
   if (M == 0) { h->reg_dirty = false; return LMPC_OK; }
   // slab, by column with stride ld (M rounded up to 32): Z [8][ld] | E [6][ld] | Xn [6][ld] | kappa [ld] | dt [ld]
   // (the last three only feed the prepare kernel)
   const size_t ld = (M + 31) & ~(size_t)31;
   std::vector<double> hd(22 * ld, 0.0);
   double* Z = hd.data(); double* Xn = Z + 14 * ld; double* kp = Xn + 6 * ld; double* dt = kp + ld;
+  // The samples are stored SORTED by one component of (x, u) -- the one with the widest spread among e_psi, v_x, v_y,
+  // omega and the controls (the abscissa and e_y are not dynamics inputs) -- so that a query's scan can be cut to the
+  // window |z - z_q| < dist_max of that component.  The order of the sums changes, nothing else.
+  struct Src { const HostLap* l; int j; };
+  std::vector<Src> src; src.reserve(M);
+  for (const HostLap& l : h->laps) for (int j = 0; j + 1 < l.n; j++) src.push_back(Src{&l, j});
+  auto comp = [](const Src& s_, int c) { return c < 6 ? s_.l->x[6 * (size_t)s_.j + c] : s_.l->u[2 * (size_t)s_.j + (c - 6)]; };
+  int sort_dim = 2; double best = -1.0;
+  for (int c = 2; c < 8; c++) {
+    double lo = 1e300, hi = -1e300;
+    for (const Src& s_ : src) { const double v = comp(s_, c); lo = std::min(lo, v); hi = std::max(hi, v); }
+    if (hi - lo > best) { best = hi - lo; sort_dim = c; }
+  }
+  std::stable_sort(src.begin(), src.end(), [&](const Src& a, const Src& b) { return comp(a, sort_dim) < comp(b, sort_dim); });
   size_t p = 0;
-  for (const HostLap& l : h->laps)
-    for (int j = 0; j + 1 < l.n; j++, p++) {
-      for (int c = 0; c < 6; c++) { Z[c * ld + p] = l.x[6 * (size_t)j + c]; Xn[c * ld + p] = l.x[6 * (size_t)(j + 1) + c]; }
-      Z[6 * ld + p] = l.u[2 * (size_t)j]; Z[7 * ld + p] = l.u[2 * (size_t)j + 1];
-      kp[p] = l.k[j]; dt[p] = l.t[j + 1] - l.t[j];
-    }
+  for (const Src& s_ : src) {
+    const HostLap& l = *s_.l; const int j = s_.j;
+    for (int c = 0; c < 6; c++) { Z[c * ld + p] = l.x[6 * (size_t)j + c]; Xn[c * ld + p] = l.x[6 * (size_t)(j + 1) + c]; }
+    Z[6 * ld + p] = l.u[2 * (size_t)j]; Z[7 * ld + p] = l.u[2 * (size_t)j + 1];
+    kp[p] = l.k[j]; dt[p] = l.t[j + 1] - l.t[j];
+    p++;
+  }
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));   // kernels in flight may still read the old slab
   int rc = dev_reserve(h, h->reg_slab, sizeof(double) * 22 * ld);
@@ -491,7 +506,7 @@ static int ensure_reg_slab(lmpc_handle* h) {
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));   // hd is stack-scoped
-  h->reg_view = LmpcRegView{d, d + 8 * ld, (int)M, (int)ld};
+  h->reg_view = LmpcRegView{d, d + 8 * ld, (int)M, (int)ld, sort_dim};
   h->reg_dirty = false;
   return LMPC_OK;
 }

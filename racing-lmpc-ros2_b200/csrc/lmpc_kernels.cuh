@@ -250,15 +250,34 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel
     }
   }
   const double h = plan.h, ih = 1.0 / h, kc = 0.75 / h;
+  // the block's window of the sorted samples: the union of its queries' windows |z[sort_dim] - z_q[sort_dim]| < h (two
+  // binary searches per query, lane 0), the whole range when the samples are not sorted
+  __shared__ int win[2];
+  if (threadIdx.x == 0) { win[0] = v.sort_dim >= 0 ? v.M : 0; win[1] = v.sort_dim >= 0 ? 0 : v.M; }
+  __syncthreads();
+  if (v.sort_dim >= 0 && live && lane == 0) {
+    const double* key = v.Z + (size_t)v.sort_dim * v.ld;
+    const double ql = zq[v.sort_dim] - h, qh = zq[v.sort_dim] + h;
+    int a = 0, b = v.M;
+    while (a < b) { const int m = (a + b) >> 1; if (key[m] < ql) a = m + 1; else b = m; }   // first key >= ql
+    const int lo = a;
+    b = v.M;
+    while (a < b) { const int m = (a + b) >> 1; if (key[m] <= qh) a = m + 1; else b = m; }  // first key > qh
+    atomicMin(&win[0], lo); atomicMax(&win[1], a);
+  }
+  __syncthreads();
   for (int r = 0; r < plan.n_out; r++) {
     const LmpcRegRow& row = plan.row[r];
     double q[D], Q[NQ], bv[D], cnt = 0.0;
+    bool uses_key = false;
 #pragma unroll
-    for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; }
+    for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; uses_key |= (row.sel[a] == v.sort_dim); }
 #pragma unroll
     for (int k = 0; k < NQ; k++) Q[k] = 0.0;
-    for (int t0 = 0; t0 < v.M; t0 += LMPC_REG_TILE) {
-      const int count = min(LMPC_REG_TILE, v.M - t0);
+    // a regression that does not use the sort component must see every sample
+    const int t_begin = (uses_key && v.sort_dim >= 0) ? (win[0] & ~31) : 0, t_end = (uses_key && v.sort_dim >= 0) ? win[1] : v.M;
+    for (int t0 = t_begin; t0 < t_end; t0 += LMPC_REG_TILE) {
+      const int count = min(LMPC_REG_TILE, t_end - t0);
       __syncthreads();   // the previous tile has been scanned by every warp
       for (int a = 0; a < row.D - 1; a++)
         for (int e = threadIdx.x; e < count; e += blockDim.x) tZ[a * LMPC_REG_TILE + e] = v.Z[(size_t)row.sel[a] * v.ld + t0 + e];

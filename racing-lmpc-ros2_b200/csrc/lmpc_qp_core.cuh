@@ -294,7 +294,13 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // scratch of the group reductions: one warp uses the (then idle) YY block of the sweep, NW warps their own NW x NRED area
   double* RED = (NW == 1) ? (sm + LO(oYY)) : (sm + LO(oRED));
   double* TB = sm + LO(oTERM);
-  const double sfloor = 1e-2, mu0 = 0.1, th0 = 0.01;
+#ifndef LMPC_MU0
+#define LMPC_MU0 0.1
+#endif
+#ifndef LMPC_SFLOOR
+#define LMPC_SFLOOR 1e-2
+#endif
+  const double sfloor = LMPC_SFLOOR, mu0 = LMPC_MU0, th0 = 0.01;
 
   // ---------------------------------------------------------------- load
   // [A|B|g] of all stages (54 (N-1) doubles, contiguous per instance): one bulk asynchronous copy (TMA) that lands while

@@ -66,6 +66,8 @@ struct LmpcRegView {
   const double* E;
   int M;
   int ld;
+  int sort_dim;   // component of (x, u) the samples are sorted by (ascending), or -1: a query whose regressions all use that
+                  // component only visits the samples with |z[sort_dim] - z_q[sort_dim]| < dist_max (binary search)
 };
 
 // One lane's share of the scan of `count` points (global memory or a shared-memory tile):

@@ -75,13 +75,8 @@ mpc.close()
 # ---- configs[3]-like: 50 stored laps, 2 nearest per lap (48 laps searched), 2048 instances, with and without the regression
 cfg4 = dict(cfg, num_ss_pts_per_lap=2, max_lap_stored=50)
 mpc = BatchedRacingMPC(veh, cfg4, max_batch=2048)
-rng = np.random.default_rng(4)
-many = []
-for q in range(50):
-    l = laps[q % 3]
-    xx = l["x"].copy(); xx[:, 1] += 0.02 * rng.standard_normal(xx.shape[0]); xx[:, 3] += 0.05 * rng.standard_normal(xx.shape[0])
-    many.append(dict(x=xx, u=l["u"], k=l["k"], t=l["t"]))
-    mpc.add_lap(xx, l["u"], l["k"], l["t"], tr["length"])
+many = P.workload.synthesise_laps(laps, 50)
+for l in many: mpc.add_lap(l["x"], l["u"], l["k"], l["t"], tr["length"])
 b4 = P.workload.make_batch(veh, cfg4, 2048, 0xB200 + 3, tr, laps)
 t0, ok0, im0, ix0 = dev_solve_time(mpc, b4, 3)
 mpc.set_error_dynamics(spec)

@@ -84,7 +84,7 @@ extern "C" int emu_regress(const lmpc_reg_spec* sp, int M, const double* Z, cons
   if (!lmpc_make_reg_plan(sp, &plan)) return -1;
   std::vector<double> Zc((size_t)8 * M), Ec((size_t)6 * M);   // the device keeps the samples by column
   for (int p = 0; p < M; p++) { for (int c = 0; c < 8; c++) Zc[(size_t)c * M + p] = Z[8 * (size_t)p + c]; for (int c = 0; c < 6; c++) Ec[(size_t)c * M + p] = E[6 * (size_t)p + c]; }
-  LmpcRegView v = {Zc.data(), Ec.data(), M, M};
+  LmpcRegView v = {Zc.data(), Ec.data(), M, M, -1};
   lmpc_regress_warp(plan, v, zq, A, B, C, npts);
   return 0;
 }
