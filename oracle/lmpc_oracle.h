@@ -139,6 +139,11 @@ int orc_step_port(const orc_vehicle* v, const orc_config* c, const orc_safe_set*
                   const orc_step_in* in, orc_step_out* out);
 /* Batch driver (OpenMP over instances) over packed arrays, instance-major; impl 0=port 1=dense.
  * Returns number of instances with status != 0. */
+/* The reference's own solver stack restated (oracle_osqp.c): the QP in the reference's scaled variables, OSQP's published
+ * ADMM with its defaults (eps 1e-3) and polish.  info[8] = {iterations, 0 solved / 1 max_iter, polish accepted, ADMM primal
+ * residual, ADMM dual residual, polished primal residual, polished dual residual, final rho}. */
+int orc_step_osqp(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss, const orc_step_in* in, orc_step_out* out,
+                  int with_var_rows, int rho_interval, int do_polish, int warm, double eps, int max_iter, double* info);
 int orc_step_batch(const orc_vehicle* v, const orc_config* c, const orc_safe_set* ss, int B,
                    const double* x_ic, const double* u_ic, const double* X_ref,
                    const double* U_ref, const double* T_ref, const double* bl, const double* br,

@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblmpc_oracle.so")
-_SRCS = ["oracle_model.c", "oracle_safeset.c", "oracle_qp_dense.c", "oracle_port.c",
+_SRCS = ["oracle_model.c", "oracle_safeset.c", "oracle_qp_dense.c", "oracle_port.c", "oracle_osqp.c",
          "lmpc_oracle.h", "oracle_internal.h", "Makefile"]
 
 
@@ -106,6 +106,8 @@ def lib():
             [dp] * 10 + [dp] * 5 + [C.POINTER(C.c_int), C.POINTER(C.c_int), dp, C.c_int, C.c_int]
         L.orc_step_sqp.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p, C.POINTER(StepIn),
                                    C.POINTER(StepOut), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), dp]
+        L.orc_step_osqp.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p, C.POINTER(StepIn), C.POINTER(StepOut),
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, dp]
         L.orc_check_candidate.restype = C.c_double
         L.orc_check_candidate.argtypes = [C.POINTER(Vehicle), C.POINTER(Config), C.c_void_p,
                                           C.POINTER(StepIn), dp, dp, dp, dp, dp, dp]
@@ -215,6 +217,20 @@ class Oracle:
         return dict(X=X, U=U, dU=dU, lam=lam, ss_x=ssx, ss_cost=ssc, cost=so.cost, sigma_b=so.sigma_b,
                     sigma_h=np.array(list(so.sigma_h)), kkt=so.kkt, status=st, iters=so.iters,
                     polished=so.polished)
+
+    def step_osqp(self, inp, with_var_rows=True, rho_interval=100, polish=True, warm=True, eps=0.0, max_iter=0):
+        """The tick's QP as the REFERENCE's stack solves it (oracle_osqp.c): scaled variables, OSQP's ADMM at its default
+        eps 1e-3, polish.  Returns X, U, dU, lam and info (iterations, solved, polish accepted, residuals)."""
+        N, K = self.N, self.K
+        si, keep = self._mk_in(inp)
+        X = np.zeros((N, 6)); U = np.zeros((N - 1, 2)); dU = np.zeros((N - 1, 2)); lam = np.zeros(max(K, 1))
+        so = StepOut()
+        so.X, so.U, so.dU, so.lambda_ = _p(X), _p(U), _p(dU), _p(lam)
+        info = np.zeros(8)
+        st = self.L.orc_step_osqp(C.byref(self.veh), C.byref(self.cfg), self.ss, C.byref(si), C.byref(so), int(bool(with_var_rows)),
+                                  int(rho_interval), int(bool(polish)), int(bool(warm)), float(eps), int(max_iter), _p(info))
+        return dict(X=X, U=U, dU=dU, lam=lam, status=st, iters=int(info[0]), solved=info[1] == 0, polished=bool(info[2]),
+                    pri_res=info[3], dua_res=info[4], pol_pri_res=info[5], pol_dua_res=info[6], rho=info[7])
 
     def step_sqp(self, inp, max_sqp_iter=20, tol=1e-9, impl="port"):
         """Full-dynamics variant (racing_mpc.cpp:67-84): SQP to convergence.  Returns the step() dict plus
