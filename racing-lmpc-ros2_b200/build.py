@@ -11,7 +11,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(CSRC, "liblmpc_b200.so")
-SOURCES = ["lmpc_capi.cu", "lmpc_qp_tu0.cu", "lmpc_qp_tu1.cu", "lmpc_qp_tu2.cu", "lmpc_qp_tu3.cu"]
+SOURCES = ["lmpc_capi.cu", "lmpc_qp_tu0.cu", "lmpc_qp_tu1.cu", "lmpc_qp_tu2.cu", "lmpc_qp_tu3.cu", "lmpc_qp_tu4.cu"]
 # every header of csrc/ is a dependency of every translation unit (globbed: a hand-kept list went stale once)
 DEPS = SOURCES + sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "lmpc_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -105,6 +105,9 @@ static int qp_fixed_n(const lmpc_handle* h) {
   const char* e = getenv("LMPC_FIXED_LAYOUT");
   if (e && atoi(e) == 0) return 0;
   if (h->P.NW == 1 && h->P.RS == 16 && (h->P.N == 20 || h->P.N == 40)) return h->P.N;
+  // the long shipped horizons (lmpc_qp_tu4.cu): N = 60 with K = 0 or 65..96, N = 80 with K = 0
+  const int kpl_ = std::max(1, (h->P.K + 31) / 32);
+  if (h->P.NW == 1 && h->P.RS == 16 && ((h->P.N == 60 && (kpl_ == 1 || kpl_ == 3)) || (h->P.N == 80 && kpl_ == 1))) return h->P.N;
   if (h->P.NW == 2 && h->P.RS == 16 && h->P.N == 20) return h->P.N;
   return 0;
 }

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include "lmpc_qp_kernel.cuh"
 
-// nf: compile-time horizon of the layout (20, 40) or 0 for the run-time layout.  Both return false when no
+// nf: compile-time horizon of the layout (20, 40; 60, 80 for the shipped long horizons) or 0 for the run-time layout.  Both return false when no
 // instantiation matches (nw, kpl, nf).
 bool lmpc_qp_set_smem(int nw, int kpl, int nf, size_t smem_bytes, cudaError_t* err);
 bool lmpc_qp_launch(int nw, int kpl, int nf, int nblocks, size_t smem_bytes, cudaStream_t stream,
@@ -19,6 +19,7 @@ LMPC_QP_TU_DECL(0);
 LMPC_QP_TU_DECL(1);
 LMPC_QP_TU_DECL(2);
 LMPC_QP_TU_DECL(3);
+LMPC_QP_TU_DECL(4);
 
 #define LMPC_QP_CASE(NW_, KPL_, NF_, RS_)                                                                          \
   if (nw == NW_ && kpl == KPL_ && nf == NF_) {                                                                     \

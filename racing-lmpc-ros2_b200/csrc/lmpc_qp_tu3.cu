@@ -8,9 +8,11 @@ LMPC_QP_TU_DECL(3) {
 bool lmpc_qp_set_smem(int nw, int kpl, int nf, size_t smem, cudaError_t* err) {
   if (err) *err = cudaSuccess;
   return lmpc_qp_tu0(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err) || lmpc_qp_tu1(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err) ||
-         lmpc_qp_tu2(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err) || lmpc_qp_tu3(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err);
+         lmpc_qp_tu2(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err) || lmpc_qp_tu3(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err) ||
+         lmpc_qp_tu4(0, nw, kpl, nf, 0, smem, nullptr, nullptr, nullptr, err);
 }
 bool lmpc_qp_launch(int nw, int kpl, int nf, int nblocks, size_t smem, cudaStream_t s, const LmpcQpParams& P, const LmpcQpBatch& a) {
   return lmpc_qp_tu0(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr) || lmpc_qp_tu1(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr) ||
-         lmpc_qp_tu2(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr) || lmpc_qp_tu3(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr);
+         lmpc_qp_tu2(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr) || lmpc_qp_tu3(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr) ||
+         lmpc_qp_tu4(1, nw, kpl, nf, nblocks, smem, s, &P, &a, nullptr);
 }

@@ -42,6 +42,8 @@ struct LaneVar {
 // ------------------------------------------------------------------ CUDA
 #define LMPC_DEV __device__ __forceinline__
 #define LMPC_HD __host__ __device__ __forceinline__
+#define LMPC_RED __device__ __forceinline__   // the multi-value reductions (tried as calls, __noinline__, to shrink the 270 KB
+                                              // kernel: nvcc inlines them regardless and the kernel grew to 304 KB)
 #define LMPC_HDM __host__ __device__ __forceinline__
 #define GROUP_SYNC(NW)                       \
   do {                                       \
@@ -163,7 +165,7 @@ LMPC_DEV double shfl_xor_f64(double v, int off) { return __shfl_xor_sync(0xfffff
 // shared memory) to every lane.  The additions are the butterfly's own (same pairs, same order; a + b is commutative),
 // so the totals are bit-identical to it.  A remainder of fewer than 8 values takes the butterfly.
 template <int NV>
-LMPC_DEV void warp_reduce_scatter_sum(LaneVar<double, 32> (&x)[NV], double* scratch) {
+LMPC_RED void warp_reduce_scatter_sum(LaneVar<double, 32> (&x)[NV], double* scratch) {
   const unsigned lane = threadIdx.x & 31u;
   constexpr int NFULL = (NV % 32 >= 8) ? NV : (NV / 32) * 32;   // values that go through the halving scheme
 #pragma unroll
@@ -194,7 +196,7 @@ LMPC_DEV void warp_reduce_scatter_sum(LaneVar<double, 32> (&x)[NV], double* scra
   __syncwarp();
 }
 template <int NW, int NV>
-LMPC_DEV void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV], double* scratch) {
+LMPC_RED void group_reduce(LaneVar<double, 32 * NW> (&x)[NV], const int (&op)[NV], double* scratch) {
 #pragma unroll
   for (int q = 0; q < NV; q++) {
 #pragma unroll
