@@ -750,6 +750,10 @@ struct DevIO {
   // side stream and travel while the QP kernel runs (5.5 of the 7.9 MB a 1024-instance tick returns).
   double *h_ssx = nullptr, *h_ssj = nullptr;
   mutable bool ss_copied = false;
+  // host callers whose output buffers are one pinned, device-mapped arena laid out like the staging area: the QP kernel
+  // stores every instance's result straight into it (byte offset host - staging); no D2H copy of those arrays follows
+  long long host_mirror_off = 0;
+  bool host_mirror = false;
 };
 
 static int check_batch_args(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_batch_out* out) {
@@ -804,6 +808,21 @@ static int stage_in(lmpc_handle* h, int B, const lmpc_batch_in* in, const lmpc_b
     if (!out->cost) io.dout[6] = nullptr;
     io.ssx = (double*)h->st_out.p + nout[0] + nout[1] + nout[2] + nout[3]; io.ssj = io.ssx + nout[4];
     io.h_ssx = out->ss_x; io.h_ssj = out->ss_j;
+    // zero-copy results: one offset must map the staging X | U | dU | lambda | cost | status | iters onto the caller's
+    // buffers (true for BatchedRacingMPC.alloc_host_outputs' arena) and the memory must be pinned and device-mapped
+    {
+      const char* e = getenv("LMPC_HOST_MIRROR");
+      cudaPointerAttributes at;
+      if (!(e && atoi(e) == 0) && out->X_optm && cudaPointerGetAttributes(&at, out->X_optm) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        const long long off = (const char*)at.devicePointer - (const char*)io.dout[0];
+        auto same = [&](const void* hp, const void* dp) { return hp && dp && ((const char*)hp - (const char*)out->X_optm) == ((const char*)dp - (const char*)io.dout[0]); };
+        const bool lam_ok = (!h->P.learning) || !out->convex_combi_optm || same(out->convex_combi_optm, io.dout[3]);
+        if (same(out->U_optm, io.dout[1]) && same(out->dU_optm, io.dout[2]) && lam_ok && (!out->cost || same(out->cost, io.dout[6])) &&
+            same(out->status, io.d_status) && same(out->iters, io.d_iters)) {
+          io.host_mirror = true; io.host_mirror_off = off;
+        }
+      } else cudaGetLastError();   // a pageable pointer makes cudaPointerGetAttributes fail on some drivers: not an error here
+    }
   } else {
     for (int k = 0; k < 11; k++) io.din[k] = hin[k];
     for (int k = 0; k < 7; k++) io.dout[k] = hout[k];
@@ -832,10 +851,13 @@ static int stage_out(lmpc_handle* h, int B, const lmpc_batch_out* out, int memsp
     if (!hout[k] || !dsrc[k]) continue;
     if ((k == 3 || k == 4 || k == 5) && !learn) continue;
     if ((k == 4 || k == 5) && io.ss_copied) continue;   // already on their way (side stream)
+    if (io.host_mirror && k != 4 && k != 5) continue;    // stored by the QP kernel itself (zero-copy), complete at the synchronise below
     CK(push(hout[k], dsrc[k], sizeof(double) * io.nout[k]));
   }
-  CK(push(out->status, io.d_status, sizeof(int32_t) * (size_t)B));
-  CK(push(out->iters, io.d_iters, sizeof(int32_t) * (size_t)B));
+  if (!io.host_mirror) {
+    CK(push(out->status, io.d_status, sizeof(int32_t) * (size_t)B));
+    CK(push(out->iters, io.d_iters, sizeof(int32_t) * (size_t)B));
+  }
   if (run_b) CK(cudaMemcpyAsync(run_dst, run_src, run_b, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (io.ss_copied) CK(cudaStreamSynchronize(h->side));
@@ -917,7 +939,10 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   a.X = io.dout[0]; a.U = io.dout[1]; a.dU = io.dout[2]; a.lam = io.dout[3]; a.cost = io.dout[6];
   a.status = io.d_status; a.iters = io.d_iters; a.ss_count = *ss_count_io; a.B = B; a.skip = skip;
   a.ss_count_v = (learn && per_agent) ? (const int*)h->ag_cnt.p : nullptr;
-  a.n_mirror = 0; a.done = nullptr; a.seq = 0;
+  a.n_mirror = 0; a.done = nullptr; a.seq = 0; a.mirror_all = 0;
+  if (io.host_mirror && first && !skip && h->gat.active_set < 0) {
+    a.n_mirror = 1; a.mirror_off[0] = io.host_mirror_off; a.peer_flag[0] = nullptr; a.mirror_all = 1;
+  }
   if (h->gat.active_set >= 0) {   // lmpc_solve_gather_batch: X, U, dU, cost, status live in this rank's block of the gather buffer
     const lmpc_handle::Gather& G = h->gat;
     for (int p = 0; p < G.world; p++) {

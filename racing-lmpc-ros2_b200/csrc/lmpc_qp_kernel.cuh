@@ -22,8 +22,12 @@ struct LmpcQpBatch {
   int n_mirror;
   long long mirror_off[LMPC_MAX_PEERS - 1];
   unsigned long long* peer_flag[LMPC_MAX_PEERS - 1];   // address (in peer m's memory) of this rank's flag slot
-  unsigned int* done;                                  // local CTA counter (reset by the last CTA)
+  unsigned int* done;                                  // local CTA counter (reset by the last CTA); null: no completion protocol
   unsigned long long seq;
+  // mirror_all != 0: the (single) mirror target is the caller's pinned HOST arena (zero-copy stores over PCIe, lmpc_solve_batch
+  // with host buffers): lambda and the iteration count are mirrored too, so that nothing of the instance's result is left to a
+  // device-to-host copy after the kernel -- the results of instances that finish early travel while the slow ones still iterate
+  int mirror_all;
 };
 
 LMPC_DEV void lmpc_st_release_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -80,18 +84,29 @@ __global__ void __launch_bounds__(32 * NW, 7) lmpc_qp_kernel(const __grid_consta
         for (int j = 0; j < 2; j++) { const int q = base + tid + NT * j; if (q < 2 * NS) { LMPC_MIR(out.U + q, off) = vu[j]; LMPC_MIR(out.dU + q, off) = vd[j]; } }
       }
     }
+    if (a.mirror_all && out.lam) {
+      for (int base = 0; base < K; base += 4 * NT) {
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int q = base + tid + NT * j; v[j] = (q < K) ? out.lam[q] : 0.0; }
+        const long long off = a.mirror_off[0];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int q = base + tid + NT * j; if (q < K) LMPC_MIR(out.lam + q, off) = v[j]; }
+      }
+    }
     if (tid == 0) {
       const double cv = out.cost ? *out.cost : 0.0;
-      const int sv = *out.status;
+      const int sv = *out.status, iv = *out.iters;
       for (int m = 0; m < a.n_mirror; m++) {
         const long long off = a.mirror_off[m];
         if (out.cost) LMPC_MIR(out.cost, off) = cv;
         *reinterpret_cast<int*>(reinterpret_cast<char*>(out.status) + off) = sv;
+        if (a.mirror_all) *reinterpret_cast<int*>(reinterpret_cast<char*>(out.iters) + off) = iv;
       }
     }
 #undef LMPC_MIR
     if (NW == 1) __syncwarp(); else __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && a.done) {
       __threadfence_system();                                   // this group's peer stores before the count
       const unsigned int prev = atomicAdd(a.done, 1u);
       if (prev == (unsigned int)a.B - 1u) {                     // last CTA of the launch: everyone's stores are ordered before this

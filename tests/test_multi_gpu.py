@@ -95,3 +95,41 @@ def test_fused_peer_exchange_equals_nccl_all_gather():
     for key in ("X_optm", "status"):
         assert np.array_equal(got[0]["host"][key], got[0]["peer"][2][0][key]), key
         assert np.array_equal(got[1]["host"][key], got[0]["host"][key]), key
+
+
+@pytest.mark.gpu
+def test_solve_gather_on_one_gpu_equals_plain_solve(pkg):
+    """world = 1: lmpc_solve_gather_batch routes the trajectory outputs into the (one-rank) gathered set and mirrors to
+    nobody; device and host forms must reproduce lmpc_solve_batch bit for bit, and the set layout must unpack."""
+    import torch
+    from racing_lmpc_ros2_b200 import distributed as D
+    from racing_lmpc_ros2_b200.solver import BatchedRacingMPC
+    veh = pkg.configs.BARC_VEHICLE; cfg = pkg.configs.barc_lmpc_config(20)
+    track = pkg.workload.load_track("barc_center"); laps = pkg.workload.load_laps()
+    Bn, N = 48, cfg["N"]
+    mpc = BatchedRacingMPC(veh, cfg, max_batch=Bn)
+    for l in laps:
+        mpc.add_lap(l["x"], l["u"], l["k"], l["t"], track["length"])
+    data = pkg.workload.make_batch(veh, cfg, Bn, 0x1C, track, laps, mode="barc")
+    plain = mpc.solve(data)
+    dev = torch.device("cuda", 0)
+    sh = D.ShardedSolver(mpc, None, Bn, dev, backend="peer", sets=2)
+    d_in = {k: torch.from_numpy(v).to(dev) for k, v in data.items()}
+    for k in range(3):
+        sh.step(d_in, k); sh.wait(k)
+    torch.cuda.synchronize()
+    assert mpc.gather_error() == 0
+    g = D.unpack_flat_slab(sh.gathered(2).cpu().numpy(), 1, Bn, N, per=sh.per)
+    for key in ("X_optm", "U_optm", "dU_optm", "cost", "status"):
+        assert np.array_equal(g[key], plain[key]), key
+        assert np.array_equal(sh.local(2)[key].cpu().numpy(), plain[key]), key
+    assert np.array_equal(sh.local(2)["iters"].cpu().numpy(), plain["iters"])
+    # host form: own shard back through the caller's buffers, or the whole set through gathered_host
+    h_in = mpc.alloc_host_inputs(data, pinned=True); h_out = mpc.alloc_host_outputs(Bn, pinned=True)
+    mpc.solve_gather(h_in, h_out, 0, wait=True)
+    for key in ("X_optm", "U_optm", "dU_optm", "cost", "status", "iters", "convex_combi_optm", "ss_x", "ss_j"):
+        assert np.array_equal(h_out[key], plain[key]), key
+    g_host = np.zeros(sh.per)
+    mpc.solve_gather(h_in, h_out, 1, wait=True, gathered_host=g_host)
+    gh = D.unpack_flat_slab(g_host, 1, Bn, N, per=sh.per)
+    assert np.array_equal(gh["X_optm"], plain["X_optm"]) and np.array_equal(gh["status"], plain["status"])
