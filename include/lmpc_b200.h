@@ -35,7 +35,10 @@
  *   - every array is fp64, instance-major: element [b] of a batch is the reference's dense
  *     column-major casadi::DM for that tick (X_ref[b] = 6 x N column-major = N rows of 6).
  *   - `memspace` says where the caller's buffers live.  LMPC_MEM_HOST buffers are staged through
- *     pinned memory owned by the handle (H2D, kernels, D2H, then a stream synchronise);
+ *     device memory owned by the handle (H2D, kernels, D2H, then a stream synchronise).  Pinned host buffers make the
+ *     copies asynchronous; when the outputs of lmpc_solve_batch are one pinned arena in the order of lmpc_batch_out
+ *     (X_optm, U_optm, dU_optm, convex_combi_optm, ss_x, ss_j, cost, status, iters back to back) the QP kernel stores
+ *     the results straight into it (zero-copy) and no D2H copy of them follows;
  *     LMPC_MEM_DEVICE buffers are used in place, work is enqueued on the handle's stream and the
  *     call returns without synchronising.
  *   - a handle is thread-compatible, not thread-safe (same contract as RacingMPC::solve, which
