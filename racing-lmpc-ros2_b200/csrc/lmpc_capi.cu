@@ -455,6 +455,16 @@ extern "C" int lmpc_recorder_step(lmpc_handle* h, const double* x, const double*
 }
 
 // ------------------------------------------------------------------------------------------ error-dynamics regression
+// one scan for regressions that share their input states (LMPC_REG_SHARED=0: one scan per regression, as round 1), else the
+// tiled kernel of the plan's size class
+static void launch_regress(lmpc_handle* h, const LmpcRegPlan& plan, const LmpcRegItems& ri, int blocks) {
+  const char* e = getenv("LMPC_REG_SHARED");
+  const int nx = (e && atoi(e) == 0) ? -1 : lmpc_reg_shared_nx(plan);
+  if (nx >= 1 && nx <= 4) lmpc_regress_shared_kernel<<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri, nx);
+  else if (lmpc_reg_size_class(plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+  else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+}
+
 static int make_reg_plan(lmpc_handle* h, const lmpc_reg_spec* sp, LmpcRegPlan* plan) {
   if (lmpc_make_reg_plan(sp, plan)) return LMPC_OK;
   h->err = "regression spec rejected (1..6 regressions, indices in range, dist_max > 0, ridge > 0, sign = +-1)";
@@ -549,8 +559,7 @@ extern "C" int lmpc_safe_set_regress_batch(lmpc_handle* h, int n, const lmpc_reg
     LmpcRegItems ri{};
     ri.n = n; ri.tick = 0; ri.xq = dxq; ri.uq = duq; ri.A = dA; ri.Bm = dB; ri.C = dC; ri.npts = dn;
     const int blocks = (n + LMPC_REG_WARPS - 1) / LMPC_REG_WARPS;
-    if (lmpc_reg_size_class(plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
-    else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+    launch_regress(h, plan, ri, blocks);
     h->launches++;
     CK(cudaGetLastError());
   } else if (dn) CK(cudaMemsetAsync(dn, 0, sizeof(int32_t) * (size_t)plan.n_out * nz, h->stream));
@@ -923,8 +932,7 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
       ri.n = B * (int)NS; ri.tick = 1; ri.B = B; ri.N = (int)N; ri.x_ic = io.din[0]; ri.X_ref = X_lin; ri.U_ref = U_lin;
       ri.total_length = io.din[9]; ri.ABg = abg; ri.skip = skip;
       const int blocks = (ri.n + LMPC_REG_WARPS - 1) / LMPC_REG_WARPS;
-      if (lmpc_reg_size_class(h->reg_plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(h->reg_plan, h->reg_view, ri);
-      else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(h->reg_plan, h->reg_view, ri);
+      launch_regress(h, h->reg_plan, ri, blocks);
       h->launches++;
       CK(cudaGetLastError());
     }

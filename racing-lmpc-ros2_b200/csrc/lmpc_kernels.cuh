@@ -296,3 +296,139 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel
     }
   }
 }
+
+
+// KR, one pass for regressions that share their input states (the LMPC choice: v_x, v_y, omega for all three outputs, one
+// control each): the tile holds the shared state columns, both control columns and the error column of every output; the
+// squared distance over the shared states is formed ONCE per (query, sample) -- and rejects most samples before any
+// per-regression work -- then each regression adds its own control part, weights and accumulates.  One scan of the window
+// instead of n_out.  Eligibility (host, lmpc_reg_shared_nx): size class 5, at most 3 regressions, identical state lists.
+#define LMPC_REG_SHARED_MAX_OUT 3
+LMPC_HD int lmpc_reg_shared_nx(const LmpcRegPlan& plan) {   // number of shared state inputs, or -1 when not eligible
+  if (plan.n_out < 1 || plan.n_out > LMPC_REG_SHARED_MAX_OUT || lmpc_reg_size_class(plan) != 5) return -1;
+  int nx = 0;
+  while (nx < plan.row[0].D && plan.row[0].sel[nx] < 6) nx++;
+  for (int r = 1; r < plan.n_out; r++) {
+    int k = 0;
+    while (k < plan.row[r].D && plan.row[r].sel[k] < 6) k++;
+    if (k != nx) return -1;
+    for (int a = 0; a < nx; a++) if (plan.row[r].sel[a] != plan.row[0].sel[a]) return -1;
+  }
+  return nx;
+}
+
+__global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_shared_kernel(LmpcRegPlan plan, LmpcRegView v, LmpcRegItems it, int nx) {
+  constexpr int D = 5, NQ = D * (D + 1) / 2, NV = NQ + D + 1, RO = LMPC_REG_SHARED_MAX_OUT;
+  __shared__ __align__(16) double tX[4 * LMPC_REG_TILE];    // shared state inputs (nx <= 4)
+  __shared__ __align__(16) double tU[2 * LMPC_REG_TILE];    // both controls
+  __shared__ __align__(16) double tE[RO * LMPC_REG_TILE];   // error of every regression's output
+  __shared__ int win[2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int item = blockIdx.x * LMPC_REG_WARPS + w;
+  bool live = item < it.n;
+  double zq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double *A = nullptr, *Bm = nullptr, *C = nullptr; int* npts = nullptr;
+  if (live) {
+    if (it.tick) {
+      const int NS = it.N - 1, b = item / NS, i = item - b * NS;
+      if (it.skip && it.skip[b]) live = false;
+      const double* xr = it.X_ref + (6 * (size_t)it.N) * b + 6 * i;
+      for (int c = 0; c < 6; c++) zq[c] = xr[c];
+      zq[0] = lmpc_align_abscissa(zq[0], it.x_ic[6 * (size_t)b], it.total_length[b]);
+      zq[6] = it.U_ref[(2 * (size_t)NS) * b + 2 * i]; zq[7] = it.U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
+      A = it.ABg + (54 * (size_t)NS) * b + 54 * i; Bm = A + 36; C = A + 48;
+    } else {
+      for (int c = 0; c < 6; c++) zq[c] = it.xq[6 * (size_t)item + c];
+      zq[6] = it.uq[2 * (size_t)item]; zq[7] = it.uq[2 * (size_t)item + 1];
+      A = it.A + 36 * (size_t)item; Bm = it.Bm + 12 * (size_t)item; C = it.C + 6 * (size_t)item;
+      npts = it.npts ? it.npts + (size_t)plan.n_out * item : nullptr;
+    }
+  }
+  const double h = plan.h, ih = 1.0 / h, kc = 0.75 / h, h2 = h * h * (1.0 + 1e-12);
+  // window of the sorted samples (valid for every regression only when the sort component is a shared state)
+  bool key_shared = false;
+  for (int a = 0; a < nx; a++) key_shared |= (plan.row[0].sel[a] == v.sort_dim);
+  if (threadIdx.x == 0) { win[0] = key_shared ? v.M : 0; win[1] = key_shared ? 0 : v.M; }
+  __syncthreads();
+  if (key_shared && live && lane == 0) {
+    const double* key = v.Z + (size_t)v.sort_dim * v.ld;
+    const double ql = zq[v.sort_dim] - h, qh = zq[v.sort_dim] + h;
+    int a = 0, b = v.M;
+    while (a < b) { const int m = (a + b) >> 1; if (key[m] < ql) a = m + 1; else b = m; }
+    const int lo = a;
+    b = v.M;
+    while (a < b) { const int m = (a + b) >> 1; if (key[m] <= qh) a = m + 1; else b = m; }
+    atomicMin(&win[0], lo); atomicMax(&win[1], a);
+  }
+  __syncthreads();
+  double qx[4], Q[RO][NQ], bv[RO][D], cnt[RO];
+#pragma unroll
+  for (int a = 0; a < 4; a++) qx[a] = (a < nx) ? zq[plan.row[0].sel[a]] : 0.0;
+#pragma unroll
+  for (int r = 0; r < RO; r++) {
+    cnt[r] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NQ; k++) Q[r][k] = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) bv[r][a] = 0.0;
+  }
+  const int t_begin = win[0] & ~31, t_end = win[1];
+  for (int t0 = t_begin; t0 < t_end; t0 += LMPC_REG_TILE) {
+    const int count = min(LMPC_REG_TILE, t_end - t0);
+    __syncthreads();
+    for (int a = 0; a < nx; a++)
+      for (int e = threadIdx.x; e < count; e += blockDim.x) tX[a * LMPC_REG_TILE + e] = v.Z[(size_t)plan.row[0].sel[a] * v.ld + t0 + e];
+    for (int e = threadIdx.x; e < count; e += blockDim.x) { tU[e] = v.Z[(size_t)6 * v.ld + t0 + e]; tU[LMPC_REG_TILE + e] = v.Z[(size_t)7 * v.ld + t0 + e]; }
+    for (int r = 0; r < plan.n_out; r++)
+      for (int e = threadIdx.x; e < count; e += blockDim.x) tE[r * LMPC_REG_TILE + e] = v.E[(size_t)plan.row[r].out * v.ld + t0 + e];
+    __syncthreads();
+    if (!live) continue;
+    for (int p = lane; p < count; p += 32) {
+      double xs[4], dx2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) { xs[a] = (a < nx) ? tX[a * LMPC_REG_TILE + p] : 0.0; const double t = xs[a] - qx[a]; dx2 += (a < nx) ? t * t : 0.0; }
+      if (!(dx2 < h2)) continue;
+      const double u0 = tU[p], u1 = tU[LMPC_REG_TILE + p];
+#pragma unroll
+      for (int r = 0; r < RO; r++) {
+        if (r >= plan.n_out) break;
+        const LmpcRegRow& row = plan.row[r];
+        double m[D], d2 = dx2;
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+          const int sl = row.sel[a];
+          m[a] = (a < nx) ? xs[a < 4 ? a : 0] : (sl == 6 ? u0 : (sl == 7 ? u1 : (sl == 8 ? 1.0 : 0.0)));
+          if (a >= nx && (sl == 6 || sl == 7)) { const double t = m[a] - zq[sl]; d2 += t * t; }
+        }
+        if (!(d2 < h2)) continue;
+        const double dd = sqrt(d2);
+        if (dd < h) {
+          const double t = dd * ih, u1_ = 1.0 - t * t;
+          const double wgt = kc * u1_ * u1_;
+          const double y = tE[r * LMPC_REG_TILE + p];
+#pragma unroll
+          for (int a = 0, k = 0; a < D; a++) {
+            const double wa = wgt * m[a];
+            bv[r][a] += wa * y;
+#pragma unroll
+            for (int b = a; b < D; b++, k++) Q[r][k] += wa * m[b];
+          }
+          cnt[r] += 1.0;
+        }
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < RO; r++) {
+      if (r >= plan.n_out) break;
+      LaneVar<double> acc[NV];
+#pragma unroll
+      for (int k = 0; k < NQ; k++) acc[k].v = Q[r][k];
+#pragma unroll
+      for (int a = 0; a < D; a++) acc[NQ + a].v = bv[r][a];
+      acc[NQ + D].v = cnt[r];
+      lmpc_reg_finish<5>(plan, plan.row[r], acc, A, Bm, C, npts ? npts + r : nullptr);
+    }
+  }
+}

@@ -367,3 +367,20 @@ def test_emulated_qp_kernel_shipped_horizon_and_hard_boundary(emu, pkg, name, N,
             m = cfg["margin"] + veh["chassis_b"] / 2
             ey = k["X"][1:, 1]
             assert (ey <= inp["bound_left"][1:] - m + 1e-9).all() and (ey >= inp["bound_right"][1:] + m - 1e-9).all()
+
+
+def test_emulated_qp_kernel_abandons_a_diverging_polish(emu, pkg):
+    """One instance per ~1000 used to set the time of a one-wave batch: its first polish came apart (2 -> 4 -> 75 rows
+    changing side) and ran all six rounds before the interior point resumed (19 trips).  A polish whose active set is
+    diverging is abandoned at once (kernel and port alike): 16 trips, same certified optimum.  Instance 39 of the batch
+    rank 3 solves in bench.py (seed 0xB200 + 2 + 7919 * 3)."""
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc", tol=1e-11)
+    batch = pkg.workload.make_batch(veh, cfg, 40, 0xB200 + 2 + 7919 * 3, track, pkg.workload.load_laps(), mode=mode)
+    inp = pkg.workload.instance(batch, 39)
+    k = _emu_solve(emu, pkg, od, veh, cfg, inp)
+    d = od.step(inp, impl="dense")
+    p = od.step(inp, impl="port")
+    assert k["status"] == 0 and d["status"] == 0 and d["kkt"] < 1e-9 and p["status"] == 0
+    assert k["iters"] <= 17, k["iters"]
+    assert abs(p["iters"] - k["iters"]) <= 2          # the port carries the same rule
+    assert max(relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"])) < 1e-8
