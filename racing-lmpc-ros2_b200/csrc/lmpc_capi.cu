@@ -455,14 +455,11 @@ extern "C" int lmpc_recorder_step(lmpc_handle* h, const double* x, const double*
 }
 
 // ------------------------------------------------------------------------------------------ error-dynamics regression
-// one scan for regressions that share their input states (LMPC_REG_SHARED=0: one scan per regression, as round 1), else the
-// tiled kernel of the plan's size class
 static void launch_regress(lmpc_handle* h, const LmpcRegPlan& plan, const LmpcRegItems& ri, int blocks) {
-  const char* e = getenv("LMPC_REG_SHARED");
-  const int nx = (e && atoi(e) == 0) ? -1 : lmpc_reg_shared_nx(plan);
-  if (nx >= 1 && nx <= 4) lmpc_regress_shared_kernel<<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri, nx);
-  else if (lmpc_reg_size_class(plan) == 5) lmpc_regress_tiled_kernel<5><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
-  else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+  // two resident blocks per SM (120 registers, no spills) measured level with three (80 registers, spills): profiles/README.md
+  if (lmpc_reg_size_class(plan) == 5) {
+    lmpc_regress_tiled_kernel<5, 2><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
+  } else lmpc_regress_tiled_kernel<LMPC_REG_D><<<blocks, 32 * LMPC_REG_WARPS, 0, h->stream>>>(plan, h->reg_view, ri);
 }
 
 static int make_reg_plan(lmpc_handle* h, const lmpc_reg_spec* sp, LmpcRegPlan* plan) {

@@ -211,22 +211,29 @@ __global__ void lmpc_reg_prepare_kernel(LmpcModel M, int n, int ld, const double
   for (int c = 0; c < 6; c++) E[(size_t)c * ld + p] = Xn[(size_t)c * ld + p] - xn[c];
 }
 
-// KR: every query scans every stored sample.  A block of LMPC_REG_WARPS warps (one query each) streams the samples through a
-// shared-memory tile that holds, by column, only the regression's own inputs and its output's error: loaded once per
-// block, read conflict-free by the scan (lane = sample), 8x less L2 traffic than every warp pulling the samples itself.
+// KR: every query scans the stored samples (its window of them when they are sorted).  A block of LMPC_REG_WARPS warps (one
+// query each) streams the samples through shared-memory tiles that hold, by column, only the regression's own inputs and
+// its output's error: loaded once per block (8x less L2 traffic than every warp pulling the samples itself), by cp.async
+// into the other of two buffers while the current tile is scanned, read conflict-free by the scan (lane = sample).
 // DD = size class of the plan (5: at most four regressors + 1 -- 20 accumulators per lane; 9: the general case, 54).
-#define LMPC_REG_TILE 256
+#define LMPC_REG_TILE_OF(DD) ((DD) == 5 ? 512 : 256)
 #define LMPC_REG_WARPS 8
+__device__ __forceinline__ void lmpc_cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void lmpc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void lmpc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 struct LmpcRegItems {          // where the items of a launch live
   int n;                       // items
   int tick;                    // 1: item = (instance b, stage i) of a tick, query at the aligned linearisation point, [A|B|g] in ABg
   const double *xq, *uq; double *A, *Bm, *C; int* npts;                                                  // generic items
   int B, N; const double *x_ic, *X_ref, *U_ref, *total_length; double* ABg; const int* skip;              // tick items
 };
-template <int DD>
-__global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel(LmpcRegPlan plan, LmpcRegView v, LmpcRegItems it) {
-  __shared__ __align__(16) double tZ[(DD - 1) * LMPC_REG_TILE];
-  __shared__ __align__(16) double tE[LMPC_REG_TILE];
+template <int DD, int MINB = 1>
+__global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_kernel(LmpcRegPlan plan, LmpcRegView v, LmpcRegItems it) {
+  constexpr int TILE = LMPC_REG_TILE_OF(DD);
+  __shared__ __align__(16) double tZ[2][(DD - 1) * TILE];
+  __shared__ __align__(16) double tE[2][TILE];
   constexpr int D = DD, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int item = blockIdx.x * LMPC_REG_WARPS + w;
@@ -276,14 +283,38 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel
     for (int k = 0; k < NQ; k++) Q[k] = 0.0;
     // a regression that does not use the sort component must see every sample
     const int t_begin = (uses_key && v.sort_dim >= 0) ? (win[0] & ~31) : 0, t_end = (uses_key && v.sort_dim >= 0) ? win[1] : v.M;
-    for (int t0 = t_begin; t0 < t_end; t0 += LMPC_REG_TILE) {
-      const int count = min(LMPC_REG_TILE, t_end - t0);
-      __syncthreads();   // the previous tile has been scanned by every warp
-      for (int a = 0; a < row.D - 1; a++)
-        for (int e = threadIdx.x; e < count; e += blockDim.x) tZ[a * LMPC_REG_TILE + e] = v.Z[(size_t)row.sel[a] * v.ld + t0 + e];
-      for (int e = threadIdx.x; e < count; e += blockDim.x) tE[e] = v.E[(size_t)row.out * v.ld + t0 + e];
+    // tile k + 1 is in flight (cp.async into the other buffer) while tile k is scanned; one barrier per tile: past it every
+    // warp has finished tile k - 1, whose buffer the next copies overwrite
+    auto issue = [&](int buf, int t0) {
+      const int count = min(TILE, t_end - t0);
+      for (int a = 0; a < row.D - 1; a++) {
+        const double* src = v.Z + (size_t)row.sel[a] * v.ld + t0;
+        for (int e = threadIdx.x; e < count; e += 32 * LMPC_REG_WARPS) lmpc_cp_async8(&tZ[buf][a * TILE + e], src + e);
+      }
+      const double* src = v.E + (size_t)row.out * v.ld + t0;
+      for (int e = threadIdx.x; e < count; e += 32 * LMPC_REG_WARPS) lmpc_cp_async8(&tE[buf][e], src + e);
+      lmpc_cp_async_commit();
+    };
+    __syncthreads();   // the previous regression's last tile has been scanned by every warp
+    if (t_begin < t_end) issue(0, t_begin);
+    int buf = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += TILE, buf ^= 1) {
+      const int count = min(TILE, t_end - t0);
+      lmpc_cp_async_wait_all();
       __syncthreads();
-      if (live) lmpc_reg_scan_lane<DD, true>(row, h, ih, kc, q, tZ, tE, LMPC_REG_TILE, count, lane, Q, bv, cnt);
+      if (t0 + TILE < t_end) issue(buf ^ 1, t0 + TILE);
+      if (live) {
+        const double *cZ = tZ[buf], *cE = tE[buf];
+        if (DD == 5) {   // exact-size scans (warp-uniform switch): no index lists in the loop
+          switch (row.D) {
+            case 5: lmpc_reg_scan_tile<5, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+            case 4: lmpc_reg_scan_tile<4, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+            case 3: lmpc_reg_scan_tile<3, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+            case 2: lmpc_reg_scan_tile<2, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+            default: lmpc_reg_scan_tile<1, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+          }
+        } else lmpc_reg_scan_lane<DD, true>(row, h, ih, kc, q, cZ, cE, TILE, count, lane, Q, bv, cnt);
+      }
     }
     if (live) {   // warp-uniform: a warp is one item
       LaneVar<double> acc[NV];
@@ -293,142 +324,6 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_tiled_kernel
       for (int a = 0; a < D; a++) acc[NQ + a].v = bv[a];
       acc[NQ + D].v = cnt;
       lmpc_reg_finish<DD>(plan, row, acc, A, Bm, C, npts ? npts + r : nullptr);
-    }
-  }
-}
-
-
-// KR, one pass for regressions that share their input states (the LMPC choice: v_x, v_y, omega for all three outputs, one
-// control each): the tile holds the shared state columns, both control columns and the error column of every output; the
-// squared distance over the shared states is formed ONCE per (query, sample) -- and rejects most samples before any
-// per-regression work -- then each regression adds its own control part, weights and accumulates.  One scan of the window
-// instead of n_out.  Eligibility (host, lmpc_reg_shared_nx): size class 5, at most 3 regressions, identical state lists.
-#define LMPC_REG_SHARED_MAX_OUT 3
-LMPC_HD int lmpc_reg_shared_nx(const LmpcRegPlan& plan) {   // number of shared state inputs, or -1 when not eligible
-  if (plan.n_out < 1 || plan.n_out > LMPC_REG_SHARED_MAX_OUT || lmpc_reg_size_class(plan) != 5) return -1;
-  int nx = 0;
-  while (nx < plan.row[0].D && plan.row[0].sel[nx] < 6) nx++;
-  for (int r = 1; r < plan.n_out; r++) {
-    int k = 0;
-    while (k < plan.row[r].D && plan.row[r].sel[k] < 6) k++;
-    if (k != nx) return -1;
-    for (int a = 0; a < nx; a++) if (plan.row[r].sel[a] != plan.row[0].sel[a]) return -1;
-  }
-  return nx;
-}
-
-__global__ void __launch_bounds__(32 * LMPC_REG_WARPS) lmpc_regress_shared_kernel(LmpcRegPlan plan, LmpcRegView v, LmpcRegItems it, int nx) {
-  constexpr int D = 5, NQ = D * (D + 1) / 2, NV = NQ + D + 1, RO = LMPC_REG_SHARED_MAX_OUT;
-  __shared__ __align__(16) double tX[4 * LMPC_REG_TILE];    // shared state inputs (nx <= 4)
-  __shared__ __align__(16) double tU[2 * LMPC_REG_TILE];    // both controls
-  __shared__ __align__(16) double tE[RO * LMPC_REG_TILE];   // error of every regression's output
-  __shared__ int win[2];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int item = blockIdx.x * LMPC_REG_WARPS + w;
-  bool live = item < it.n;
-  double zq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  double *A = nullptr, *Bm = nullptr, *C = nullptr; int* npts = nullptr;
-  if (live) {
-    if (it.tick) {
-      const int NS = it.N - 1, b = item / NS, i = item - b * NS;
-      if (it.skip && it.skip[b]) live = false;
-      const double* xr = it.X_ref + (6 * (size_t)it.N) * b + 6 * i;
-      for (int c = 0; c < 6; c++) zq[c] = xr[c];
-      zq[0] = lmpc_align_abscissa(zq[0], it.x_ic[6 * (size_t)b], it.total_length[b]);
-      zq[6] = it.U_ref[(2 * (size_t)NS) * b + 2 * i]; zq[7] = it.U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
-      A = it.ABg + (54 * (size_t)NS) * b + 54 * i; Bm = A + 36; C = A + 48;
-    } else {
-      for (int c = 0; c < 6; c++) zq[c] = it.xq[6 * (size_t)item + c];
-      zq[6] = it.uq[2 * (size_t)item]; zq[7] = it.uq[2 * (size_t)item + 1];
-      A = it.A + 36 * (size_t)item; Bm = it.Bm + 12 * (size_t)item; C = it.C + 6 * (size_t)item;
-      npts = it.npts ? it.npts + (size_t)plan.n_out * item : nullptr;
-    }
-  }
-  const double h = plan.h, ih = 1.0 / h, kc = 0.75 / h, h2 = h * h * (1.0 + 1e-12);
-  // window of the sorted samples (valid for every regression only when the sort component is a shared state)
-  bool key_shared = false;
-  for (int a = 0; a < nx; a++) key_shared |= (plan.row[0].sel[a] == v.sort_dim);
-  if (threadIdx.x == 0) { win[0] = key_shared ? v.M : 0; win[1] = key_shared ? 0 : v.M; }
-  __syncthreads();
-  if (key_shared && live && lane == 0) {
-    const double* key = v.Z + (size_t)v.sort_dim * v.ld;
-    const double ql = zq[v.sort_dim] - h, qh = zq[v.sort_dim] + h;
-    int a = 0, b = v.M;
-    while (a < b) { const int m = (a + b) >> 1; if (key[m] < ql) a = m + 1; else b = m; }
-    const int lo = a;
-    b = v.M;
-    while (a < b) { const int m = (a + b) >> 1; if (key[m] <= qh) a = m + 1; else b = m; }
-    atomicMin(&win[0], lo); atomicMax(&win[1], a);
-  }
-  __syncthreads();
-  double qx[4], Q[RO][NQ], bv[RO][D], cnt[RO];
-#pragma unroll
-  for (int a = 0; a < 4; a++) qx[a] = (a < nx) ? zq[plan.row[0].sel[a]] : 0.0;
-#pragma unroll
-  for (int r = 0; r < RO; r++) {
-    cnt[r] = 0.0;
-#pragma unroll
-    for (int k = 0; k < NQ; k++) Q[r][k] = 0.0;
-#pragma unroll
-    for (int a = 0; a < D; a++) bv[r][a] = 0.0;
-  }
-  const int t_begin = win[0] & ~31, t_end = win[1];
-  for (int t0 = t_begin; t0 < t_end; t0 += LMPC_REG_TILE) {
-    const int count = min(LMPC_REG_TILE, t_end - t0);
-    __syncthreads();
-    for (int a = 0; a < nx; a++)
-      for (int e = threadIdx.x; e < count; e += blockDim.x) tX[a * LMPC_REG_TILE + e] = v.Z[(size_t)plan.row[0].sel[a] * v.ld + t0 + e];
-    for (int e = threadIdx.x; e < count; e += blockDim.x) { tU[e] = v.Z[(size_t)6 * v.ld + t0 + e]; tU[LMPC_REG_TILE + e] = v.Z[(size_t)7 * v.ld + t0 + e]; }
-    for (int r = 0; r < plan.n_out; r++)
-      for (int e = threadIdx.x; e < count; e += blockDim.x) tE[r * LMPC_REG_TILE + e] = v.E[(size_t)plan.row[r].out * v.ld + t0 + e];
-    __syncthreads();
-    if (!live) continue;
-    for (int p = lane; p < count; p += 32) {
-      double xs[4], dx2 = 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; a++) { xs[a] = (a < nx) ? tX[a * LMPC_REG_TILE + p] : 0.0; const double t = xs[a] - qx[a]; dx2 += (a < nx) ? t * t : 0.0; }
-      if (!(dx2 < h2)) continue;
-      const double u0 = tU[p], u1 = tU[LMPC_REG_TILE + p];
-#pragma unroll
-      for (int r = 0; r < RO; r++) {
-        if (r >= plan.n_out) break;
-        const LmpcRegRow& row = plan.row[r];
-        double m[D], d2 = dx2;
-#pragma unroll
-        for (int a = 0; a < D; a++) {
-          const int sl = row.sel[a];
-          m[a] = (a < nx) ? xs[a < 4 ? a : 0] : (sl == 6 ? u0 : (sl == 7 ? u1 : (sl == 8 ? 1.0 : 0.0)));
-          if (a >= nx && (sl == 6 || sl == 7)) { const double t = m[a] - zq[sl]; d2 += t * t; }
-        }
-        if (!(d2 < h2)) continue;
-        const double dd = sqrt(d2);
-        if (dd < h) {
-          const double t = dd * ih, u1_ = 1.0 - t * t;
-          const double wgt = kc * u1_ * u1_;
-          const double y = tE[r * LMPC_REG_TILE + p];
-#pragma unroll
-          for (int a = 0, k = 0; a < D; a++) {
-            const double wa = wgt * m[a];
-            bv[r][a] += wa * y;
-#pragma unroll
-            for (int b = a; b < D; b++, k++) Q[r][k] += wa * m[b];
-          }
-          cnt[r] += 1.0;
-        }
-      }
-    }
-  }
-  if (live) {
-#pragma unroll
-    for (int r = 0; r < RO; r++) {
-      if (r >= plan.n_out) break;
-      LaneVar<double> acc[NV];
-#pragma unroll
-      for (int k = 0; k < NQ; k++) acc[k].v = Q[r][k];
-#pragma unroll
-      for (int a = 0; a < D; a++) acc[NQ + a].v = bv[r][a];
-      acc[NQ + D].v = cnt[r];
-      lmpc_reg_finish<5>(plan, plan.row[r], acc, A, Bm, C, npts ? npts + r : nullptr);
     }
   }
 }

@@ -80,7 +80,8 @@ template <int DD, bool GATHERED>
 LMPC_DEV void lmpc_reg_scan_lane(const LmpcRegRow& row, double h, double ih, double kc, const double* q, const double* Z,
                                  const double* E, int ld, int count, int lane, double* Q, double* bv, double& cnt) {
   constexpr int D = DD;
-  const double h2 = h * h * (1.0 + 1e-12);   // cheap rejection on the squared distance; the exact test d < h follows
+  // d < h and (d / h)^2 from the squared distance: no square root in the scan (the weight is the same polynomial in d^2)
+  const double h2 = h * h, ih2 = ih * ih;
   for (int p = lane; p < count; p += 32) {
     double m[D], d2 = 0.0;
 #pragma unroll
@@ -89,10 +90,8 @@ LMPC_DEV void lmpc_reg_scan_lane(const LmpcRegRow& row, double h, double ih, dou
       m[a] = (s < 8) ? Z[(size_t)(GATHERED ? a : s) * ld + p] : (s == 8 ? 1.0 : 0.0);
       if (s < 8) { const double t = m[a] - q[a]; d2 += t * t; }
     }
-    if (!(d2 < h2)) continue;
-    const double d = sqrt(d2);
-    if (d < h) {
-      const double t = d * ih, u1 = 1.0 - t * t;
+    if (d2 < h2) {
+      const double u1 = 1.0 - d2 * ih2;
       const double w = kc * u1 * u1;
       const double y = E[(size_t)(GATHERED ? 0 : row.out) * ld + p];
 #pragma unroll
@@ -101,6 +100,40 @@ LMPC_DEV void lmpc_reg_scan_lane(const LmpcRegRow& row, double h, double ih, dou
         bv[a] += wa * y;
 #pragma unroll
         for (int b = a; b < D; b++, k++) Q[k] += wa * m[b];
+      }
+      cnt += 1.0;
+    }
+  }
+}
+
+// The same sums for a regression of exactly DE regressors (DE - 1 inputs and the constant) over a shared-memory tile that
+// holds its inputs by column (column a at tZ + a * LD) and its output's error (tE): no index lists in the loop, the
+// constant regressor folded (w * 1 = w).  Q, bv are laid out for the size class DD >= DE (the unused rows stay zero), the
+// order of the additions per lane is that of lmpc_reg_scan_lane.
+template <int DE, int DD, int LD>
+LMPC_DEV void lmpc_reg_scan_tile(double h, double ih, double kc, const double* q, const double* tZ, const double* tE, int count,
+                                 int lane, double* Q, double* bv, double& cnt) {
+  constexpr int NI = DE - 1;
+  const double h2 = h * h, ih2 = ih * ih;
+#pragma unroll 2
+  for (int p = lane; p < count; p += 32) {
+    double m[DE], d2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < NI; a++) { m[a] = tZ[a * LD + p]; const double t = m[a] - q[a]; d2 += t * t; }
+    m[NI] = 1.0;
+    if (d2 < h2) {
+      const double u1 = 1.0 - d2 * ih2;
+      const double w = kc * u1 * u1;
+      const double y = tE[p];
+#pragma unroll
+      for (int a = 0; a < DE; a++) {
+        const double wa = (a < NI) ? w * m[a] : w;
+        bv[a] += wa * y;
+#pragma unroll
+        for (int b = a; b < DE; b++) {
+          const int k = a * DD - a * (a - 1) / 2 + (b - a);
+          if (b < NI) Q[k] += wa * m[b]; else Q[k] += wa;
+        }
       }
       cnt += 1.0;
     }
