@@ -216,7 +216,7 @@ __global__ void lmpc_reg_prepare_kernel(LmpcModel M, int n, int ld, const double
 // its output's error: loaded once per block (8x less L2 traffic than every warp pulling the samples itself), by cp.async
 // into the other of two buffers while the current tile is scanned, read conflict-free by the scan (lane = sample).
 // DD = size class of the plan (5: at most four regressors + 1 -- 20 accumulators per lane; 9: the general case, 54).
-#define LMPC_REG_TILE_OF(DD) ((DD) == 5 ? 512 : 256)
+#define LMPC_REG_TILE_OF(DD) ((DD) == 5 ? 480 : 256)   // two buffers of 4 + 2 columns stay inside the 48 KB of static shared memory
 #define LMPC_REG_WARPS 8
 __device__ __forceinline__ void lmpc_cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_
   constexpr int TILE = LMPC_REG_TILE_OF(DD);
   __shared__ __align__(16) double tZ[2][(DD - 1) * TILE];
   __shared__ __align__(16) double tE[2][TILE];
+  __shared__ __align__(16) double tE2[DD == 5 ? 2 : 1][DD == 5 ? TILE : 1];   // the paired regression's output (size class 5 only)
   constexpr int D = DD, NQ = D * (D + 1) / 2, NV = NQ + D + 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int item = blockIdx.x * LMPC_REG_WARPS + w;
@@ -275,10 +276,13 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_
   __syncthreads();
   for (int r = 0; r < plan.n_out; r++) {
     const LmpcRegRow& row = plan.row[r];
-    double q[D], Q[NQ], bv[D], cnt = 0.0;
+    // a regression with the input lists of an earlier one was scanned with it (same regressors, same weights, same M'KM)
+    const int fo = (DD == 5) ? row.follower : -1;
+    if (DD == 5 && row.lead != r) continue;
+    double q[D], Q[NQ], bv[D], bv2[DD == 5 ? D : 1], cnt = 0.0;
     bool uses_key = false;
 #pragma unroll
-    for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; uses_key |= (row.sel[a] == v.sort_dim); }
+    for (int a = 0; a < D; a++) { q[a] = (row.sel[a] < 8) ? zq[row.sel[a]] : 0.0; bv[a] = 0.0; if (DD == 5) bv2[a] = 0.0; uses_key |= (row.sel[a] == v.sort_dim); }
 #pragma unroll
     for (int k = 0; k < NQ; k++) Q[k] = 0.0;
     // a regression that does not use the sort component must see every sample
@@ -293,6 +297,10 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_
       }
       const double* src = v.E + (size_t)row.out * v.ld + t0;
       for (int e = threadIdx.x; e < count; e += 32 * LMPC_REG_WARPS) lmpc_cp_async8(&tE[buf][e], src + e);
+      if (DD == 5 && fo >= 0) {
+        const double* src2 = v.E + (size_t)plan.row[fo].out * v.ld + t0;
+        for (int e = threadIdx.x; e < count; e += 32 * LMPC_REG_WARPS) lmpc_cp_async8(&tE2[buf][e], src2 + e);
+      }
       lmpc_cp_async_commit();
     };
     __syncthreads();   // the previous regression's last tile has been scanned by every warp
@@ -305,14 +313,19 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_
       if (t0 + TILE < t_end) issue(buf ^ 1, t0 + TILE);
       if (live) {
         const double *cZ = tZ[buf], *cE = tE[buf];
-        if (DD == 5) {   // exact-size scans (warp-uniform switch): no index lists in the loop
+        if constexpr (DD == 5) {   // exact-size scans (warp-uniform switch): no index lists in the loop
+          const double* cE2 = tE2[buf];
+#define LMPC_REG_SCAN_(DE_)                                                                                              \
+  if (fo >= 0) lmpc_reg_scan_tile<DE_, DD, TILE, true>(h, ih, kc, q, cZ, cE, cE2, count, lane, Q, bv, bv2, cnt);         \
+  else lmpc_reg_scan_tile<DE_, DD, TILE, false>(h, ih, kc, q, cZ, cE, cE2, count, lane, Q, bv, bv2, cnt);
           switch (row.D) {
-            case 5: lmpc_reg_scan_tile<5, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
-            case 4: lmpc_reg_scan_tile<4, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
-            case 3: lmpc_reg_scan_tile<3, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
-            case 2: lmpc_reg_scan_tile<2, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
-            default: lmpc_reg_scan_tile<1, DD, TILE>(h, ih, kc, q, cZ, cE, count, lane, Q, bv, cnt); break;
+            case 5: LMPC_REG_SCAN_(5) break;
+            case 4: LMPC_REG_SCAN_(4) break;
+            case 3: LMPC_REG_SCAN_(3) break;
+            case 2: LMPC_REG_SCAN_(2) break;
+            default: LMPC_REG_SCAN_(1) break;
           }
+#undef LMPC_REG_SCAN_
         } else lmpc_reg_scan_lane<DD, true>(row, h, ih, kc, q, cZ, cE, TILE, count, lane, Q, bv, cnt);
       }
     }
@@ -324,6 +337,14 @@ __global__ void __launch_bounds__(32 * LMPC_REG_WARPS, MINB) lmpc_regress_tiled_
       for (int a = 0; a < D; a++) acc[NQ + a].v = bv[a];
       acc[NQ + D].v = cnt;
       lmpc_reg_finish<DD>(plan, row, acc, A, Bm, C, npts ? npts + r : nullptr);
+      if (DD == 5 && fo >= 0) {   // the paired regression: the same sums, its own M'Ky
+#pragma unroll
+        for (int k = 0; k < NQ; k++) acc[k].v = Q[k];
+#pragma unroll
+        for (int a = 0; a < D; a++) acc[NQ + a].v = bv2[DD == 5 ? a : 0];
+        acc[NQ + D].v = cnt;
+        lmpc_reg_finish<DD>(plan, plan.row[fo], acc, A, Bm, C, npts ? npts + fo : nullptr);
+      }
     }
   }
 }

@@ -26,7 +26,10 @@ struct LmpcModel {
 // The transcendental part of f: independent chains (front tyre, rear tyre, controls, heading), kept apart from the algebra.
 // (Measured in round 1: giving each chain of an item to its own thread -- four threads per item, two tangent columns each,
 // bit-identical results -- made the linearisation kernel slower, 66-77 us against 51 us: the redundant algebra with its
-// fifteen IEEE divisions and a second wave of blocks cost more than the shorter chains saved.)
+// fifteen IEEE divisions and a second wave of blocks cost more than the shorter chains saved.  Round 2: half- and
+// quarter-filled warps, to give every scheduler two or four chains, were slower too -- 75 and 97 us against 46 us: a wave of
+// blocks lasts one chain whatever shares the scheduler, and the partial warps only add waves.  What shortens the chain is
+// fewer instructions in it: the reciprocals below took it from 46 to 38 us.)
 struct LmpcTrig { double th, sd, cdl, sph, cph, a_rf, a_rr, sqf, cqf, sqr, cqr; };
 LMPC_HD void lmpc_trig_front(const LmpcModel& P, const double* x, const double* u, LmpcTrig& T) {
   const double ivxe = 1.0 / (x[3] + 1e-3);
@@ -51,6 +54,9 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
   const double ey = x[1], vx = x[3], vy = x[4], om = x[5];
   const double ul = u[0], de = u[1];
   const double m = P.m, l = P.l, lr = P.lr, lf = P.lf;
+  // the divisions by the mass and the yaw inertia are multiplications by their reciprocals (24 IEEE divisions per evaluation
+  // otherwise; a last-place difference from the formulas as written, far inside the parity tolerance)
+  const double im = 1.0 / m, iJ = 1.0 / P.Jzz;
   // longitudinal command -> drive / brake force (single_track_planar_model.cpp:214-217)
   const double th = T.th;
   const double fd = ul * (0.5 * th + 0.5) * 1000.0;
@@ -60,7 +66,7 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
   const double Fxf = 0.5 * P.kd * fd + 0.5 * P.kb * fb - 0.5 * P.fr * m * LMPC_GRAVITY * lr / l;
   const double Fxr = 0.5 * (1.0 - P.kd) * fd + 0.5 * (1.0 - P.kb) * fb - 0.5 * P.fr * m * LMPC_GRAVITY * lf / l;
   // :267 (drag without rho here, as the reference writes it)
-  const double ax = (fd + fb - 0.5 * P.cd * P.Af * vsq - P.fr * m * LMPC_GRAVITY) / m;
+  const double ax = (fd + fb - 0.5 * P.cd * P.Af * vsq - P.fr * m * LMPC_GRAVITY) * im;
   // :270-276
   const double c4 = 0.5 * P.hcog / (lf + lr) * m;
   const double Fzf = 0.5 * m * LMPC_GRAVITY * lr / (lf + lr) - c4 * ax + 0.25 * P.clf * P.rho * P.Af * vsq;
@@ -78,9 +84,9 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
   const double Fyr = P.mu * Fzr * sqr;
   // :309-319
   const double latf = 2.0 * Fyf * cdl + 2.0 * Fxf * sd;  // front axle force along body y
-  xd[5] = (-2.0 * Fyr * lr + latf * lf) / P.Jzz;
-  xd[3] = (2.0 * Fxr + 2.0 * Fxf * cdl - 2.0 * Fyf * sd - 0.5 * P.cd * P.rho * P.Af * vsq) / m + om * vy;
-  xd[4] = (2.0 * Fyr + latf) / m - om * vx;
+  xd[5] = (-2.0 * Fyr * lr + latf * lf) * iJ;
+  xd[3] = (2.0 * Fxr + 2.0 * Fxf * cdl - 2.0 * Fyf * sd - 0.5 * P.cd * P.rho * P.Af * vsq) * im + om * vy;
+  xd[4] = (2.0 * Fyr + latf) * im - om * vx;
   // :322-330 (Frenet)
   const double iden = 1.0 / (1.0 - ey * kappa);
   const double num = vx * cph - vy * sph;
@@ -107,8 +113,8 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
     const double dfb = 1000.0 * ((-0.5 * th + 0.5) - ul * 0.5 * sech2);
     const double dFxf_ul = 0.5 * P.kd * dfd + 0.5 * P.kb * dfb;
     const double dFxr_ul = 0.5 * (1.0 - P.kd) * dfd + 0.5 * (1.0 - P.kb) * dfb;
-    const double dax_ul = (dfd + dfb) / m;
-    const double dax_vx = -P.cd * P.Af * vx / m;
+    const double dax_ul = (dfd + dfb) * im;
+    const double dax_vx = -P.cd * P.Af * vx * im;
     const double dFzf_vx = -c4 * dax_vx + 0.5 * P.clf * P.rho * P.Af * vx;
     const double dFzr_vx = c4 * dax_vx + 0.5 * P.clr * P.rho * P.Af * vx;
     const double dFzf_ul = -c4 * dax_ul, dFzr_ul = c4 * dax_ul;
@@ -125,17 +131,17 @@ LMPC_HD void lmpc_f_algebra(const LmpcModel& P, const double* x, const double* u
     const double dFxr[5] = {0.0, 0.0, 0.0, dFxr_ul, 0.0};
     for (int c = 0; c < 5; c++) {
       const double dlat = 2.0 * dFyf[c] * cdl + 2.0 * dFxf[c] * sd;
-      J[5][2 + c] = (-2.0 * dFyr[c] * lr + dlat * lf) / P.Jzz;
-      J[3][2 + c] = (2.0 * dFxr[c] + 2.0 * dFxf[c] * cdl - 2.0 * dFyf[c] * sd) / m;
-      J[4][2 + c] = (2.0 * dFyr[c] + dlat) / m;
+      J[5][2 + c] = (-2.0 * dFyr[c] * lr + dlat * lf) * iJ;
+      J[3][2 + c] = (2.0 * dFxr[c] + 2.0 * dFxf[c] * cdl - 2.0 * dFyf[c] * sd) * im;
+      J[4][2 + c] = (2.0 * dFyr[c] + dlat) * im;
     }
     // explicit delta dependence through cos/sin(delta)
     const double dlat_de = -2.0 * Fyf * sd + 2.0 * Fxf * cdl;
-    J[5][6] += dlat_de * lf / P.Jzz;
-    J[3][6] += (-2.0 * Fxf * sd - 2.0 * Fyf * cdl) / m;
-    J[4][6] += dlat_de / m;
+    J[5][6] += dlat_de * lf * iJ;
+    J[3][6] += (-2.0 * Fxf * sd - 2.0 * Fyf * cdl) * im;
+    J[4][6] += dlat_de * im;
     // drag and the omega*v coupling terms
-    J[3][2] += -P.cd * P.rho * P.Af * vx / m;
+    J[3][2] += -P.cd * P.rho * P.Af * vx * im;
     J[3][3] += om;
     J[3][4] += vy;
     J[4][2] += -om;

@@ -34,6 +34,9 @@ struct LmpcRegRow {
   int out;                 // output state
   int D;                   // |S| + |C| + 1
   int sel[LMPC_REG_D];
+  int lead;                // the first regression with the same input lists (itself when there is none before it), and
+  int follower;            // for a leader the next regression with its lists, or -1: the two share regressors and weights,
+                           // hence M'KM -- the tiled kernel scans once for the pair and keeps a second M'Ky
 };
 struct LmpcRegPlan {
   int n_out;
@@ -55,6 +58,13 @@ static inline bool lmpc_make_reg_plan(const lmpc_reg_spec* sp, LmpcRegPlan* plan
     for (int q = 0; q < nu; q++) { const int c = sp->in_u[r][q]; if (c < 0 || c >= 2) return false; row.sel[a++] = 6 + c; }
     row.sel[a++] = 8;
     while (a < LMPC_REG_D) row.sel[a++] = 9;
+    row.lead = r; row.follower = -1;
+    for (int e = 0; e < r && row.lead == r; e++) {   // pair it with an earlier unpaired leader of identical lists
+      const LmpcRegRow& o = plan->row[e];
+      bool same = o.lead == e && o.follower < 0 && o.D == row.D;
+      for (int q = 0; same && q < LMPC_REG_D; q++) same = o.sel[q] == row.sel[q];
+      if (same) { row.lead = e; plan->row[e].follower = r; }
+    }
   }
   return true;
 }
@@ -110,9 +120,10 @@ LMPC_DEV void lmpc_reg_scan_lane(const LmpcRegRow& row, double h, double ih, dou
 // holds its inputs by column (column a at tZ + a * LD) and its output's error (tE): no index lists in the loop, the
 // constant regressor folded (w * 1 = w).  Q, bv are laid out for the size class DD >= DE (the unused rows stay zero), the
 // order of the additions per lane is that of lmpc_reg_scan_lane.
-template <int DE, int DD, int LD>
-LMPC_DEV void lmpc_reg_scan_tile(double h, double ih, double kc, const double* q, const double* tZ, const double* tE, int count,
-                                 int lane, double* Q, double* bv, double& cnt) {
+// TWO: a second output over the same regressors (tE2 -> bv2).
+template <int DE, int DD, int LD, bool TWO>
+LMPC_DEV void lmpc_reg_scan_tile(double h, double ih, double kc, const double* q, const double* tZ, const double* tE, const double* tE2,
+                                 int count, int lane, double* Q, double* bv, double* bv2, double& cnt) {
   constexpr int NI = DE - 1;
   const double h2 = h * h, ih2 = ih * ih;
 #pragma unroll 2
@@ -124,11 +135,12 @@ LMPC_DEV void lmpc_reg_scan_tile(double h, double ih, double kc, const double* q
     if (d2 < h2) {
       const double u1 = 1.0 - d2 * ih2;
       const double w = kc * u1 * u1;
-      const double y = tE[p];
+      const double y = tE[p], y2 = TWO ? tE2[p] : 0.0;
 #pragma unroll
       for (int a = 0; a < DE; a++) {
         const double wa = (a < NI) ? w * m[a] : w;
         bv[a] += wa * y;
+        if (TWO) bv2[a] += wa * y2;
 #pragma unroll
         for (int b = a; b < DE; b++) {
           const int k = a * DD - a * (a - 1) / 2 + (b - a);
