@@ -914,7 +914,7 @@ static int run_tick_kernels(lmpc_handle* h, int B, const DevIO& io, const double
   }
   // K1: linearise
   {
-    const int n = B * (int)NS, threads = 64, blocks = (n + threads - 1) / threads;
+    const int n = B * (int)NS, threads = LMPC_K1_THREADS, blocks = (n + threads - 1) / threads;
     lmpc_linearise_kernel<<<blocks, threads, 0, h->stream>>>(h->M, B, (int)N, io.din[0], X_lin, U_lin, io.din[4], io.din[7], io.din[9], abg,
                                                              first ? cen : nullptr, skip);
     h->launches++;

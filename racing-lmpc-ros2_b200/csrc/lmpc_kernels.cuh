@@ -55,32 +55,45 @@ __global__ void lmpc_step_items_kernel(LmpcModel M, int n, const double* __restr
 // linearise at (X_ref_i, U_ref_i, kappa_i, T_i) (racing_mpc.cpp:169-176), write [A|B|g] (54 doubles).
 // Stage 0's thread also writes the aligned query / centre point X_ref[:, N-1] (when cen is given).
 // skip: optional per-instance mask (converged SQP instances keep their linearisation).
-__global__ void lmpc_linearise_kernel(LmpcModel M, int B, int N, const double* __restrict__ x_ic,
+#define LMPC_K1_THREADS 64
+__global__ void __launch_bounds__(LMPC_K1_THREADS) lmpc_linearise_kernel(LmpcModel M, int B, int N, const double* __restrict__ x_ic,
                                       const double* __restrict__ X_ref, const double* __restrict__ U_ref,
                                       const double* __restrict__ T_ref, const double* __restrict__ kappa,
                                       const double* __restrict__ total_length, double* __restrict__ ABg,
                                       double* __restrict__ cen, const int* __restrict__ skip) {
+  // a thread's 54 results are 432 bytes apart from its neighbour's: staged by value index ([54][65], conflict-free both
+  // ways) and written out as the block's one contiguous run of 64 x 54 doubles
+  __shared__ double stage[54 * (LMPC_K1_THREADS + 1)];
+  __shared__ int wrote[LMPC_K1_THREADS];
   const int NS = N - 1;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= B * NS) return;
-  const int b = t / NS, i = t - b * NS;
-  if (skip && skip[b]) return;
-  const double L = total_length[b], s0 = x_ic[6 * (size_t)b];
-  const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
-  double xl[6], ul[2], Al[36], Bl[12], gl[6];
-  for (int k = 0; k < 6; k++) xl[k] = xr[k];
-  xl[0] = lmpc_align_abscissa(xl[0], s0, L);
-  ul[0] = U_ref[(2 * (size_t)NS) * b + 2 * i]; ul[1] = U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
-  lmpc_linearise(M, xl, ul, kappa[(size_t)N * b + i], T_ref[(size_t)NS * b + i], Al, Bl, gl, nullptr);
-  double* o = ABg + (54 * (size_t)NS) * b + 54 * i;
-  for (int k = 0; k < 36; k++) o[k] = Al[k];
-  for (int k = 0; k < 12; k++) o[36 + k] = Bl[k];
-  for (int k = 0; k < 6; k++) o[48 + k] = gl[k];
-  if (i == 0 && cen) {
-    const double* xe = X_ref + (6 * (size_t)N) * b + 6 * (N - 1);
-    double* c = cen + 6 * (size_t)b;
-    c[0] = lmpc_align_abscissa(xe[0], s0, L);
-    for (int k = 1; k < 6; k++) c[k] = xe[k];
+  const bool mine = t < B * NS && !(skip && skip[t / NS]);
+  wrote[threadIdx.x] = mine ? 1 : 0;
+  if (mine) {
+    const int b = t / NS, i = t - b * NS;
+    const double L = total_length[b], s0 = x_ic[6 * (size_t)b];
+    const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
+    double xl[6], ul[2], Al[36], Bl[12], gl[6];
+    for (int k = 0; k < 6; k++) xl[k] = xr[k];
+    xl[0] = lmpc_align_abscissa(xl[0], s0, L);
+    ul[0] = U_ref[(2 * (size_t)NS) * b + 2 * i]; ul[1] = U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
+    lmpc_linearise(M, xl, ul, kappa[(size_t)N * b + i], T_ref[(size_t)NS * b + i], Al, Bl, gl, nullptr);
+    double* o = stage + threadIdx.x;
+    for (int k = 0; k < 36; k++) o[k * (LMPC_K1_THREADS + 1)] = Al[k];
+    for (int k = 0; k < 12; k++) o[(36 + k) * (LMPC_K1_THREADS + 1)] = Bl[k];
+    for (int k = 0; k < 6; k++) o[(48 + k) * (LMPC_K1_THREADS + 1)] = gl[k];
+    if (i == 0 && cen) {
+      const double* xe = X_ref + (6 * (size_t)N) * b + 6 * (N - 1);
+      double* c = cen + 6 * (size_t)b;
+      c[0] = lmpc_align_abscissa(xe[0], s0, L);
+      for (int k = 1; k < 6; k++) c[k] = xe[k];
+    }
+  }
+  __syncthreads();
+  double* o = ABg + 54 * (size_t)blockIdx.x * LMPC_K1_THREADS;   // item t's block is ABg + 54 t
+  for (int e = threadIdx.x; e < 54 * LMPC_K1_THREADS; e += LMPC_K1_THREADS) {
+    const int th = e / 54, k = e - 54 * th;
+    if (wrote[th]) o[e] = stage[k * (LMPC_K1_THREADS + 1) + th];
   }
 }
 
