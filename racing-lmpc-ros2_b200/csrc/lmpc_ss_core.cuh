@@ -15,6 +15,9 @@
 #include "lmpc_warp.cuh"
 
 #define LMPC_SS_T 4   // candidates kept per lane
+#ifndef LMPC_SS_PPT
+#define LMPC_SS_PPT 8 // points per lane and trip of the scan
+#endif
 
 struct LmpcLapView {
   const double* ps;     // [m] s of the tripled points
@@ -38,18 +41,19 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
   LANES_BEGIN
     double a0 = 1e300, a1 = 1e300, a2 = 1e300, a3 = 1e300;
     int b0 = 1 << 30, b1 = 1 << 30, b2 = 1 << 30, b3 = 1 << 30;
-    // four points per trip: their eight loads go out together, then the (branchy, usually one-test) insertions
-    for (int base = lane; base < m; base += 128) {
-      double vv[4];
+    // LMPC_SS_PPT points per trip: their loads go out together (the scan waits for the L2, not for arithmetic), then the
+    // (branchy, usually one-test) insertions in index order
+    for (int base = lane; base < m; base += 32 * LMPC_SS_PPT) {
+      double vv[LMPC_SS_PPT];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < LMPC_SS_PPT; u++) {
         const int idx = base + 32 * u;
         const int ic = idx < m ? idx : base;   // clamp: always a valid address
         const double ds = qs - lap.ps[ic], de = qe - lap.pe[ic];
         vv[u] = idx < m ? ds * ds + de * de : 1e300;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < LMPC_SS_PPT; u++) {
         const int idx = base + 32 * u;
         const double v = vv[u];
         // strided indices increase, so on equal distance the earlier (lower) index stays ahead
@@ -81,7 +85,7 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
     LANES_BEGIN
       hv(lane) = c0(lane); hi(lane) = j0(lane);
     LANES_END
-    warp_argmin(hv, hi);
+    warp_argmin_nonneg(hv, hi);
     const int wi = hi(0); const double wv = hv(0);
     LaneVar<int> anyex;
     LANES_BEGIN
@@ -128,7 +132,7 @@ LMPC_DEV void lmpc_ss_query_warp(const LmpcLapView& lap, double qs, double qe, i
         }
         hv(lane) = bv; hi(lane) = bi;
       LANES_END
-      warp_argmin(hv, hi);
+      warp_argmin_nonneg(hv, hi);
       last_d = hv(0); last_i = hi(0);
       const int wi = last_i;
       if (r < 32) {

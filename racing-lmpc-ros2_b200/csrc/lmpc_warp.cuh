@@ -313,3 +313,20 @@ LMPC_DEV void group_max(LaneVar<double, 32 * NW>& x, double* scratch) {
 // single-warp spellings used by the safe-set kernel
 LMPC_DEV void warp_argmin(LaneVar<double>& val, LaneVar<int>& idx) { group_argbest<1>(val, idx, false, nullptr); }
 LMPC_DEV void warp_or(LaneVar<int>& x) { group_or<1>(x, nullptr); }
+// arg-min of NON-NEGATIVE values (squared distances; NaN sorts last), ties to the lowest index -- the same answer as
+// warp_argmin.  On the GPU: the bit pattern of a non-negative double orders like an unsigned integer, so three integer
+// warp reductions (high word, low word among the lanes that matched, index among those) replace five exchange steps of
+// (value, index) pairs: 12 instructions instead of 55 in each of the safe-set query's 32 rounds.
+LMPC_DEV void warp_argmin_nonneg(LaneVar<double>& val, LaneVar<int>& idx) {
+#if defined(LMPC_EMULATE)
+  warp_argmin(val, idx);
+#else
+  const unsigned long long b = (unsigned long long)__double_as_longlong(val.v);
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  const unsigned mi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)idx.v : 0xffffffffu);
+  val.v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  idx.v = (int)mi;
+#endif
+}
