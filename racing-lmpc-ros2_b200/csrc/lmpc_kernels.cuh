@@ -73,15 +73,12 @@ __global__ void __launch_bounds__(LMPC_K1_THREADS) lmpc_linearise_kernel(LmpcMod
     const int b = t / NS, i = t - b * NS;
     const double L = total_length[b], s0 = x_ic[6 * (size_t)b];
     const double* xr = X_ref + (6 * (size_t)N) * b + 6 * i;
-    double xl[6], ul[2], Al[36], Bl[12], gl[6];
+    double xl[6], ul[2];
     for (int k = 0; k < 6; k++) xl[k] = xr[k];
     xl[0] = lmpc_align_abscissa(xl[0], s0, L);
     ul[0] = U_ref[(2 * (size_t)NS) * b + 2 * i]; ul[1] = U_ref[(2 * (size_t)NS) * b + 2 * i + 1];
-    lmpc_linearise(M, xl, ul, kappa[(size_t)N * b + i], T_ref[(size_t)NS * b + i], Al, Bl, gl, nullptr);
-    double* o = stage + threadIdx.x;
-    for (int k = 0; k < 36; k++) o[k * (LMPC_K1_THREADS + 1)] = Al[k];
-    for (int k = 0; k < 12; k++) o[(36 + k) * (LMPC_K1_THREADS + 1)] = Bl[k];
-    for (int k = 0; k < 6; k++) o[(48 + k) * (LMPC_K1_THREADS + 1)] = gl[k];
+    // the thread's staging column is also where the tangents are accumulated (lmpc_linearise_staged)
+    lmpc_linearise_staged(M, xl, ul, kappa[(size_t)N * b + i], T_ref[(size_t)NS * b + i], stage + threadIdx.x, LMPC_K1_THREADS + 1);
     if (i == 0 && cen) {
       const double* xe = X_ref + (6 * (size_t)N) * b + 6 * (N - 1);
       double* c = cen + 6 * (size_t)b;

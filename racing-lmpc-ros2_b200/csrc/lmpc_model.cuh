@@ -246,6 +246,71 @@ LMPC_HD void lmpc_linearise(const LmpcModel& P, const double* x, const double* u
   }
 }
 
+// The same linearisation with the accumulated tangents kept OUTSIDE the registers: `o` is the item's 54-value result
+// [A 36 | B 12 | g 6] with element k at o[k * S] (the linearisation kernel's shared-memory staging column).  The sum over
+// the stages of w_n dk_n/d(x,u) is accumulated where it will be stored -- dk[r][col] belongs to element r + 6 col of
+// [A | B] -- and the tangents of the previous stage are overwritten column by column (column col of the new stage depends
+// on column col of the old one only), so one 6 x 7 array lives in registers instead of three 6 x 8 arrays: no local
+// memory (a third of the kernel's stall samples were waiting for it).  Column 0 (d/ds) is identically zero and skipped.
+// The arithmetic per element is that of lmpc_linearise (tests/test_emulator.py compares the two bit for bit).
+#if defined(__CUDACC__) && !defined(LMPC_EMULATE)
+#define LMPC_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define LMPC_HD_NOINLINE static __attribute__((noinline))
+#endif
+// explicit Euler: one stage, through the plain form (its own function: its arrays stay out of the RK4 path's frame)
+LMPC_HD_NOINLINE void lmpc_linearise_staged_euler(const LmpcModel& P, const double* x, const double* u, double kappa, double dt, double* o, int S) {
+  double A[36], B[12], g[6];
+  lmpc_linearise(P, x, u, kappa, dt, A, B, g, nullptr);
+  for (int k = 0; k < 36; k++) o[k * S] = A[k];
+  for (int k = 0; k < 12; k++) o[(36 + k) * S] = B[k];
+  for (int k = 0; k < 6; k++) o[(48 + k) * S] = g[k];
+}
+LMPC_HD void lmpc_linearise_staged(const LmpcModel& P, const double* x, const double* u, double kappa, double dt, double* o_, int S) {
+  if (P.integrator == 1) { lmpc_linearise_staged_euler(P, x, u, kappa, dt, o_, S); return; }
+  volatile double* o = o_;   // every access is a load or a store: the sums must not be promoted back into registers
+  double J[6][7], k[6], xt[6], acc[6], D[6][7];   // D[r][col - 1], col = 1..7
+  LmpcTrig Tu;
+  lmpc_trig_controls(u, Tu);
+  for (int i = 0; i < 6; i++) { acc[i] = 0.0; k[i] = 0.0; }
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 7; c++) D[r][c] = 0.0;
+  for (int e = 0; e < 48; e++) o[e * S] = 0.0;
+  LMPC_NOUNROLL
+  for (int n = 0; n < 4; n++) {
+    const double cn = (n == 0) ? 0.0 : (n == 3 ? dt : dt / 2.0), wn = (n == 0 || n == 3) ? 1.0 : 2.0;
+    for (int i = 0; i < 6; i++) xt[i] = (n == 0) ? x[i] : x[i] + cn * k[i];
+    lmpc_f_u<true>(P, xt, u, kappa, Tu, k, J);
+    for (int i = 0; i < 6; i++) acc[i] += wn * k[i];
+    LMPC_UNROLL
+    for (int col = 1; col < 8; col++) {
+      double v[6];
+      LMPC_UNROLL
+      for (int r = 0; r < 6; r++) v[r] = cn * D[r][col - 1] + ((col < 6 && r == col) ? 1.0 : 0.0);
+      LMPC_UNROLL
+      for (int r = 0; r < 6; r++) {
+        double a = 0.0;
+        LMPC_UNROLL
+        for (int q = 1; q < 6; q++) a += J[r][q - 1] * v[q];
+        if (col >= 6) a += J[r][5 + (col - 6)];
+        D[r][col - 1] = a;
+        o[(r + 6 * col) * S] += wn * a;
+      }
+    }
+  }
+  const double w6 = dt / 6.0;
+  for (int i = 0; i < 6; i++) acc[i] = x[i] + w6 * acc[i];
+  for (int r = 0; r < 6; r++) {
+    double a = 0.0;
+    for (int c = 0; c < 8; c++) {
+      const double t = w6 * o[(r + 6 * c) * S];
+      const double e = (c < 6) ? t + (r == c ? 1.0 : 0.0) : t;
+      o[(r + 6 * c) * S] = e;
+      a += e * (c < 6 ? x[c] : u[c - 6]);
+    }
+    o[(48 + r) * S] = acc[r] - a;
+  }
+}
+
 // lmpc_utils align_abscissa (src/tools/lmpc_utils/include/lmpc_utils/utils.hpp:35-41)
 LMPC_HD double lmpc_align_abscissa(double s1, double s2, double total) {
   const double k = fabs(s2 - s1) + total / 2.0;

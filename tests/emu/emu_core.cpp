@@ -19,6 +19,13 @@ extern "C" void emu_linearise(const lmpc_vehicle_params* v, const double* x, con
   lmpc_linearise(P, x, u, kappa, dt, A, B, g, xn);
 }
 
+// the linearisation kernel's form (tangent sums accumulated in the output, strided): out [54] = A | B | g
+extern "C" void emu_linearise_staged(const lmpc_vehicle_params* v, const double* x, const double* u, double kappa, double dt,
+                                     double* out, int stride) {
+  LmpcModel P = lmpc_make_model(*v);
+  lmpc_linearise_staged(P, x, u, kappa, dt, out, stride);
+}
+
 // one lap at a time: (query, lap) exactly as the kernel does it
 extern "C" void emu_ss_query_lap(int m, const double* ps, const double* pe, const double* xr, const double* J, const int* canon,
                                  int take, int out_off, double qs, double qe, int max_total, double* ss_x, double* ss_j,

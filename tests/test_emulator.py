@@ -386,3 +386,26 @@ def test_emulated_qp_kernel_abandons_a_diverging_polish(emu, pkg):
     assert k["iters"] <= 17, k["iters"]
     assert abs(p["iters"] - k["iters"]) <= 2          # the port carries the same rule
     assert max(relerr(k["X"], d["X"]), relerr(k["U"], d["U"]), relerr(k["dU"], d["dU"])) < 1e-8
+
+
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_staged_linearisation_equals_the_plain_form_bit_for_bit(emu, pkg, integrator):
+    """The linearisation kernel accumulates the stage tangents in its (strided) output column and overwrites the previous
+    stage's tangents in place (lmpc_linearise_staged); the model header's plain form keeps three 6 x 8 arrays.  Same
+    products, same sums, same order: identical bits (compiled without contraction here; A[:, 0] = e0 exactly)."""
+    from racing_lmpc_ros2_b200 import binding as Bd
+    veh = dict(pkg.configs.BARC_VEHICLE, integrator=integrator)
+    vs = Bd.fill_struct(Bd.VehicleParams(), veh)
+    rng = np.random.default_rng(5)
+    for _ in range(100):
+        x = np.array([rng.uniform(0, 10), rng.uniform(-.3, .3), rng.uniform(-.3, .3), rng.uniform(0.5, 2.5), rng.uniform(-.2, .2), rng.uniform(-1, 1)])
+        u = np.array([rng.uniform(-1, 1), rng.uniform(-.3, .3)])
+        kap, dt = rng.uniform(-1, 1), rng.uniform(0.01, 0.1)
+        A = np.zeros(36); B = np.zeros(12); g = np.zeros(6); xn = np.zeros(6)
+        emu.emu_linearise(C.byref(vs), _p(x), _p(u), C.c_double(kap), C.c_double(dt), _p(A), _p(B), _p(g), _p(xn))
+        for stride in (1, 65):
+            out = np.full(54 * stride, np.nan)
+            emu.emu_linearise_staged(C.byref(vs), _p(x), _p(u), C.c_double(kap), C.c_double(dt), _p(out), stride)
+            got = out[::stride][:54]
+            assert np.array_equal(got[:36], A) and np.array_equal(got[36:48], B) and np.array_equal(got[48:], g)
+        assert np.array_equal(A.reshape(6, 6, order="F")[:, 0], np.eye(6)[0])
