@@ -401,6 +401,7 @@ polish_failed:
           for (int q = 0; q < w->mB; q++) {            /* top-MB by Omega, ties -> lowest index */
             int best = -1; double bv = -1.0;
             for (int j = 0; j < K; j++) if (!w->isB[j] && w->om[j] > bv) { bv = w->om[j]; best = j; }
+            if (best < 0) best = 0;                    /* NaN weights (an iterate that blew up; it ends as NUMERIC): no winner, no address */
             w->Bidx[q] = best; w->isB[best] = 1;
           }
         }

@@ -661,6 +661,9 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
               int kb = kbs[0];
 #pragma unroll
               for (int r = 1; r < LMPC_MB; r++) kb = (q == r) ? kbs[r] : kb;
+              // an iterate that has gone NaN (it ends as LMPC_NUMERIC) has no largest weight: the arg-max returns its
+              // "none" index, which must not become an address
+              kb = (kb >= 0 && kb < K) ? kb : 0;
               TB[TB_BCOL + lane] = ST[6 * kb + a];
             }
           GLANES_END(NW)

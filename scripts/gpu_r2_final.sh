@@ -1,16 +1,14 @@
 #!/bin/bash
-# round 2 closing call (one GPU): row timings, bench line, launch list, compute-sanitizer on the kernels changed last
+# round 2 closing call (one GPU): GPU suite with its parity figures, bench line, launch list, row timings
 mkdir -p gpurun_out
-timeout 600 python scripts/time_rows.py > gpurun_out/r2e_rows.txt 2>&1; cat gpurun_out/r2e_rows.txt | cut -c1-230
-timeout 600 python bench.py > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err; tail -c 200 gpurun_out/r2e_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2e_launches.csv python bench.py --steps 3 --warmup 3 --no-configs > gpurun_out/r2e_ncu_bench.log 2>&1
-{
-echo "compute-sanitizer, second session of round 2 (B200): the kernels changed after sanitizer_r2.txt's first part"; echo
-echo '$ compute-sanitizer --tool memcheck python -m pytest tests/test_regress.py -m gpu -q   (regression scan: cp.async double-buffered tiles, paired regressions; staged linearisation kernel inside the tick test)'
-timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_regress.py -m gpu -q 2>&1 | grep -E "passed|failed|ERROR SUMMARY|Invalid" | head -8
-echo; echo '$ compute-sanitizer --tool racecheck --racecheck-report all python -m pytest tests/test_regress.py -m gpu -q -k "regression_matches or tick_with"'
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python -m pytest tests/test_regress.py -m gpu -q -k "regression_matches or tick_with" 2>&1 | grep -E "passed|failed|RACECHECK SUMMARY|hazard" | head -8
-echo; echo '$ compute-sanitizer --tool memcheck python scripts/prof_qp.py 64 1   (linearise with the staged stores, safe-set query, QP)'
-timeout 600 compute-sanitizer --tool memcheck python scripts/prof_qp.py 64 1 2>&1 | grep -E "iters hist|ERROR SUMMARY|Invalid|Error" | head -8
-} > gpurun_out/sanitizer_r2b.txt 2>&1
-cat gpurun_out/sanitizer_r2b.txt
+timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/r2f_tests.txt 2>&1; echo "pytest exit $?" >> gpurun_out/r2f_tests.txt
+timeout 600 python bench.py > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 3 --warmup 3 --no-configs > gpurun_out/r2f_ncu_bench.log 2>&1
+timeout 600 python scripts/time_rows.py > gpurun_out/r2f_rows.txt 2>&1
+tail -3 gpurun_out/r2f_tests.txt; cut -c1-200 gpurun_out/r2f_rows.txt; tail -c 300 gpurun_out/r2f_bench.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2f_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline']['other_kernels_ms'], d['roofline']['fp64']['frac'], d['cpu_baseline']['value'])
+for k,v in (d.get('configs') or {}).items(): print(k, v['value'], v['ms_per_step'], v['solved_fraction'], v['kernel_ms'])
+"
