@@ -176,6 +176,7 @@ extern "C" int lmpc_create(const lmpc_mpc_config* config, const lmpc_vehicle_par
   h->M = lmpc_make_model(*vehicle);
   if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return LMPC_ERR_NO_DEVICE; }
   h->qp_smem = sizeof(double) * (size_t)h->P.lay.total;
+  if (const char* e = getenv("LMPC_QP_EXTRA_SMEM")) h->qp_smem += (size_t)atoi(e);   // occupancy experiments (profiles/README.md)
   rc = set_qp_attr(h);
   if (rc != LMPC_OK) { fprintf(stderr, "lmpc_create: %s\n", h->err.c_str()); delete h; return rc; }
   const size_t B = (size_t)max_batch, N = (size_t)h->P.N, NS = (size_t)h->P.NS, K = (size_t)std::max(h->P.K, 1);
