@@ -85,6 +85,14 @@ extern "C" void emu_track_f2g(int n, const double* f, double* g) { const LmpcTra
 extern "C" void emu_track_g2f(int n, const double* g, double* f) { const LmpcTrack T = g_trk.view(); for (int i = 0; i < n; i++) lmpc_global_to_frenet(T, g + 3 * i, f + 3 * i); }
 
 // error-dynamics regression of one query item over M prepared points (Z [M][8], E [M][6]); A, B column-major, in place
+// the plan the host builds from a spec: which regressions the tiled kernel scans as a pair (lead / follower per row)
+extern "C" int emu_reg_plan_pairs(const lmpc_reg_spec* sp, int* lead, int* follower) {
+  LmpcRegPlan plan;
+  if (!lmpc_make_reg_plan(sp, &plan)) return -1;
+  for (int r = 0; r < plan.n_out; r++) { lead[r] = plan.row[r].lead; follower[r] = plan.row[r].follower; }
+  return plan.n_out;
+}
+
 extern "C" int emu_regress(const lmpc_reg_spec* sp, int M, const double* Z, const double* E, const double* zq, double* A, double* B,
                            double* C, int* npts) {
   LmpcRegPlan plan;

@@ -155,6 +155,18 @@ def test_gpu_regression_matches_oracle(pkg):
     n0 = m.launch_count
     m.regress(spec, xq, uq, A0, B0, C0)
     assert m.launch_count - n0 == 1     # points are prepared once per safe-set update
+    # other shapes of the plan: a pair and singles of different sizes (the exact-size scans for 1, 3 and 4 regressors),
+    # and the general size class (six states and both controls: the index-list scan)
+    for out_s, inx_s, inu_s in (([3, 4, 5, 2], [[3, 4], [3, 4], [5], [5, 3, 4]], [[0], [0], [], [1]]),
+                                ([5, 3], [[0, 1, 2, 3, 4, 5], [3, 4, 5]], [[0, 1], [1]])):
+        sp = make_reg_spec(out_s, inx_s, inu_s, H)
+        A3, B3, C3, n3 = m.regress(sp, xq[:32], uq[:32], A0[:32], B0[:32], C0[:32])
+        w2 = 0.0
+        for i in range(32):
+            A2, B2, C2, n2 = R.regress(pts, out_s, inx_s, inu_s, H, xq[i], uq[i], A0[i], B0[i], C0[i])
+            assert (n3[i] == n2).all(), (out_s, i, n3[i], n2)
+            w2 = max(w2, np.abs(A3[i] - A2).max(), np.abs(B3[i] - B2).max(), np.abs(C3[i] - C2).max())
+        assert n3.sum() > 0 and w2 < 1e-8, (out_s, w2)
 
 
 @pytest.mark.gpu
@@ -249,3 +261,23 @@ def test_gpu_config4_batch_survives_instances_that_blow_up(pkg):
     assert (st == 0).mean() > 0.9 and (st == 4).sum() >= 1, np.bincount(st)
     assert np.isfinite(out["X_optm"][st == 0]).all()
     m.close()
+
+
+def test_regression_plan_pairs_identical_input_lists(emu, pkg):
+    """Regressions with the same input lists share regressors and weights, hence M'KM: the plan marks them as a pair and
+    the tiled kernel scans once for both (lmpc_reg_core.cuh, LmpcRegRow::lead / follower).  Pairs only: a third
+    regression with the same lists leads its own scan; different lists never pair."""
+    import ctypes as C
+    from racing_lmpc_ros2_b200.binding import make_reg_spec
+
+    def pairs(out, in_x, in_u):
+        spec = make_reg_spec(out, in_x, in_u, 0.6)
+        lead = (C.c_int * 6)(); fol = (C.c_int * 6)()
+        n = emu.emu_reg_plan_pairs(C.byref(spec), lead, fol)
+        assert n == len(out)
+        return list(lead[:n]), list(fol[:n])
+
+    assert pairs([3, 4, 5], [[3, 4, 5]] * 3, [[0], [1], [1]]) == ([0, 1, 1], [-1, 2, -1])      # the LMPC choice: v_y and omega pair
+    assert pairs([3, 4, 5], [[3, 4, 5]] * 3, [[1], [1], [1]]) == ([0, 0, 2], [1, -1, -1])      # three alike: one pair, one alone
+    assert pairs([3, 4], [[3, 4, 5], [3, 5, 4]], [[1], [1]]) == ([0, 1], [-1, -1])             # same set, other order: not a pair
+    assert pairs([3, 4, 5, 2], [[3, 4], [3, 4], [5], [5]], [[0], [0], [], []]) == ([0, 0, 2, 2], [1, -1, 3, -1])
