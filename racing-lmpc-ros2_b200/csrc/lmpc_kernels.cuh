@@ -2,7 +2,7 @@
 //
 //   K1 lmpc_linearise_kernel   thread per (instance, stage): abscissa alignment + RK4 Jacobians -> A,B,g
 //   K2 lmpc_ss_query_kernel    warp per (instance, lap): exact k-NN in the safe-set slab + cost-to-go gather
-//   KR lmpc_regress_kernel     warp per (instance, stage): error-dynamics regression added to [A|B|g] (optional, between K1 and K3)
+//   KR lmpc_regress_tiled_kernel  warp per (instance, stage), 8 per block: error-dynamics regression added to [A|B|g] (optional, between K1 and K3)
 //   K3 lmpc_qp_kernel          warp group (1, 2 or 4 warps = one CTA) per instance: interior-point / Riccati solve in shared memory
 //
 // Batch arrays are instance-major, so a warp's (or thread's) reads of its own instance are contiguous.

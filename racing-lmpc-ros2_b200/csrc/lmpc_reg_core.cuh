@@ -19,10 +19,16 @@
 // b = -M'Ky as written (:229), +1 is the local-linear-regression correction of the LMPC paper (error = actual -
 // predicted is *added* to the nominal model).  The per-lap sort by distance (:94-108) only permutes the sums.
 //
+// Both the test d_p < h and the weight are evaluated from d_p^2 (d_p^2 < h^2, K_p = 0.75/h (1 - d_p^2/h^2)^2): the same
+// numbers to the last place or two, no square root in the scan.
+//
 // The model error y_p does not depend on the query: it is computed once per safe-set update by lmpc_reg_prepare
 // (thread per point) and kept next to the points.  The scan is exact brute force over the device-resident slab
 // (L2-resident: 14 doubles per point), lanes stride the points, partial normal equations live in registers
-// (45 + 9 accumulators), one butterfly all-reduce, then every lane runs the same 9x9 Cholesky.
+// (45 + 9 accumulators; 15 + 5 in the size class of at most four inputs), one butterfly all-reduce, then every lane runs
+// the same Cholesky.  The CUDA kernel (lmpc_regress_tiled_kernel, lmpc_kernels.cuh) streams the points through
+// shared-memory tiles, scans only the window of the sorted points a query can reach, instantiates the scan for the exact
+// number of regressors and scans regressions with identical input lists as a pair.
 #pragma once
 #include "lmpc_warp.cuh"
 #include "../../include/lmpc_b200.h"
