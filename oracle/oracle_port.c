@@ -18,6 +18,11 @@
 #include "oracle_internal.h"
 
 #define NS ORC_NMAX
+/* sigma_b >= 0 carried as a FREE variable (same optimum for q_b > 0; removes a complementarity pair that is degenerate
+ * whenever no boundary row is active) -- the rule of csrc/lmpc_qp_core.cuh (LMPC_FREE_THETA), mirrored */
+#ifndef ORC_FREE_THETA
+#define ORC_FREE_THETA 1
+#endif
 #define QMAX 9              /* 1 + max explicit (basic) safe-set columns */
 #define PMAX 6               /* active-set refinement rounds of the polish */
 #define MAXROW 22            /* per-stage row slots: 12 x-box + 4 u-box + 4 du-box + 2 boundary */
@@ -123,7 +128,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
     }
   }
   for (int j = 0; j < N * MAXROW; j++) m_total += w->act[j];
-  if (soft) m_total += 1;
+  if (soft && !ORC_FREE_THETA) m_total += 1;
   m_total += K;
   w->m_total = m_total;
 
@@ -220,7 +225,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       }
     if (thoff >= 0.0 && viol + thoff > w->th) w->th = viol + thoff;
   }
-  w->yth = mu0 / w->th;
+  w->yth = ORC_FREE_THETA ? 0.0 : mu0 / w->th;
   for (int j = 0; j < K; j++) { w->lam[j] = 1.0 / K; w->ylam[j] = mu0 * K; }
   double R0 = 1.0; /* size of the initial dual residual (pi0 = 0): bounds the tracked reduction */
   {
@@ -272,12 +277,13 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
         mu += w->s[j] * w->y[j];
       }
     }
-    if (soft) mu += w->th * w->yth;
+    if (soft && !ORC_FREE_THETA) mu += w->th * w->yth;
     double rnu = -1.0;
     for (int j = 0; j < K; j++) { mu += w->lam[j] * w->ylam[j]; rnu += w->lam[j]; }
     if (!learn) rnu = 0.0;
     mu /= (double)m_total;
-    if (!polishing && mu < tol2 && rpn < tol2 && rho_d * R0 < tol2 && fabs(rnu) < tol2) {
+    if (!polishing && ((mu < tol2 && rpn < tol2 && rho_d * R0 < tol2 && fabs(rnu) < tol2) ||
+                       (mu < 1e-13 && rpn < 1e-9 && rho_d * R0 < 1e-9 && fabs(rnu) < 1e-9))) {   /* or the floor of double precision */
       if (!do_polish) { status = ORC_OK; break; }
       polishing = 1;
     }
@@ -290,7 +296,7 @@ int orc_step_port(const orc_vehicle* vp, const orc_config* c, const orc_safe_set
       memcpy(w->xsave, w->x, sizeof w->xsave); memcpy(w->usave, w->u, sizeof w->usave); memcpy(w->lsave, w->lam, sizeof w->lsave); w->thsave = w->th;
       memcpy(w->ysave, w->y, sizeof w->y); memcpy(w->ylsave, w->ylam, sizeof w->ylam); w->ythsave = w->yth; polish_tries++; prev_changed = 0;
       for (int j = 0; j < N * MAXROW; j++) w->pact[j] = w->act[j] && w->y[j] > w->s[j];
-      w->pact_th = soft && w->yth > w->th;
+      w->pact_th = !ORC_FREE_THETA && soft && w->yth > w->th;
       for (int j = 0; j < K; j++) w->pnb[j] = !(w->lam[j] >= w->ylam[j]);
       for (int j = 0; j < N * MAXROW; j++) if (w->act[j] && !w->pact[j]) w->y[j] = 0.0;
       if (soft && !w->pact_th) w->yth = 0.0;
@@ -330,7 +336,8 @@ polish_failed:
       const double smu = sigma * mu;
       /* ---------- assemble stage data ---------- */
       double Dthth = 0.0, cth = 0.0;
-      if (soft) { Dthth = 2.0 * qb + w->yth / w->th; cth = 2.0 * qb * w->th - (smu - (pass ? w->corr_th : 0.0)) / w->th; }
+      if (soft && ORC_FREE_THETA) { Dthth = 2.0 * qb; cth = 2.0 * qb * w->th; }
+      else if (soft) { Dthth = 2.0 * qb + w->yth / w->th; cth = 2.0 * qb * w->th - (smu - (pass ? w->corr_th : 0.0)) / w->th; }
       if (soft && polishing) {
         Dthth = 2.0 * qb; cth = 2.0 * qb * w->th;
         if (w->pact_th) { Dthth += prho; cth += -w->yth + prho * w->th; }
@@ -601,7 +608,8 @@ polish_failed:
           w->dylam[j] = tl - w->ylam[j] - w->dlam[j] * (w->ylam[j] / w->lam[j]);
         }
       }
-      if (soft) { const double tt = (smu - (pass ? w->corr_th : 0.0)) / w->th; w->dyth = tt - w->yth - (w->yth / w->th) * w->dth; }
+      if (soft && !ORC_FREE_THETA) { const double tt = (smu - (pass ? w->corr_th : 0.0)) / w->th; w->dyth = tt - w->yth - (w->yth / w->th) * w->dth; }
+      else w->dyth = 0.0;
       /* ---------- row directions and step length ---------- */
       double amax = 1e300;
       for (int i = 0; i < N; i++) {
@@ -620,7 +628,7 @@ polish_failed:
           if (w->dy[j] < 0.0 && -w->y[j] / w->dy[j] < amax) amax = -w->y[j] / w->dy[j];
         }
       }
-      if (soft) {
+      if (soft && !ORC_FREE_THETA) {
         if (w->dth < 0.0 && -w->th / w->dth < amax) amax = -w->th / w->dth;
         if (w->dyth < 0.0 && -w->yth / w->dyth < amax) amax = -w->yth / w->dyth;
       }
@@ -632,7 +640,7 @@ polish_failed:
         const double aa = amax < 1.0 ? amax : 1.0;
         double mua = 0.0;
         for (int j = 0; j < N * MAXROW; j++) if (w->act[j]) { mua += (w->s[j] + aa * w->ds[j]) * (w->y[j] + aa * w->dy[j]); w->corr[j] = w->ds[j] * w->dy[j]; }
-        if (soft) { mua += (w->th + aa * w->dth) * (w->yth + aa * w->dyth); w->corr_th = w->dth * w->dyth; }
+        if (soft && !ORC_FREE_THETA) { mua += (w->th + aa * w->dth) * (w->yth + aa * w->dyth); w->corr_th = w->dth * w->dyth; }
         for (int j = 0; j < K; j++) { mua += (w->lam[j] + aa * w->dlam[j]) * (w->ylam[j] + aa * w->dylam[j]); w->corr_lam[j] = w->dlam[j] * w->dylam[j]; }
         mua /= (double)m_total;
         sigma = pow(mua / mu, 3.0);
@@ -661,7 +669,7 @@ polish_failed:
       if (soft) {
         w->th += w->dth;
         if (w->pact_th) { dymax = fmax(dymax, fabs(prho * w->th) / (1.0 + fabs(w->yth))); w->yth += prho * (-w->th); if (w->yth < -dtol) { w->pact_th = 0; w->yth = 0.0; changed++; } }
-        else if (w->th < -ftol) { w->pact_th = 1; changed++; }
+        else if (!ORC_FREE_THETA && w->th < -ftol) { w->pact_th = 1; changed++; }
       }
       for (int j = 0; j < K; j++) {
         w->lam[j] += w->dlam[j];
@@ -685,7 +693,7 @@ polish_failed:
       /* same rule as the kernel (lmpc_qp_core.cuh): a polish whose active set is coming apart is abandoned at once */
       const int diverging = polishing >= 2 && changed > 8 && changed > 2 * prev_changed;
       prev_changed = changed;
-      if (!diverging && (changed || dymax > 1e-4) && polishing < PMAX) { polishing++; continue; }
+      if (!diverging && (changed || dymax > (polishing >= 2 ? 1e-4 : 1e-6)) && polishing < PMAX) { polishing++; continue; }   /* LMPC_PDY / LMPC_PDY2 of the kernel */
       out->polished = (!diverging && changed == 0 && viol == 0) ? polishing : 0;
       if (out->polished) { status = ORC_OK; break; }
       goto polish_failed;

@@ -32,7 +32,11 @@
 #define LMPC_PMAX 6             // active-set refinement rounds of the polish
 #endif
 #ifndef LMPC_PDY
-#define LMPC_PDY 1e-4           // relative multiplier change below which the augmented-Lagrangian iteration stops
+#define LMPC_PDY 1e-6           // relative multiplier change below which the polish stops after its first round (with the boundary
+                                // slack free most instances do, and this is what bounds their error: change / rho)
+#endif
+#ifndef LMPC_PDY2
+#define LMPC_PDY2 1e-4          // ... and after a later round (an ill-conditioned instance does not get below 1e-6 at all)
 #endif
 #ifndef LMPC_PRHO
 #define LMPC_PRHO 1e7           // augmented-Lagrangian weight of the polish
@@ -294,6 +298,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
   // scratch of the group reductions: one warp uses the (then idle) YY block of the sweep, NW warps their own NW x NRED area
   double* RED = (NW == 1) ? (sm + LO(oYY)) : (sm + LO(oRED));
   double* TB = sm + LO(oTERM);
+// LMPC_FREE_THETA: the boundary slack sigma_b >= 0 (racing_mpc.cpp: slack of the soft track boundary, cost q_b sigma_b^2)
+// carried as a FREE variable.  With q_b > 0 the bound is redundant -- a negative slack tightens every boundary row and
+// costs q_b sigma_b^2, so it is never optimal -- and the optimum is the same; what goes away is a complementarity pair that
+// is degenerate whenever no boundary row is active (sigma_b* = 0 with multiplier 0), i.e. on most instances, which made
+// the interior point crawl (sigma_b shrinking 2.5x per iteration while mu fell 10x).
+#ifndef LMPC_FREE_THETA
+#define LMPC_FREE_THETA 1
+#endif
 #ifndef LMPC_MU0
 #define LMPC_MU0 0.1
 #endif
@@ -413,7 +425,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
     group_max<NW>(bv, RED);
     if (bv(0) + 0.1 > th_start) th_start = bv(0) + 0.1;
   }
-  double th = th_start, yth = mu0 / th_start, dth = 0.0, dyth = 0.0, dtha = 0.0, dytha = 0.0;
+  double th = th_start, yth = LMPC_FREE_THETA ? 0.0 : mu0 / th_start, dth = 0.0, dyth = 0.0, dtha = 0.0, dytha = 0.0;
   LaneVar<ArrK, NT> lam, ylam, omg_;   // lambda block: iterate and weights in registers ...
   double* const SCRK = in.scratch + 6 * P.K + 8 * P.N + 2 * P.K;
   const ScrK<NT> dla{SCRK}, dya{SCRK + LMPC_MAX_SS_PTS}, dlf{SCRK + 2 * LMPC_MAX_SS_PTS}, dyf{SCRK + 3 * LMPC_MAX_SS_PTS},
@@ -467,7 +479,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
                          LMPC_RED_MAX, LMPC_RED_MAX, LMPC_RED_MAX, LMPC_RED_MAX, LMPC_RED_MAX};
     group_reduce<NW, 12>(r, ops, RED);
     R0 = r[0](0);
-    m_total = (int)(r[1](0) + 0.5) + (soft ? 1 : 0) + K;
+    m_total = (int)(r[1](0) + 0.5) + ((soft && !LMPC_FREE_THETA) ? 1 : 0) + K;
     for (int q = 0; q < 10; q++) chs_[q] = 1.0 / r[2 + q](0);
   }
   if (soft) R0 = fmax(R0, 2.0 * P.qb * th);
@@ -513,7 +525,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         }
       GLANES_END(NW)
       th_save = th; yth_save = yth;
-      pact_th = (soft && yth > th) ? 1 : 0;
+      pact_th = (!LMPC_FREE_THETA && soft && yth > th) ? 1 : 0;
       if (soft && !pact_th) yth = 0.0;
       classified = 1; polish_tries++; prev_changed = 0.0;
     }
@@ -586,11 +598,14 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       }
       double Dthth = rs[0](0), cth = rs[1](0);
       if (!pass) {
-        mu = (rs[2](0) + (soft ? th * yth : 0.0)) * inv_m;
+        mu = (rs[2](0) + ((soft && !LMPC_FREE_THETA) ? th * yth : 0.0)) * inv_m;
         rpn = rmx(0);
         rnu = learn ? rs[4](0) - 1.0 : 0.0;
         if (learn) for (int a = 0; a < 6; a++) sig[a] = (a < nh) ? X[P.hidx[a] * d + N - 1] - in.cen[P.hidx[a]] - rs[5 + a](0) : 0.0;
-        if (!polishing && mu < tol_mu && rpn < tol_mu && rho_d * R0 < tol_mu && fabs(rnu) < tol_mu) {
+        // (second alternative: the floor of double precision -- below mu = 1e-13 the products s y are rounding noise and the
+        // primal residual cannot follow a tolerance tighter than its own 1e-13: a caller's tol < 1e-12 ends here)
+        if (!polishing && ((mu < tol_mu && rpn < tol_mu && rho_d * R0 < tol_mu && fabs(rnu) < tol_mu) ||
+                           (mu < 1e-13 && rpn < 1e-9 && rho_d * R0 < 1e-9 && fabs(rnu) < 1e-9))) {
           // complementarity floor reached: polish from here (restart the trip so that the rows are re-assembled)
           polishing = 1; classified = 0; restart = true; break;
         }
@@ -609,7 +624,8 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
           if (pact_th) { Dthth += LMPC_PRHO; cth += -yth + LMPC_PRHO * th; }
         } else {
           if (pass) corr_th = csc * dtha * dytha;
-          { const double ith = lmpc_rcp(th); Dthth += 2.0 * P.qb + yth * ith; cth += 2.0 * P.qb * th - (smu - corr_th) * ith; }
+          if (LMPC_FREE_THETA) { Dthth += 2.0 * P.qb; cth += 2.0 * P.qb * th; }
+          else { const double ith = lmpc_rcp(th); Dthth += 2.0 * P.qb + yth * ith; cth += 2.0 * P.qb * th - (smu - corr_th) * ith; }
         }
       }
 
@@ -1168,7 +1184,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       }
       double dthc = dthp, dythc = 0.0;
       if (polishing) { dtha = dthc; break; }   // the polish takes the full step below, no ratio test
-      if (soft) { const double ith = lmpc_rcp(th); const double tt = (smu - corr_th) * ith; dythc = tt - yth - (yth * ith) * dthc; }
+      if (soft && !LMPC_FREE_THETA) { const double ith = lmpc_rcp(th); const double tt = (smu - corr_th) * ith; dythc = tt - yth - (yth * ith) * dthc; }
       if (pass) { dth = dthc; dyth = dythc; } else { dtha = dthc; dytha = dythc; }
 
       // ---------- row directions, step length
@@ -1208,7 +1224,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
         group_reduce<NW, 2>(ra, ops, RED);
       }
       double rmax = ra[0](0), cross = ra[1](0);
-      if (soft) {
+      if (soft && !LMPC_FREE_THETA) {
         rmax = fmax(rmax, fmax(-dthc / th, -dythc / yth));
         if (!pass) cross += dthc * dythc;
       }
@@ -1251,7 +1267,7 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       if (soft) {
         th += dtha;
         if (pact_th) { dymax_u = fabs(LMPC_PRHO * th) / (1.0 + fabs(yth)); yth += LMPC_PRHO * (-th); if (yth < -dtol) { pact_th = 0; yth = 0.0; changed += 1.0; } }
-        else if (th < -ftol) { pact_th = 1; changed += 1.0; }
+        else if (!LMPC_FREE_THETA && th < -ftol) { pact_th = 1; changed += 1.0; }
       }
       LaneVar<double, NT> rc2[3];
       GLANES_BEGIN(NT)
@@ -1298,7 +1314,9 @@ LMPC_DEV void lmpc_qp_solve(const LmpcQpParams& P, const LmpcQpIn& in, double* s
       // time of a one-wave batch: 6 wasted rounds = 3.3 iteration-equivalents)
       const bool diverging = polishing >= 2 && changed > 8.5 && changed > 2.0 * prev_changed;
       prev_changed = changed;
-      if (!diverging && (changed > 0.5 || dymax > LMPC_PDY) && polishing < LMPC_PMAX) { polishing++; continue; }
+      // stop after the FIRST round only when it moved the multipliers by less than LMPC_PDY (its feasibility error is that
+      // change / rho); from the second round on the bar is LMPC_PDY2, the change a second augmented-Lagrangian step leaves
+      if (!diverging && (changed > 0.5 || dymax > (polishing >= 2 ? LMPC_PDY2 : LMPC_PDY)) && polishing < LMPC_PMAX) { polishing++; continue; }
       if (!diverging && changed < 0.5 && rc2[1](0) < 0.5) { status = LMPC_SOLVED; it++; break; }
       polish_failed = true;
     }
