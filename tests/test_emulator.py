@@ -409,3 +409,23 @@ def test_staged_linearisation_equals_the_plain_form_bit_for_bit(emu, pkg, integr
             got = out[::stride][:54]
             assert np.array_equal(got[:36], A) and np.array_equal(got[36:48], B) and np.array_equal(got[48:], g)
         assert np.array_equal(A.reshape(6, 6, order="F")[:, 0], np.eye(6)[0])
+
+
+def test_emulated_qp_kernel_tolerance_below_the_floor_of_double_precision(emu, pkg):
+    """A caller's tol of 1e-15 cannot be met by the primal residual (its own rounding floor is 1e-13): the interior point
+    hands over to the polish once the complementarity is below 1e-13 instead of iterating on noise until max_iter (found
+    when the boundary slack became a free variable: the last iterations then converge quadratically, mu 6e-10 -> 5e-16 ->
+    3e-27, and ran past every test)."""
+    od, veh, cfg, track, mode = make_oracle(pkg, "barc_lmpc", tol=1e-11)
+    batch = pkg.workload.make_batch(veh, cfg, 6, 0x7071, track, pkg.workload.load_laps(), mode=mode)
+    worst, its = 0.0, []
+    for b in range(6):
+        inp = pkg.workload.instance(batch, b)
+        d = od.step(inp, impl="dense")
+        if not (d["status"] == 0 and d["polished"] == 1 and d["kkt"] < 1e-9):
+            continue
+        k = _emu_solve(emu, pkg, od, veh, dict(cfg, tol=1e-15), inp)
+        assert k["status"] == 0, (b, k["status"], k["iters"])
+        worst = max(worst, relerr(k["X"], d["X"]), relerr(k["U"], d["U"]))
+        its.append(k["iters"])
+    assert len(its) >= 4 and max(its) <= 16 and worst < 1e-9, (its, worst)
